@@ -1,0 +1,160 @@
+/*
+ * turdb_cuda.h — C ABI of libturdb_cuda.so: the B200 (sm_100a) implementation of TurDB's HNSW
+ * vector-search hot path.  This is the drop-in boundary: exactly what a `turdb-cuda` Rust crate
+ * binds with `extern "C"`.  Plain pointers and sizes only; no exceptions or
+ * aborts cross it; every entry returns an int32 status (0 = ok) and leaves a message readable
+ * through turdb_cuda_last_error() (thread-local).
+ *
+ * Citations are into kahflane/TurDB (/root/reference).  The reference has no plugin/FFI interface
+ * for this path; each entry names the Rust call site it stands behind.
+ *
+ * Conventions
+ *   - node id  = dense u32, the i-th node allocated by allocate_node (src/hnsw/mod.rs:883-904);
+ *                the host keeps the NodeId(page_no, slot) <-> dense id map.
+ *   - metric   = DistanceFunction discriminant (src/hnsw/mod.rs:129-137): 0 L2, 1 Cosine, 2 IP.
+ *                Distances follow select_squared_distance_fn (src/hnsw/distance.rs:438-444):
+ *                L2 -> squared L2, Cosine -> 1 - cos (1.0 on a zero norm), IP -> -dot, computed in
+ *                the lane order of the reference's AVX2 kernels (distance.rs:105-161,210-285) so
+ *                results are bit-identical to the reference on an AVX2+FMA host.
+ *   - "host"   entries take host pointers and do their own H2D/D2H copies;
+ *     "_device" entries take device pointers on the index's device and enqueue on `stream`
+ *                (a cudaStream_t passed as void*; NULL = the legacy default stream).
+ */
+#ifndef TURDB_CUDA_H
+#define TURDB_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TURDB_CUDA_ABI_VERSION 1u
+
+#define TURDB_MAX_L0_NEIGHBORS 32u    /* src/hnsw/mod.rs:126 */
+#define TURDB_MAX_LEVEL_NEIGHBORS 16u /* src/hnsw/mod.rs:127 */
+#define TURDB_INVALID_NODE 0xFFFFFFFFu /* NodeId::none(), src/hnsw/mod.rs:161-166 */
+#define TURDB_INVALID_ROW 0xFFFFFFFFFFFFFFFFull
+
+enum turdb_metric { TURDB_METRIC_L2 = 0, TURDB_METRIC_COSINE = 1, TURDB_METRIC_IP = 2 };
+
+enum turdb_status {
+  TURDB_OK = 0,
+  TURDB_ERR_INVALID_ARGUMENT = 1,
+  TURDB_ERR_DIMENSION_MISMATCH = 2, /* "query dimension {} does not match index dimension {}", mod.rs:1099-1104 */
+  TURDB_ERR_CUDA = 3,
+  TURDB_ERR_OUT_OF_MEMORY = 4,
+  TURDB_ERR_UNSUPPORTED = 5,
+  TURDB_ERR_NO_DEVICE = 6
+};
+
+typedef struct turdb_cuda_index turdb_cuda_index; /* opaque; owns the device arena + adjacency */
+
+/*
+ * The flattened graph the host uploads once.  Replaces the per-evaluation read_node() /
+ * get_vector() closures of PersistentHnswIndex::search (src/hnsw/mod.rs:1111-1127): node records
+ * (HnswNode, mod.rs:228-234) become fixed-stride adjacency rows, vectors a contiguous arena.
+ */
+typedef struct {
+  uint32_t dim;            /* HnswIndex::dimensions, mod.rs:615 */
+  uint32_t max_level;      /* HnswIndex::max_level, mod.rs:624 */
+  uint64_t n;              /* nodes (node_count, mod.rs:625); may be 0 (empty index) */
+  uint32_t entry;          /* dense id of HnswIndex::entry_point, TURDB_INVALID_NODE if None */
+  uint32_t reserved;
+  const float* vectors;    /* [n][dim] row-major; row i = vector of node i */
+  const uint64_t* row_ids; /* [n]  HnswNode::row_id */
+  const uint8_t* levels;   /* [n]  HnswNode::max_level */
+  const uint32_t* l0_adj;  /* [n][32] level-0 neighbours in stored order (l0_neighbors) */
+  const uint8_t* l0_cnt;   /* [n]  l0_count */
+  const uint32_t* up_base; /* [n]  first upper slot of node i (slot of level l = up_base[i]+l-1), or INVALID */
+  const uint32_t* up_adj;  /* [n_up_slots][16] higher_levels[l-1] in stored order */
+  const uint8_t* up_cnt;   /* [n_up_slots] */
+  uint64_t n_up_slots;     /* sum over nodes of levels[i] */
+} turdb_cuda_graph;
+
+/* per-query traversal counters; feed the bytes-gathered roofline */
+typedef struct {
+  uint32_t n_dist;       /* all distance evaluations */
+  uint32_t n_dist_upper; /* entry + greedy upper-level evaluations */
+  uint32_t n_expanded;   /* level-0 adjacency rows read */
+  uint32_t n_upper_hops; /* upper-level adjacency rows read */
+} turdb_cuda_search_stats;
+
+/* ---- library ------------------------------------------------------------------------------ */
+uint32_t turdb_cuda_abi_version(void);
+const char* turdb_cuda_last_error(void);
+int32_t turdb_cuda_device_count(int32_t* out_count);
+
+/* ---- index lifetime: replaces PersistentHnswIndex::open's in-memory state (mod.rs:810-859) --- */
+int32_t turdb_cuda_index_create(const turdb_cuda_graph* graph, int32_t device, turdb_cuda_index** out);
+int32_t turdb_cuda_index_destroy(turdb_cuda_index* idx);
+int32_t turdb_cuda_index_info(const turdb_cuda_index* idx, uint64_t* n, uint32_t* dim,
+                              uint32_t* max_level, uint32_t* entry, uint64_t* device_bytes);
+
+/*
+ * ---- search: PersistentHnswIndex::search (mod.rs:1092-1174) for a batch of queries ----------
+ * For each query: greedy descent over levels max_level..1 (search.rs:283-309), level-0 beam search
+ * with ef (search.rs:311-350), truncate to k (search.rs:245-252).  `ef` plays
+ * HnswSearchContext::ef_search (search.rs:202-225).  visible == NULL -> search(); otherwise
+ * search_filtered (mod.rs:1176-1273, search.rs:352-398) with one bit per NODE id
+ * (bit i of word i/64 = is_visible(row_id of node i)).
+ *
+ * Outputs are [nq][k]; out_counts[q] results are valid (<= min(k, ef)), the rest are filled with
+ * TURDB_INVALID_ROW / TURDB_INVALID_NODE / +inf.  Results ascend by distance.  out_node_ids,
+ * out_stats may be NULL.  Empty index -> counts 0, status OK (mod.rs:1106-1109).
+ * query_dim != index dim -> TURDB_ERR_DIMENSION_MISMATCH.  ef == 0 is rejected with
+ * TURDB_ERR_INVALID_ARGUMENT (the reference would traverse the whole component and return
+ * nothing; documented deviation).  k == 0 returns counts 0.
+ */
+int32_t turdb_cuda_search_batch(turdb_cuda_index* idx, const float* queries, uint32_t query_dim,
+                                uint32_t nq, uint32_t k, uint32_t ef, uint8_t metric,
+                                const uint64_t* visible, uint64_t* out_row_ids,
+                                uint32_t* out_node_ids, float* out_dist, uint32_t* out_counts,
+                                turdb_cuda_search_stats* out_stats);
+
+int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const float* d_queries,
+                                       uint32_t query_dim, uint32_t nq, uint32_t k, uint32_t ef,
+                                       uint8_t metric, const uint64_t* d_visible,
+                                       uint64_t* d_out_row_ids, uint32_t* d_out_node_ids,
+                                       float* d_out_dist, uint32_t* d_out_counts,
+                                       turdb_cuda_search_stats* d_out_stats, void* stream);
+
+/* Tunables of the traversal kernel (0 = automatic).  warps_per_cta queries are resident per CTA,
+ * staging_slots neighbour vectors are in flight per query, hash_bits sizes the visited table. */
+int32_t turdb_cuda_index_set_tuning(turdb_cuda_index* idx, uint32_t warps_per_cta,
+                                    uint32_t staging_slots, uint32_t hash_bits);
+
+/*
+ * ---- exact path: the SQL `ORDER BY vec <op> q LIMIT k` scan (TopKExec, ---------------------
+ * src/sql/executor.rs:2239-2392 with the distance of :169-212) over the index's arena.
+ * Tensor-core dot-product pass keeping rerank_factor*k candidates per query, then an FP32 rerank in
+ * the reference's lane order.  Distances follow the HNSW metric contract above (squared L2 /
+ * 1-cos / -dot), NOT the SQL sqrt form; the host operator applies sqrt when it projects the value.
+ */
+int32_t turdb_cuda_bruteforce_topk(turdb_cuda_index* idx, const float* queries, uint32_t query_dim,
+                                   uint32_t nq, uint32_t k, uint8_t metric, uint32_t rerank_factor,
+                                   uint64_t* out_row_ids, uint32_t* out_node_ids, float* out_dist,
+                                   uint32_t* out_counts);
+
+int32_t turdb_cuda_bruteforce_topk_device(turdb_cuda_index* idx, const float* d_queries,
+                                          uint32_t query_dim, uint32_t nq, uint32_t k,
+                                          uint8_t metric, uint32_t rerank_factor,
+                                          uint64_t* d_out_row_ids, uint32_t* d_out_node_ids,
+                                          float* d_out_dist, uint32_t* d_out_counts, void* stream);
+
+/*
+ * ---- multi-GPU: merge of per-shard top-k after the all-gather (one sub-index per GPU) --------
+ * gathered_* are [n_shards][nq][k] device arrays (the NCCL all-gather output); ties order by
+ * (distance, row_id).  Output [nq][k].
+ */
+int32_t turdb_cuda_merge_topk_device(int32_t device, const uint64_t* d_gathered_row_ids,
+                                     const float* d_gathered_dist, const uint32_t* d_gathered_counts,
+                                     uint32_t n_shards, uint32_t nq, uint32_t k,
+                                     uint64_t* d_out_row_ids, float* d_out_dist,
+                                     uint32_t* d_out_counts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TURDB_CUDA_H */

@@ -147,9 +147,12 @@ class OracleGraph:
         return cls(h, dim)
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().tdo_graph_free(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None) and _lib is not None:
+                _lib.tdo_graph_free(self._h)
+                self._h = None
+        except Exception:
+            pass
 
     def insert(self, row_id, vec, random_value):
         vec = np.ascontiguousarray(vec, dtype=np.float32)

@@ -1,0 +1,128 @@
+// common.cuh — shared device helpers for libturdb_cuda (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace turdb {
+
+constexpr uint32_t kInvalid = 0xFFFFFFFFu;
+constexpr uint32_t kExpandedBit = 0x80000000u;  // bit 31 of a list id: adjacency already read
+constexpr uint32_t kFullMask = 0xFFFFFFFFu;
+constexpr uint32_t kL0 = 32;  // MAX_L0_NEIGHBORS, src/hnsw/mod.rs:126
+constexpr uint32_t kUp = 16;  // MAX_LEVEL_NEIGHBORS, src/hnsw/mod.rs:127
+
+enum Metric : int { kL2 = 0, kCosine = 1, kIP = 2 };
+
+// Device view of the uploaded index.
+struct DeviceIndex {
+  const float* arena;       // [n][ds] row stride ds = round_up(dim, 4) floats, 16 B aligned rows
+  const float* norm2;       // [n] dot(b, b) in the reference's AVX2 lane order (cosine only)
+  const uint32_t* l0_adj;   // [n][32], INVALID padded
+  const uint32_t* up_base;  // [n]
+  const uint32_t* up_adj;   // [slots][16], INVALID padded
+  const uint64_t* row_ids;  // [n]
+  const uint8_t* levels;    // [n]
+  uint64_t n;
+  uint32_t dim;
+  uint32_t ds;
+  uint32_t entry;
+  uint32_t max_level;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier + TMA bulk copy (cp.async.bulk; SASS: UBLKCP) ---------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// global -> shared bulk copy, completion counted in bytes on `bar`.  16 B aligned, size % 16 == 0.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
+// ---- the reference's AVX2 reduction order, one QUAD (4 lanes) per vector ---------------------
+// Lane p of a quad owns AVX lanes 2p and 2p+1 (distance.rs:105-129): it walks elements 8t+2p,
+// 8t+2p+1 with one fused multiply-add each, then the quad reproduces horizontal_sum_avx2
+// (distance.rs:150-161): (lo128 + hi128) = xor-2 exchange, movehl add = xor-1 exchange, x + y.
+__device__ __forceinline__ float quad_hsum(float2 acc) {
+  acc.x = __fadd_rn(acc.x, __shfl_xor_sync(kFullMask, acc.x, 2));
+  acc.y = __fadd_rn(acc.y, __shfl_xor_sync(kFullMask, acc.y, 2));
+  acc.x = __fadd_rn(acc.x, __shfl_xor_sync(kFullMask, acc.x, 1));
+  acc.y = __fadd_rn(acc.y, __shfl_xor_sync(kFullMask, acc.y, 1));
+  return __fadd_rn(acc.x, acc.y);
+}
+
+// a, b: 8 B aligned float pointers (shared or global); p = lane & 3.  Returns squared L2.
+__device__ __forceinline__ float quad_l2sq(const float* a, const float* b, uint32_t dim, uint32_t p) {
+  const float2* av = reinterpret_cast<const float2*>(a) + p;
+  const float2* bv = reinterpret_cast<const float2*>(b) + p;
+  float2 acc = make_float2(0.f, 0.f);
+  const uint32_t steps = dim >> 3;
+#pragma unroll 4
+  for (uint32_t t = 0; t < steps; ++t) {
+    float2 x = av[4 * t], y = bv[4 * t];
+    float d0 = __fsub_rn(x.x, y.x), d1 = __fsub_rn(x.y, y.y);
+    acc.x = __fmaf_rn(d0, d0, acc.x);
+    acc.y = __fmaf_rn(d1, d1, acc.y);
+  }
+  float r = quad_hsum(acc);
+  for (uint32_t i = steps << 3; i < dim; ++i) {  // unfused scalar tail, distance.rs:122-126
+    float d = __fsub_rn(a[i], b[i]);
+    r = __fadd_rn(r, __fmul_rn(d, d));
+  }
+  return r;
+}
+
+__device__ __forceinline__ float quad_dot(const float* a, const float* b, uint32_t dim, uint32_t p) {
+  const float2* av = reinterpret_cast<const float2*>(a) + p;
+  const float2* bv = reinterpret_cast<const float2*>(b) + p;
+  float2 acc = make_float2(0.f, 0.f);
+  const uint32_t steps = dim >> 3;
+#pragma unroll 4
+  for (uint32_t t = 0; t < steps; ++t) {
+    float2 x = av[4 * t], y = bv[4 * t];
+    acc.x = __fmaf_rn(x.x, y.x, acc.x);
+    acc.y = __fmaf_rn(x.y, y.y, acc.y);
+  }
+  float r = quad_hsum(acc);
+  for (uint32_t i = steps << 3; i < dim; ++i) r = __fadd_rn(r, __fmul_rn(a[i], b[i]));
+  return r;
+}
+
+// cosine_avx2's epilogue, distance.rs:279-284
+__device__ __forceinline__ float cosine_finish(float dot, float na, float nb) {
+  float np = __fsqrt_rn(__fmul_rn(na, nb));
+  if (np == 0.0f) return 1.0f;
+  return __fsub_rn(1.0f, __fdiv_rn(dot, np));
+}
+
+}  // namespace turdb

@@ -1,0 +1,527 @@
+// turdb_cuda.cu — C ABI of libturdb_cuda.so (include/turdb_cuda.h).  sm_100a only.
+#include "../../include/turdb_cuda.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+
+#include "common.cuh"
+#include "exact_search.cuh"
+#include "hnsw_search.cuh"
+
+using namespace turdb;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int32_t fail(int32_t code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      int32_t _c = (_e == cudaErrorMemoryAllocation) ? TURDB_ERR_OUT_OF_MEMORY : TURDB_ERR_CUDA; \
+      return fail(_c, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    }                                                                                        \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// index
+// ------------------------------------------------------------------------------------------
+struct turdb_cuda_index {
+  int device = 0;
+  int num_sms = 0;
+  int max_smem_optin = 0;
+  DeviceIndex ix{};
+  float* d_arena = nullptr;
+  float* d_norm2 = nullptr;
+  uint32_t* d_l0_adj = nullptr;
+  uint32_t* d_up_base = nullptr;
+  uint32_t* d_up_adj = nullptr;
+  uint64_t* d_row_ids = nullptr;
+  uint8_t* d_levels = nullptr;
+  __nv_bfloat16* d_arena_bf16 = nullptr;  // exact path operand, built lazily
+  uint64_t device_bytes = 0;
+  uint32_t tune_warps = 0, tune_slots = 0, tune_hash_bits = 0;
+  std::mutex mu;
+};
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// adjacency rows arrive with counts; entries >= count become INVALID and ids are range-checked
+__global__ void sanitize_adj_kernel(uint32_t* adj, const uint8_t* cnt, uint64_t rows, uint32_t width,
+                                    uint64_t n, uint32_t* bad) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * width) return;
+  uint64_t r = i / width;
+  uint32_t c = i % width;
+  uint32_t limit = min((uint32_t)cnt[r], width);
+  if (c >= limit) {
+    adj[i] = kInvalid;
+  } else if (adj[i] >= n) {
+    atomicAdd(bad, 1u);
+    adj[i] = kInvalid;
+  }
+}
+
+// dot(b, b) per arena row in the reference's AVX2 lane order (cosine_avx2's norm_b chain)
+__global__ void norm2_kernel(const float* arena, uint32_t dim, uint32_t ds, uint64_t n, float* out) {
+  uint64_t quad = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  uint64_t row = quad < n ? quad : n - 1;  // keep the quad shuffles converged
+  const float* b = arena + row * ds;
+  float r = quad_dot(b, b, dim, threadIdx.x & 3);
+  if (quad < n && (threadIdx.x & 3) == 0) out[quad] = r;
+}
+
+extern "C" {
+
+uint32_t turdb_cuda_abi_version(void) { return TURDB_CUDA_ABI_VERSION; }
+
+const char* turdb_cuda_last_error(void) { return g_last_error.c_str(); }
+
+int32_t turdb_cuda_device_count(int32_t* out_count) {
+  if (!out_count) return fail(TURDB_ERR_INVALID_ARGUMENT, "out_count is null");
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) {
+    *out_count = 0;
+    return fail(TURDB_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  }
+  *out_count = c;
+  return TURDB_OK;
+}
+
+int32_t turdb_cuda_index_destroy(turdb_cuda_index* idx) {
+  if (!idx) return TURDB_OK;
+  {
+    DeviceGuard g(idx->device);
+    cudaFree(idx->d_arena);
+    cudaFree(idx->d_norm2);
+    cudaFree(idx->d_l0_adj);
+    cudaFree(idx->d_up_base);
+    cudaFree(idx->d_up_adj);
+    cudaFree(idx->d_row_ids);
+    cudaFree(idx->d_levels);
+    cudaFree(idx->d_arena_bf16);
+  }
+  delete idx;
+  return TURDB_OK;
+}
+
+int32_t turdb_cuda_index_create(const turdb_cuda_graph* g, int32_t device, turdb_cuda_index** out) {
+  if (!g || !out) return fail(TURDB_ERR_INVALID_ARGUMENT, "graph/out is null");
+  *out = nullptr;
+  if (g->dim == 0 || g->dim > 65535) return fail(TURDB_ERR_INVALID_ARGUMENT, "dim %u out of range", g->dim);
+  if (g->n >= 0x7FFFFFFFull) return fail(TURDB_ERR_UNSUPPORTED, "n %llu exceeds 2^31-2 nodes per index", (unsigned long long)g->n);
+  if (g->n > 0) {
+    if (!g->vectors || !g->row_ids || !g->levels || !g->l0_adj || !g->l0_cnt || !g->up_base)
+      return fail(TURDB_ERR_INVALID_ARGUMENT, "graph array pointer is null");
+    if (g->n_up_slots && (!g->up_adj || !g->up_cnt))
+      return fail(TURDB_ERR_INVALID_ARGUMENT, "upper-level arrays are null");
+    if (g->entry != TURDB_INVALID_NODE && g->entry >= g->n)
+      return fail(TURDB_ERR_INVALID_ARGUMENT, "entry %u >= n", g->entry);
+    if (g->entry != TURDB_INVALID_NODE && g->levels[g->entry] < g->max_level)
+      return fail(TURDB_ERR_INVALID_ARGUMENT, "entry level %u < max_level %u", g->levels[g->entry], g->max_level);
+    for (uint64_t i = 0; i < g->n; ++i) {
+      if (g->levels[i] > 0) {
+        if (g->up_base[i] == TURDB_INVALID_NODE || (uint64_t)g->up_base[i] + g->levels[i] > g->n_up_slots)
+          return fail(TURDB_ERR_INVALID_ARGUMENT, "node %llu: upper slots out of range", (unsigned long long)i);
+      }
+    }
+  }
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    return fail(TURDB_ERR_NO_DEVICE, "no CUDA device available (libturdb_cuda has no CPU fallback)");
+  if (device < 0 || device >= count) return fail(TURDB_ERR_INVALID_ARGUMENT, "device %d out of range", device);
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(TURDB_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+
+  turdb_cuda_index* idx = new (std::nothrow) turdb_cuda_index();
+  if (!idx) return fail(TURDB_ERR_OUT_OF_MEMORY, "host allocation failed");
+  idx->device = device;
+  cudaDeviceProp prop{};
+  cudaGetDeviceProperties(&prop, device);
+  idx->num_sms = prop.multiProcessorCount;
+  idx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  if (prop.major < 10) {
+    delete idx;
+    return fail(TURDB_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  }
+
+  const uint64_t n = g->n;
+  const uint32_t dim = g->dim, ds = (dim + 3) & ~3u;
+  idx->ix.n = n;
+  idx->ix.dim = dim;
+  idx->ix.ds = ds;
+  idx->ix.entry = n ? g->entry : kInvalid;
+  idx->ix.max_level = g->max_level;
+
+#define IDX_TRY(expr)                                                          \
+  do {                                                                         \
+    cudaError_t _e = (expr);                                                   \
+    if (_e != cudaSuccess) {                                                   \
+      int32_t _c = (_e == cudaErrorMemoryAllocation) ? TURDB_ERR_OUT_OF_MEMORY : TURDB_ERR_CUDA; \
+      fail(_c, "%s failed: %s", #expr, cudaGetErrorString(_e));                \
+      turdb_cuda_index_destroy(idx);                                           \
+      return _c;                                                               \
+    }                                                                          \
+  } while (0)
+
+  if (n > 0) {
+    const size_t arena_bytes = (size_t)n * ds * 4;
+    IDX_TRY(cudaMalloc(&idx->d_arena, arena_bytes));
+    if (ds == dim) {
+      IDX_TRY(cudaMemcpy(idx->d_arena, g->vectors, arena_bytes, cudaMemcpyHostToDevice));
+    } else {
+      IDX_TRY(cudaMemset(idx->d_arena, 0, arena_bytes));
+      IDX_TRY(cudaMemcpy2D(idx->d_arena, (size_t)ds * 4, g->vectors, (size_t)dim * 4, (size_t)dim * 4, n,
+                           cudaMemcpyHostToDevice));
+    }
+    IDX_TRY(cudaMalloc(&idx->d_norm2, n * 4));
+    IDX_TRY(cudaMalloc(&idx->d_l0_adj, n * kL0 * 4));
+    IDX_TRY(cudaMemcpy(idx->d_l0_adj, g->l0_adj, n * kL0 * 4, cudaMemcpyHostToDevice));
+    IDX_TRY(cudaMalloc(&idx->d_up_base, n * 4));
+    IDX_TRY(cudaMemcpy(idx->d_up_base, g->up_base, n * 4, cudaMemcpyHostToDevice));
+    IDX_TRY(cudaMalloc(&idx->d_row_ids, n * 8));
+    IDX_TRY(cudaMemcpy(idx->d_row_ids, g->row_ids, n * 8, cudaMemcpyHostToDevice));
+    IDX_TRY(cudaMalloc(&idx->d_levels, n));
+    IDX_TRY(cudaMemcpy(idx->d_levels, g->levels, n, cudaMemcpyHostToDevice));
+    const uint64_t slots = g->n_up_slots;
+    IDX_TRY(cudaMalloc(&idx->d_up_adj, std::max<uint64_t>(slots, 1) * kUp * 4));
+    if (slots) IDX_TRY(cudaMemcpy(idx->d_up_adj, g->up_adj, slots * kUp * 4, cudaMemcpyHostToDevice));
+    idx->device_bytes = arena_bytes + n * 4 + n * kL0 * 4 + n * 4 + n * 8 + n + slots * kUp * 4;
+
+    // counts -> INVALID padding, id range check
+    uint8_t* d_cnt = nullptr;
+    uint32_t* d_bad = nullptr;
+    IDX_TRY(cudaMalloc(&d_cnt, std::max<uint64_t>(n, slots)));
+    IDX_TRY(cudaMalloc(&d_bad, 4));
+    IDX_TRY(cudaMemset(d_bad, 0, 4));
+    IDX_TRY(cudaMemcpy(d_cnt, g->l0_cnt, n, cudaMemcpyHostToDevice));
+    {
+      uint64_t total = n * kL0;
+      sanitize_adj_kernel<<<(unsigned)((total + 255) / 256), 256>>>(idx->d_l0_adj, d_cnt, n, kL0, n, d_bad);
+    }
+    if (slots) {
+      IDX_TRY(cudaMemcpy(d_cnt, g->up_cnt, slots, cudaMemcpyHostToDevice));
+      uint64_t total = slots * kUp;
+      sanitize_adj_kernel<<<(unsigned)((total + 255) / 256), 256>>>(idx->d_up_adj, d_cnt, slots, kUp, n, d_bad);
+    }
+    norm2_kernel<<<(unsigned)((n * 4 + 255) / 256), 256>>>(idx->d_arena, dim, ds, n, idx->d_norm2);
+    uint32_t bad = 0;
+    IDX_TRY(cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost));
+    cudaFree(d_cnt);
+    cudaFree(d_bad);
+    IDX_TRY(cudaGetLastError());
+    if (bad) {
+      turdb_cuda_index_destroy(idx);
+      return fail(TURDB_ERR_INVALID_ARGUMENT, "%u adjacency entries reference nodes >= n", bad);
+    }
+  }
+#undef IDX_TRY
+  idx->ix.arena = idx->d_arena;
+  idx->ix.norm2 = idx->d_norm2;
+  idx->ix.l0_adj = idx->d_l0_adj;
+  idx->ix.up_base = idx->d_up_base;
+  idx->ix.up_adj = idx->d_up_adj;
+  idx->ix.row_ids = idx->d_row_ids;
+  idx->ix.levels = idx->d_levels;
+  *out = idx;
+  return TURDB_OK;
+}
+
+int32_t turdb_cuda_index_info(const turdb_cuda_index* idx, uint64_t* n, uint32_t* dim, uint32_t* max_level,
+                              uint32_t* entry, uint64_t* device_bytes) {
+  if (!idx) return fail(TURDB_ERR_INVALID_ARGUMENT, "idx is null");
+  if (n) *n = idx->ix.n;
+  if (dim) *dim = idx->ix.dim;
+  if (max_level) *max_level = idx->ix.max_level;
+  if (entry) *entry = idx->ix.entry;
+  if (device_bytes) *device_bytes = idx->device_bytes;
+  return TURDB_OK;
+}
+
+int32_t turdb_cuda_index_set_tuning(turdb_cuda_index* idx, uint32_t warps_per_cta, uint32_t staging_slots,
+                                    uint32_t hash_bits) {
+  if (!idx) return fail(TURDB_ERR_INVALID_ARGUMENT, "idx is null");
+  if (warps_per_cta > 8) return fail(TURDB_ERR_INVALID_ARGUMENT, "warps_per_cta must be <= 8");
+  if (staging_slots > 32 || (staging_slots & 7)) return fail(TURDB_ERR_INVALID_ARGUMENT, "staging_slots must be 0, 8, 16, 24 or 32");
+  if (hash_bits != 0 && (hash_bits < 8 || hash_bits > 15)) return fail(TURDB_ERR_INVALID_ARGUMENT, "hash_bits must be 0 or 8..15");
+  std::lock_guard<std::mutex> lk(idx->mu);
+  idx->tune_warps = warps_per_cta;
+  idx->tune_slots = staging_slots;
+  idx->tune_hash_bits = hash_bits;
+  return TURDB_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// traversal launch
+// ------------------------------------------------------------------------------------------
+static uint32_t ceil_log2(uint32_t v) {
+  uint32_t b = 0;
+  while ((1u << b) < v) ++b;
+  return b;
+}
+
+static WarpLayout make_layout(uint32_t ds, uint32_t ef, uint32_t hash_bits, uint32_t n_slots, bool global_visited) {
+  WarpLayout L{};
+  L.vec_bytes = ds * 4;
+  const uint32_t pad_words = (8 + 32 - (ds & 31)) & 31;
+  L.stride = (ds + pad_words) * 4;
+  L.hash_bits = hash_bits;
+  L.n_slots = n_slots;
+  uint32_t off = 0;
+  L.off_bar = off;   off += 64;
+  L.off_q = off;     off += (ds * 4 + 15) & ~15u;
+  L.off_list = off;  off += ef * 16;
+  L.off_tmp = off;   off += 256;
+  L.off_hash = off;  off += global_visited ? 0 : (4u << hash_bits);
+  off = (off + 127) & ~127u;
+  L.off_stage = off; off += n_slots * L.stride;
+  L.warp_bytes = (off + 127) & ~127u;
+  return L;
+}
+
+template <int METRIC, bool GV>
+static cudaError_t launch_search(const SearchArgs& a, uint32_t warps, int num_sms, uint32_t max_ctas,
+                                 cudaStream_t stream, uint32_t* resident_warps) {
+  auto kern = hnsw_search_kernel<METRIC, GV>;
+  const size_t smem = (size_t)a.lay.warp_bytes * warps;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * warps, smem);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) return cudaErrorInvalidConfiguration;
+  uint32_t grid = (uint32_t)occ * num_sms;
+  if (max_ctas && grid > max_ctas) grid = max_ctas;
+  if (grid < 1) grid = 1;
+  if (resident_warps) *resident_warps = grid * warps;
+  kern<<<grid, 32 * warps, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+template <bool GV>
+static cudaError_t launch_metric(int metric, const SearchArgs& a, uint32_t warps, int num_sms, uint32_t max_ctas,
+                                 cudaStream_t stream, uint32_t* rw) {
+  switch (metric) {
+    case kCosine: return launch_search<kCosine, GV>(a, warps, num_sms, max_ctas, stream, rw);
+    case kIP: return launch_search<kIP, GV>(a, warps, num_sms, max_ctas, stream, rw);
+    default: return launch_search<kL2, GV>(a, warps, num_sms, max_ctas, stream, rw);
+  }
+}
+
+__global__ void fill_empty_results_kernel(uint64_t* rows, uint32_t* nodes, float* dist, uint32_t* counts,
+                                          uint32_t* stats, uint32_t nq, uint32_t k) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (uint64_t)nq * k) {
+    rows[i] = 0xFFFFFFFFFFFFFFFFull;
+    if (nodes) nodes[i] = kInvalid;
+    dist[i] = INFINITY;
+  }
+  if (i < nq) counts[i] = 0;
+  if (stats && i < (uint64_t)nq * 4) stats[i] = 0;
+}
+
+extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const float* d_queries, uint32_t query_dim,
+                                                  uint32_t nq, uint32_t k, uint32_t ef, uint8_t metric,
+                                                  const uint64_t* d_visible, uint64_t* d_out_row_ids,
+                                                  uint32_t* d_out_node_ids, float* d_out_dist,
+                                                  uint32_t* d_out_counts, turdb_cuda_search_stats* d_out_stats,
+                                                  void* stream_) {
+  if (!idx) return fail(TURDB_ERR_INVALID_ARGUMENT, "idx is null");
+  if (query_dim != idx->ix.dim)
+    return fail(TURDB_ERR_DIMENSION_MISMATCH, "query dimension %u does not match index dimension %u", query_dim, idx->ix.dim);
+  if (metric > 2) return fail(TURDB_ERR_INVALID_ARGUMENT, "metric %u unknown", metric);
+  if (ef == 0) return fail(TURDB_ERR_INVALID_ARGUMENT, "ef_search must be >= 1");
+  if (ef > 2048) return fail(TURDB_ERR_UNSUPPORTED, "ef_search %u > 2048", ef);
+  if (nq == 0) return TURDB_OK;
+  if (!d_queries || !d_out_counts || (k && (!d_out_row_ids || !d_out_dist)))
+    return fail(TURDB_ERR_INVALID_ARGUMENT, "null query/output pointer");
+  if (d_visible) return fail(TURDB_ERR_UNSUPPORTED, "search_filtered is not implemented on the device yet");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DeviceGuard guard(idx->device);
+  if (!guard.ok) return fail(TURDB_ERR_CUDA, "cudaSetDevice(%d) failed", idx->device);
+
+  if (idx->ix.n == 0 || idx->ix.entry == kInvalid || k == 0) {  // Ok(vec![]), mod.rs:1106-1109
+    uint64_t total = std::max<uint64_t>((uint64_t)nq * std::max(k, 1u), (uint64_t)nq * 4);
+    fill_empty_results_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+        d_out_row_ids, d_out_node_ids, d_out_dist, d_out_counts, (uint32_t*)d_out_stats, nq, k);
+    CUDA_TRY(cudaGetLastError());
+    return TURDB_OK;
+  }
+
+  uint32_t tw, ts, th;
+  {
+    std::lock_guard<std::mutex> lk(idx->mu);
+    tw = idx->tune_warps;
+    ts = idx->tune_slots;
+    th = idx->tune_hash_bits;
+  }
+  const uint32_t ds = idx->ix.ds;
+  uint32_t hash_bits = th ? th : std::min(15u, std::max(9u, ceil_log2(ef * 64)));
+  uint32_t warps = tw ? tw : 1;
+  uint32_t slots = ts;
+  const uint32_t budget = (uint32_t)idx->max_smem_optin;
+  if (!slots) {  // fit one query's state in ~56 KB (4 resident queries per SM) when possible
+    WarpLayout probe = make_layout(ds, ef, hash_bits, 0, false);
+    uint32_t target = 56 * 1024;
+    uint32_t room = target > probe.warp_bytes ? target - probe.warp_bytes : 0;
+    slots = std::min(32u, std::max(8u, (room / probe.stride) & ~7u));
+  }
+  WarpLayout lay = make_layout(ds, ef, hash_bits, slots, false);
+  while (lay.warp_bytes * warps > budget && warps > 1) --warps;
+  while (lay.warp_bytes > budget && lay.n_slots > 8) lay = make_layout(ds, ef, hash_bits, lay.n_slots - 8, false);
+  while (lay.warp_bytes > budget && hash_bits > 8) lay = make_layout(ds, ef, --hash_bits, lay.n_slots, false);
+  if (lay.warp_bytes > budget)
+    return fail(TURDB_ERR_UNSUPPORTED, "dim %u / ef %u need %u B of shared memory per query (> %u)", idx->ix.dim, ef, lay.warp_bytes, budget);
+
+  uint32_t* d_scratch = nullptr;  // [0] work counter, [1] overflow count, [2] fallback work counter, [4..] overflow list
+  CUDA_TRY(cudaMallocAsync(&d_scratch, (size_t)(4 + nq) * 4, stream));
+  CUDA_TRY(cudaMemsetAsync(d_scratch, 0, 16, stream));
+
+  SearchArgs a{};
+  a.ix = idx->ix;
+  a.lay = lay;
+  a.queries = d_queries;
+  a.nq = nq;
+  a.k = k;
+  a.ef = ef;
+  a.out_row_ids = d_out_row_ids;
+  a.out_node_ids = d_out_node_ids;
+  a.out_dist = d_out_dist;
+  a.out_counts = d_out_counts;
+  a.out_stats = (uint32_t*)d_out_stats;
+  a.work_counter = d_scratch;
+  a.overflow_count = d_scratch + 1;
+  a.overflow_list = d_scratch + 4;
+  a.global_visited = nullptr;
+  a.vis_words = 0;
+  cudaError_t e = launch_metric<false>(metric, a, warps, idx->num_sms, (nq + warps - 1) / warps, stream, nullptr);
+  if (e != cudaSuccess) {
+    cudaFreeAsync(d_scratch, stream);
+    return fail(TURDB_ERR_CUDA, "traversal kernel launch failed: %s", cudaGetErrorString(e));
+  }
+
+  // exact fallback for queries whose shared visited table filled: same kernel, one bit per node in
+  // global memory.  Always enqueued (no host sync); exits immediately when the list is empty.
+  {
+    WarpLayout glay = make_layout(ds, ef, 8, lay.n_slots, true);
+    SearchArgs b = a;
+    b.lay = glay;
+    b.work_counter = d_scratch + 2;
+    b.vis_words = (uint32_t)(((idx->ix.n + 31) / 32 + 3) & ~3ull);
+    const uint32_t fb_ctas = (uint32_t)std::min<uint32_t>((uint32_t)idx->num_sms, nq);
+    uint32_t* d_gv = nullptr;
+    e = cudaMallocAsync(&d_gv, (size_t)fb_ctas * b.vis_words * 4, stream);
+    if (e == cudaSuccess) {
+      b.global_visited = d_gv;
+      e = launch_metric<true>(metric, b, 1, idx->num_sms, fb_ctas, stream, nullptr);
+      cudaFreeAsync(d_gv, stream);
+    }
+    if (e != cudaSuccess) {
+      cudaFreeAsync(d_scratch, stream);
+      return fail(TURDB_ERR_CUDA, "fallback traversal launch failed: %s", cudaGetErrorString(e));
+    }
+  }
+  CUDA_TRY(cudaFreeAsync(d_scratch, stream));
+  return TURDB_OK;
+}
+
+extern "C" int32_t turdb_cuda_search_batch(turdb_cuda_index* idx, const float* queries, uint32_t query_dim, uint32_t nq,
+                                           uint32_t k, uint32_t ef, uint8_t metric, const uint64_t* visible,
+                                           uint64_t* out_row_ids, uint32_t* out_node_ids, float* out_dist,
+                                           uint32_t* out_counts, turdb_cuda_search_stats* out_stats) {
+  if (!idx) return fail(TURDB_ERR_INVALID_ARGUMENT, "idx is null");
+  if (query_dim != idx->ix.dim)
+    return fail(TURDB_ERR_DIMENSION_MISMATCH, "query dimension %u does not match index dimension %u", query_dim, idx->ix.dim);
+  if (nq == 0) return TURDB_OK;
+  if (!queries || !out_counts || (k && (!out_row_ids || !out_dist)))
+    return fail(TURDB_ERR_INVALID_ARGUMENT, "null query/output pointer");
+  DeviceGuard guard(idx->device);
+  if (!guard.ok) return fail(TURDB_ERR_CUDA, "cudaSetDevice(%d) failed", idx->device);
+  cudaStream_t stream;
+  CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  const size_t kk = std::max(k, 1u);
+  const size_t qbytes = (size_t)nq * query_dim * 4;
+  const size_t vis_bytes = visible ? ((idx->ix.n + 63) / 64) * 8 : 0;
+  // one device slab: queries | rows | dist | nodes | counts | stats | visible
+  size_t off_q = 0, off_rows = (qbytes + 255) & ~255ull, off_dist = off_rows + nq * kk * 8,
+         off_nodes = off_dist + nq * kk * 4, off_counts = off_nodes + nq * kk * 4,
+         off_stats = off_counts + ((nq * 4 + 15) & ~15ull), off_vis = off_stats + (size_t)nq * 16,
+         total = off_vis + vis_bytes;
+  uint8_t* slab = nullptr;
+  int32_t rc = TURDB_OK;
+  cudaError_t e = cudaMallocAsync(&slab, total, stream);
+  if (e != cudaSuccess) {
+    cudaStreamDestroy(stream);
+    return fail(TURDB_ERR_OUT_OF_MEMORY, "cudaMallocAsync(%zu) failed: %s", total, cudaGetErrorString(e));
+  }
+  auto cleanup = [&]() {
+    cudaFreeAsync(slab, stream);
+    cudaStreamSynchronize(stream);
+    cudaStreamDestroy(stream);
+  };
+  e = cudaMemcpyAsync(slab + off_q, queries, qbytes, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess && visible)
+    e = cudaMemcpyAsync(slab + off_vis, visible, vis_bytes, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) {
+    cleanup();
+    return fail(TURDB_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+  }
+  rc = turdb_cuda_search_batch_device(idx, (const float*)(slab + off_q), query_dim, nq, k, ef, metric,
+                                      visible ? (const uint64_t*)(slab + off_vis) : nullptr,
+                                      (uint64_t*)(slab + off_rows), (uint32_t*)(slab + off_nodes),
+                                      (float*)(slab + off_dist), (uint32_t*)(slab + off_counts),
+                                      out_stats ? (turdb_cuda_search_stats*)(slab + off_stats) : nullptr, stream);
+  if (rc != TURDB_OK) {
+    cleanup();
+    return rc;
+  }
+  if (k) {
+    e = cudaMemcpyAsync(out_row_ids, slab + off_rows, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_dist, slab + off_dist, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && out_node_ids)
+      e = cudaMemcpyAsync(out_node_ids, slab + off_nodes, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, stream);
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_counts, slab + off_counts, (size_t)nq * 4, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess && out_stats)
+    e = cudaMemcpyAsync(out_stats, slab + off_stats, (size_t)nq * 16, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  cudaFreeAsync(slab, stream);
+  cudaStreamSynchronize(stream);
+  cudaStreamDestroy(stream);
+  if (e != cudaSuccess) return fail(TURDB_ERR_CUDA, "search failed: %s", cudaGetErrorString(e));
+  return TURDB_OK;
+}
+
+// exact path + merge entry points live in exact_search.cuh / below
+#include "exact_abi.inl"
