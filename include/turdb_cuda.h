@@ -126,6 +126,17 @@ int32_t turdb_cuda_index_set_tuning(turdb_cuda_index* idx, uint32_t warps_per_ct
                                     uint32_t staging_slots, uint32_t hash_bits);
 
 /*
+ * ---- measurement: per-launch device times of the traversal kernel --------------------------
+ * profile_begin arms a ring of `capacity` CUDA-event pairs; every later search_batch_device call on
+ * this index brackets its traversal kernel (and the overflow pass) with events on the caller's stream.
+ * profile_read (after the caller synchronised the stream) returns up to `cap` per-launch durations in
+ * ms, oldest first, and disarms.  Used by bench.py for the roofline's kernel time.
+ */
+int32_t turdb_cuda_index_profile_begin(turdb_cuda_index* idx, uint32_t capacity);
+int32_t turdb_cuda_index_profile_read(turdb_cuda_index* idx, float* main_ms, float* overflow_ms,
+                                      uint32_t cap, uint32_t* out_n);
+
+/*
  * ---- exact path: the SQL `ORDER BY vec <op> q LIMIT k` scan (TopKExec, ---------------------
  * src/sql/executor.rs:2239-2392 with the distance of :169-212) over the index's arena.
  * Tensor-core dot-product pass keeping rerank_factor*k candidates per query, then an FP32 rerank in

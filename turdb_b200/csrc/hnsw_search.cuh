@@ -22,7 +22,12 @@ struct WarpLayout {
   uint32_t n_slots;    // staging slots (multiple of 8, <= 32)
   uint32_t stride;     // bytes between staging slots; stride/4 == 8 (mod 32) -> conflict-free quads
   uint32_t vec_bytes;  // ds * 4
-  uint32_t hash_bits;  // shared visited table has 1 << hash_bits u32 slots
+  uint32_t hash_bits;  // shared visited table has 1 << hash_bits slots
+  // compact table (hash16 != 0): 16-bit entries = (displacement+1) << rem_bits | remainder of a
+  // bijective hash of the id, so an entry still identifies exactly one node (exact set, half the bytes)
+  uint32_t hash16;
+  uint32_t rem_bits;   // key_bits - hash_bits
+  uint32_t key_bits;   // ceil(log2(n)), >= hash_bits
 };
 
 struct SearchArgs {
@@ -55,59 +60,85 @@ struct WarpCtx {
 
 // Distances from the query to the m vectors whose ids sit in lanes 0..m-1 (`cid`).
 // Returns d in lane j for id j; +inf in lanes >= m.
+//
+// The m vectors are gathered in chunks of 8 (one quad of lanes per vector).  Chunk c lands in staging
+// group c % G (G = n_slots / 8, one mbarrier per group); the first G chunks are requested up front and
+// group g is re-armed with chunk c + G as soon as chunk c has been reduced, so up to n_slots vectors
+// stay in flight for the whole hop.
 template <int METRIC>
 __device__ __forceinline__ float gather_distances(const DeviceIndex& ix, WarpCtx& w, uint32_t cid,
                                                   uint32_t m) {
+  const uint32_t lane = w.lane, p = lane & 3, sub = lane & 7, my_chunk = lane >> 3;
+  const uint32_t G = w.n_slots >> 3;
+  const uint32_t nchunks = (m + 7) >> 3;
+  const bool have = lane < m;
+  const float* src = ix.arena + (size_t)(have ? cid : 0) * ix.ds;
   float raw = 0.f, nb = 0.f;
-  const uint32_t p = w.lane & 3;
-  for (uint32_t base = 0; base < m; base += w.n_slots) {
-    const uint32_t cnt = min(w.n_slots, m - base);
-    const uint32_t slot = w.lane - base;
-    const bool mine = (w.lane >= base) && (slot < cnt);
-    const uint32_t groups = (cnt + 7) >> 3;
-    if (mine && (slot & 7) == 0)
-      mbar_expect_tx(w.bar0 + 8 * (slot >> 3), min(8u, cnt - slot) * w.vec_bytes);
+  if (METRIC == kCosine && have) nb = __ldg(ix.norm2 + cid);
+
+  auto issue = [&](uint32_t c) {
+    const uint32_t g = c % G;
+    const uint32_t bar = w.bar0 + 8 * g;
+    if (have && my_chunk == c && sub == 0) mbar_expect_tx(bar, min(8u, m - 8 * c) * w.vec_bytes);
     __syncwarp();
-    if (mine) {
-      bulk_g2s(w.stage_u32 + slot * w.stride, ix.arena + (size_t)cid * ix.ds, w.vec_bytes,
-               w.bar0 + 8 * (slot >> 3));
-      if (METRIC == kCosine) nb = __ldg(ix.norm2 + cid);
-    }
-    for (uint32_t g = 0; g < groups; ++g) {
-      mbar_wait(w.bar0 + 8 * g, (w.phases >> g) & 1u);
-      w.phases ^= (1u << g);
-      const float* b = reinterpret_cast<const float*>(w.stage + (g * 8 + (w.lane >> 2)) * w.stride);
-      float r = (METRIC == kL2) ? quad_l2sq(w.q, b, ix.dim, p) : quad_dot(w.q, b, ix.dim, p);
-      float t = __shfl_sync(kFullMask, r, (slot & 7) * 4);
-      if (mine && (slot >> 3) == g) raw = t;
-    }
-    __syncwarp();
+    if (have && my_chunk == c) bulk_g2s(w.stage_u32 + (g * 8 + sub) * w.stride, src, w.vec_bytes, bar);
+  };
+  const uint32_t pro = min(G, nchunks);
+  for (uint32_t c = 0; c < pro; ++c) issue(c);
+  for (uint32_t c = 0; c < nchunks; ++c) {
+    const uint32_t g = c % G;
+    mbar_wait(w.bar0 + 8 * g, (w.phases >> g) & 1u);
+    w.phases ^= (1u << g);
+    const float* b = reinterpret_cast<const float*>(w.stage + (g * 8 + (lane >> 2)) * w.stride);
+    const float r = (METRIC == kL2) ? quad_l2sq(w.q, b, ix.dim, p) : quad_dot(w.q, b, ix.dim, p);
+    const float t = __shfl_sync(kFullMask, r, sub * 4);
+    if (my_chunk == c) raw = t;
+    if (c + G < nchunks) issue(c + G);
   }
-  if (w.lane >= m) return INFINITY;
+  __syncwarp();
+  if (!have) return INFINITY;
   if (METRIC == kL2) return raw;
   if (METRIC == kIP) return -raw;  // inner_product_avx2, distance.rs:240-242
   return cosine_finish(raw, w.qnorm, nb);
 }
 
-// Exact visited set.  Shared: open-addressing table of full ids.  Global: one bit per node.
+// Exact visited set.  Returns 1 = newly inserted, 0 = already present, 2 = table cannot place the key
+// (the query is then redone by the global-bitset pass).
+//   GLOBAL : one bit per node in global memory.
+//   shared, 32-bit entries: open addressing on the full id.
+//   shared, 16-bit entries: h = id * odd (mod 2^key_bits) is a bijection; home = top hash_bits of h, the
+//     entry stores the remaining rem_bits plus (displacement + 1), which together name h and so the id.
 template <bool GLOBAL>
-__device__ __forceinline__ bool visited_insert(uint32_t* tab, uint32_t id, uint32_t hash_bits) {
+__device__ __forceinline__ uint32_t visited_insert(uint32_t* tab, uint32_t id, const WarpLayout& L) {
   if (GLOBAL) {
     const uint32_t bit = 1u << (id & 31);
-    return (atomicOr(tab + (id >> 5), bit) & bit) == 0;
+    return (atomicOr(tab + (id >> 5), bit) & bit) == 0 ? 1u : 0u;
   }
-  const uint32_t mask = (1u << hash_bits) - 1;
-  uint32_t slot = (id * 0x9E3779B1u) >> (32 - hash_bits);
+  const uint32_t mask = (1u << L.hash_bits) - 1;
+  if (L.hash16) {
+    unsigned short* t16 = reinterpret_cast<unsigned short*>(tab);
+    const uint32_t h = (id * 0x9E3779B1u) & ((1u << L.key_bits) - 1);
+    const uint32_t home = h >> L.rem_bits, rem = h & ((1u << L.rem_bits) - 1);
+    const uint32_t max_disp = (1u << (16 - L.rem_bits)) - 1;  // displacement+1 must fit
+    for (uint32_t disp = 0; disp < max_disp; ++disp) {
+      const unsigned short want = (unsigned short)(((disp + 1) << L.rem_bits) | rem);
+      const unsigned short old = atomicCAS(t16 + ((home + disp) & mask), (unsigned short)0, want);
+      if (old == 0) return 1u;
+      if (old == want) return 0u;
+    }
+    return 2u;
+  }
+  uint32_t slot = (id * 0x9E3779B1u) >> (32 - L.hash_bits);
   for (;;) {
-    uint32_t old = atomicCAS(tab + slot, kInvalid, id);
-    if (old == kInvalid) return true;
-    if (old == id) return false;
+    const uint32_t old = atomicCAS(tab + slot, kInvalid, id);
+    if (old == kInvalid) return 1u;
+    if (old == id) return 0u;
     slot = (slot + 1) & mask;
   }
 }
 
 template <int METRIC, bool GLOBAL_VISITED>
-__global__ void __launch_bounds__(256) hnsw_search_kernel(const SearchArgs a) {
+__global__ void __launch_bounds__(256, 1) hnsw_search_kernel(const SearchArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const DeviceIndex& ix = a.ix;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -159,6 +190,9 @@ __global__ void __launch_bounds__(256) hnsw_search_kernel(const SearchArgs a) {
     if (GLOBAL_VISITED) {
       uint4* v4 = reinterpret_cast<uint4*>(vis);
       for (uint32_t i = lane; i < (a.vis_words >> 2); i += 32) v4[i] = make_uint4(0, 0, 0, 0);
+    } else if (a.lay.hash16) {
+      uint4* v4 = reinterpret_cast<uint4*>(vis);
+      for (uint32_t i = lane; i < (hash_slots >> 3); i += 32) v4[i] = make_uint4(0, 0, 0, 0);
     } else {
       uint4* v4 = reinterpret_cast<uint4*>(vis);
       for (uint32_t i = lane; i < (hash_slots >> 2); i += 32)
@@ -215,33 +249,52 @@ __global__ void __launch_bounds__(256) hnsw_search_kernel(const SearchArgs a) {
       if (lane == 0) {
         A_d[0] = cur_d;
         A_id[0] = cur;
-        (void)visited_insert<GLOBAL_VISITED>(vis, cur, a.lay.hash_bits);
+        (void)visited_insert<GLOBAL_VISITED>(vis, cur, a.lay);
       }
       len = 1;
       uint32_t n_visited = 1;
+      uint32_t spec_node = kInvalid, spec_nid = kInvalid;  // speculatively fetched adjacency row
       __syncwarp();
 
       for (;;) {
-        // closest unexpanded entry == the reference's candidates.pop() that passes `d <= worst`
-        uint32_t idx = 0xFFFFFFFFu;
+        // closest unexpanded entry == the reference's candidates.pop() that passes `d <= worst`;
+        // the runner-up is the likely next hop: its adjacency row is fetched while this hop gathers.
+        uint32_t i1 = 0xFFFFFFFFu, i2 = 0xFFFFFFFFu;
         for (uint32_t i = lane; i < len; i += 32)
           if (!(A_id[i] & kExpandedBit)) {
-            idx = i;
-            break;
+            if (i1 == 0xFFFFFFFFu) i1 = i;
+            else {
+              i2 = i;
+              break;
+            }
           }
-        idx = __reduce_min_sync(kFullMask, idx);
+        const uint32_t idx = __reduce_min_sync(kFullMask, i1);
         if (idx >= len) break;
+        const uint32_t idx2 = __reduce_min_sync(kFullMask, i1 == idx ? i2 : i1);
         const uint32_t c = A_id[idx];
+        const uint32_t c2 = idx2 < len ? A_id[idx2] : kInvalid;
         __syncwarp();
         if (lane == 0) A_id[idx] = c | kExpandedBit;
+        __syncwarp();
         n_expanded += 1;
 
         if (!GLOBAL_VISITED && n_visited + kL0 > hash_limit) {
           overflow = true;
           break;
         }
-        const uint32_t nid = __ldg(ix.l0_adj + (size_t)c * kL0 + lane);
-        const bool isnew = (nid != kInvalid) && visited_insert<GLOBAL_VISITED>(vis, nid, a.lay.hash_bits);
+        const uint32_t nid = (c == spec_node) ? spec_nid : __ldg(ix.l0_adj + (size_t)c * kL0 + lane);
+        if (c2 != kInvalid) {
+          spec_node = c2;
+          spec_nid = __ldg(ix.l0_adj + (size_t)c2 * kL0 + lane);
+        } else {
+          spec_node = kInvalid;
+        }
+        const uint32_t ins = (nid != kInvalid) ? visited_insert<GLOBAL_VISITED>(vis, nid, a.lay) : 0u;
+        if (__any_sync(kFullMask, ins == 2u)) {
+          overflow = true;
+          break;
+        }
+        const bool isnew = ins == 1u;
         const uint32_t newmask = __ballot_sync(kFullMask, isnew);
         const uint32_t m = __popc(newmask);
         if (m == 0) continue;

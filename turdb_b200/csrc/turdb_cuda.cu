@@ -10,6 +10,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 #include "exact_search.cuh"
@@ -41,6 +42,12 @@ static int32_t fail(int32_t code, const char* fmt, ...) {
     }                                                                                        \
   } while (0)
 
+static uint32_t ceil_log2(uint32_t v) {
+  uint32_t b = 0;
+  while (b < 31 && (1u << b) < v) ++b;
+  return b;
+}
+
 // ------------------------------------------------------------------------------------------
 // index
 // ------------------------------------------------------------------------------------------
@@ -57,8 +64,12 @@ struct turdb_cuda_index {
   uint64_t* d_row_ids = nullptr;
   uint8_t* d_levels = nullptr;
   __nv_bfloat16* d_arena_bf16 = nullptr;  // exact path operand, built lazily
+  cudaMemPool_t pool = nullptr;            // per-index stream-ordered scratch pool (never trimmed)
   uint64_t device_bytes = 0;
   uint32_t tune_warps = 0, tune_slots = 0, tune_hash_bits = 0;
+  // profiling ring: 3 events per call (before main, after main, after overflow pass)
+  std::vector<cudaEvent_t> prof_events;
+  uint32_t prof_capacity = 0, prof_used = 0;
   std::mutex mu;
 };
 
@@ -129,6 +140,8 @@ int32_t turdb_cuda_index_destroy(turdb_cuda_index* idx) {
     cudaFree(idx->d_row_ids);
     cudaFree(idx->d_levels);
     cudaFree(idx->d_arena_bf16);
+    for (cudaEvent_t ev : idx->prof_events) cudaEventDestroy(ev);
+    if (idx->pool) cudaMemPoolDestroy(idx->pool);
   }
   delete idx;
   return TURDB_OK;
@@ -174,6 +187,19 @@ int32_t turdb_cuda_index_create(const turdb_cuda_graph* g, int32_t device, turdb
     return fail(TURDB_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
   }
 
+  {
+    cudaMemPoolProps pp{};
+    pp.allocType = cudaMemAllocationTypePinned;
+    pp.handleTypes = cudaMemHandleTypeNone;
+    pp.location.type = cudaMemLocationTypeDevice;
+    pp.location.id = device;
+    if (cudaMemPoolCreate(&idx->pool, &pp) != cudaSuccess) {
+      delete idx;
+      return fail(TURDB_ERR_CUDA, "cudaMemPoolCreate failed");
+    }
+    uint64_t keep = ~0ull;  // keep freed scratch cached across synchronisations
+    cudaMemPoolSetAttribute(idx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
   const uint64_t n = g->n;
   const uint32_t dim = g->dim, ds = (dim + 3) & ~3u;
   idx->ix.n = n;
@@ -280,30 +306,62 @@ int32_t turdb_cuda_index_set_tuning(turdb_cuda_index* idx, uint32_t warps_per_ct
   return TURDB_OK;
 }
 
+int32_t turdb_cuda_index_profile_begin(turdb_cuda_index* idx, uint32_t capacity) {
+  if (!idx) return fail(TURDB_ERR_INVALID_ARGUMENT, "idx is null");
+  if (capacity > 4096) return fail(TURDB_ERR_INVALID_ARGUMENT, "capacity > 4096");
+  DeviceGuard guard(idx->device);
+  std::lock_guard<std::mutex> lk(idx->mu);
+  while (idx->prof_events.size() < (size_t)capacity * 3) {
+    cudaEvent_t ev;
+    CUDA_TRY(cudaEventCreate(&ev));
+    idx->prof_events.push_back(ev);
+  }
+  idx->prof_capacity = capacity;
+  idx->prof_used = 0;
+  return TURDB_OK;
+}
+
+int32_t turdb_cuda_index_profile_read(turdb_cuda_index* idx, float* main_ms, float* overflow_ms, uint32_t cap,
+                                      uint32_t* out_n) {
+  if (!idx || !out_n) return fail(TURDB_ERR_INVALID_ARGUMENT, "null argument");
+  DeviceGuard guard(idx->device);
+  std::lock_guard<std::mutex> lk(idx->mu);
+  uint32_t n = std::min(idx->prof_used, cap);
+  for (uint32_t i = 0; i < n; ++i) {
+    float a = 0.f, b = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&a, idx->prof_events[3 * i], idx->prof_events[3 * i + 1]));
+    CUDA_TRY(cudaEventElapsedTime(&b, idx->prof_events[3 * i + 1], idx->prof_events[3 * i + 2]));
+    if (main_ms) main_ms[i] = a;
+    if (overflow_ms) overflow_ms[i] = b;
+  }
+  *out_n = n;
+  idx->prof_capacity = 0;
+  idx->prof_used = 0;
+  return TURDB_OK;
+}
+
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------
 // traversal launch
 // ------------------------------------------------------------------------------------------
-static uint32_t ceil_log2(uint32_t v) {
-  uint32_t b = 0;
-  while ((1u << b) < v) ++b;
-  return b;
-}
-
-static WarpLayout make_layout(uint32_t ds, uint32_t ef, uint32_t hash_bits, uint32_t n_slots, bool global_visited) {
+static WarpLayout make_layout(uint32_t ds, uint32_t ef, uint32_t hash_bits, uint32_t n_slots, bool global_visited,
+                              uint64_t n_nodes) {
   WarpLayout L{};
   L.vec_bytes = ds * 4;
   const uint32_t pad_words = (8 + 32 - (ds & 31)) & 31;
   L.stride = (ds + pad_words) * 4;
   L.hash_bits = hash_bits;
   L.n_slots = n_slots;
+  L.key_bits = std::max(hash_bits, ceil_log2((uint32_t)std::max<uint64_t>(n_nodes, 2)));
+  L.rem_bits = L.key_bits - hash_bits;
+  L.hash16 = (!global_visited && L.rem_bits <= 11) ? 1u : 0u;  // displacement field >= 5 bits
   uint32_t off = 0;
   L.off_bar = off;   off += 64;
   L.off_q = off;     off += (ds * 4 + 15) & ~15u;
   L.off_list = off;  off += ef * 16;
   L.off_tmp = off;   off += 256;
-  L.off_hash = off;  off += global_visited ? 0 : (4u << hash_bits);
+  L.off_hash = off;  off += global_visited ? 0 : ((L.hash16 ? 2u : 4u) << hash_bits);
   off = (off + 127) & ~127u;
   L.off_stage = off; off += n_slots * L.stride;
   L.warp_bytes = (off + 127) & ~127u;
@@ -389,23 +447,35 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
   const uint32_t ds = idx->ix.ds;
   uint32_t hash_bits = th ? th : std::min(15u, std::max(9u, ceil_log2(ef * 64)));
   uint32_t warps = tw ? tw : 1;
-  uint32_t slots = ts;
   const uint32_t budget = (uint32_t)idx->max_smem_optin;
-  if (!slots) {  // fit one query's state in ~56 KB (4 resident queries per SM) when possible
-    WarpLayout probe = make_layout(ds, ef, hash_bits, 0, false);
-    uint32_t target = 56 * 1024;
-    uint32_t room = target > probe.warp_bytes ? target - probe.warp_bytes : 0;
-    slots = std::min(32u, std::max(8u, (room / probe.stride) & ~7u));
+  const uint64_t nn = idx->ix.n;
+  uint32_t slots = ts;
+  if (!slots) {
+    // most neighbour vectors in flight per SM: resident queries x staging slots (a hop rarely has
+    // more than ~24 unvisited neighbours); ties go to the deeper staging
+    const uint32_t sm_bytes = budget + 1024;
+    uint32_t best = 0;
+    for (uint32_t cand = 8; cand <= 32; cand += 8) {
+      WarpLayout L = make_layout(ds, ef, hash_bits, cand, false, nn);
+      if (L.warp_bytes > budget) break;
+      uint32_t occ = std::min(32u, sm_bytes / (L.warp_bytes + 1024));
+      uint32_t score = occ * std::min(cand, 24u);
+      if (score >= best) {
+        best = score;
+        slots = cand;
+      }
+    }
+    if (!slots) slots = 8;
   }
-  WarpLayout lay = make_layout(ds, ef, hash_bits, slots, false);
+  WarpLayout lay = make_layout(ds, ef, hash_bits, slots, false, nn);
   while (lay.warp_bytes * warps > budget && warps > 1) --warps;
-  while (lay.warp_bytes > budget && lay.n_slots > 8) lay = make_layout(ds, ef, hash_bits, lay.n_slots - 8, false);
-  while (lay.warp_bytes > budget && hash_bits > 8) lay = make_layout(ds, ef, --hash_bits, lay.n_slots, false);
+  while (lay.warp_bytes > budget && lay.n_slots > 8) lay = make_layout(ds, ef, hash_bits, lay.n_slots - 8, false, nn);
+  while (lay.warp_bytes > budget && hash_bits > 8) lay = make_layout(ds, ef, --hash_bits, lay.n_slots, false, nn);
   if (lay.warp_bytes > budget)
     return fail(TURDB_ERR_UNSUPPORTED, "dim %u / ef %u need %u B of shared memory per query (> %u)", idx->ix.dim, ef, lay.warp_bytes, budget);
 
   uint32_t* d_scratch = nullptr;  // [0] work counter, [1] overflow count, [2] fallback work counter, [4..] overflow list
-  CUDA_TRY(cudaMallocAsync(&d_scratch, (size_t)(4 + nq) * 4, stream));
+  CUDA_TRY(cudaMallocFromPoolAsync(&d_scratch, (size_t)(4 + nq) * 4, idx->pool, stream));
   CUDA_TRY(cudaMemsetAsync(d_scratch, 0, 16, stream));
 
   SearchArgs a{};
@@ -425,7 +495,14 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
   a.overflow_list = d_scratch + 4;
   a.global_visited = nullptr;
   a.vis_words = 0;
+  cudaEvent_t* pev = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(idx->mu);
+    if (idx->prof_used < idx->prof_capacity) pev = &idx->prof_events[3 * idx->prof_used++];
+  }
+  if (pev) cudaEventRecord(pev[0], stream);
   cudaError_t e = launch_metric<false>(metric, a, warps, idx->num_sms, (nq + warps - 1) / warps, stream, nullptr);
+  if (pev) cudaEventRecord(pev[1], stream);
   if (e != cudaSuccess) {
     cudaFreeAsync(d_scratch, stream);
     return fail(TURDB_ERR_CUDA, "traversal kernel launch failed: %s", cudaGetErrorString(e));
@@ -434,17 +511,18 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
   // exact fallback for queries whose shared visited table filled: same kernel, one bit per node in
   // global memory.  Always enqueued (no host sync); exits immediately when the list is empty.
   {
-    WarpLayout glay = make_layout(ds, ef, 8, lay.n_slots, true);
+    WarpLayout glay = make_layout(ds, ef, 8, lay.n_slots, true, nn);
     SearchArgs b = a;
     b.lay = glay;
     b.work_counter = d_scratch + 2;
     b.vis_words = (uint32_t)(((idx->ix.n + 31) / 32 + 3) & ~3ull);
     const uint32_t fb_ctas = (uint32_t)std::min<uint32_t>((uint32_t)idx->num_sms, nq);
     uint32_t* d_gv = nullptr;
-    e = cudaMallocAsync(&d_gv, (size_t)fb_ctas * b.vis_words * 4, stream);
+    e = cudaMallocFromPoolAsync(&d_gv, (size_t)fb_ctas * b.vis_words * 4, idx->pool, stream);
     if (e == cudaSuccess) {
       b.global_visited = d_gv;
       e = launch_metric<true>(metric, b, 1, idx->num_sms, fb_ctas, stream, nullptr);
+      if (pev) cudaEventRecord(pev[2], stream);
       cudaFreeAsync(d_gv, stream);
     }
     if (e != cudaSuccess) {
@@ -480,7 +558,7 @@ extern "C" int32_t turdb_cuda_search_batch(turdb_cuda_index* idx, const float* q
          total = off_vis + vis_bytes;
   uint8_t* slab = nullptr;
   int32_t rc = TURDB_OK;
-  cudaError_t e = cudaMallocAsync(&slab, total, stream);
+  cudaError_t e = cudaMallocFromPoolAsync(&slab, total, idx->pool, stream);
   if (e != cudaSuccess) {
     cudaStreamDestroy(stream);
     return fail(TURDB_ERR_OUT_OF_MEMORY, "cudaMallocAsync(%zu) failed: %s", total, cudaGetErrorString(e));

@@ -1,0 +1,203 @@
+"""Bulk HNSW graph construction on the GPU — a BUILD-TIME UTILITY, not the search hot path.
+
+The reference builds its graph one insert at a time (`insert_with_callback`, src/hnsw/mod.rs:999-1084):
+~1.2 ms per insert single-threaded, i.e. hours for the 1M-100M corpora BASELINE.json names.  Benches
+need those graphs in seconds, so this module builds a graph with the SAME structure the reference
+stores — levels drawn by `select_level` (operations.rs:76-83), level-0 lists capped at 32, upper lists
+at 16 (mod.rs:126-127), entry = first node of the top level — but fills the lists from an exact
+k-nearest-neighbour pass per level followed by the reference's own `select_neighbors_heuristic`
+(operations.rs:181-233) and its back-link rule (append if room, re-select on overflow: the
+"reference-intent" mode of SURVEY.md §7).  Distances are squared L2 on the raw vectors, as in the
+reference's insert path (mod.rs:1031,1046).
+
+Result files label this provenance "knn-heuristic"; graphs from the oracle's sequential restatement of
+the insert path are labelled "reference-intent" / "verbatim".  Search parity (GPU kernel vs CPU
+oracle) is always measured on the same arrays, whichever builder made them.
+
+torch is used here for dense algebra (matmul/topk/sort); none of it runs inside a timed region.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+MAX_L0, MAX_UP, INVALID = 32, 16, 0xFFFFFFFF
+
+
+def select_levels(randoms: np.ndarray, m: int = 16) -> np.ndarray:
+    """select_level(random_value, 1/ln(m)) for a stream of random values in (0, 1]."""
+    ml = 1.0 / math.log(float(m))
+    lv = np.floor(-np.log(randoms.astype(np.float64)) * ml)
+    return np.clip(np.nan_to_num(lv, nan=0.0), 0, 15).astype(np.uint8)
+
+
+@torch.no_grad()
+def _knn_level(xf: torch.Tensor, norms: torch.Tensor, ids: torch.Tensor, k: int, margin: int, chunk: int):
+    """Exact k-NN (squared L2) of every node in `ids` among `ids`.  Returns local positions [n_l,k], d [n_l,k]."""
+    n_l = ids.numel()
+    whole = n_l == xf.shape[0]
+    cols = xf if whole else xf[ids]
+    cn = norms if whole else norms[ids]
+    kc = min(k + margin, n_l - 1)
+    out_pos = torch.empty((n_l, k), dtype=torch.int64, device=xf.device)
+    out_d = torch.empty((n_l, k), dtype=torch.float32, device=xf.device)
+    ar = torch.arange(chunk, device=xf.device)
+    for s in range(0, n_l, chunk):
+        e = min(n_l, s + chunk)
+        rows = cols[s:e]
+        score = rows @ cols.T  # TF32 tensor-core pass (candidates only; re-evaluated in FP32 below)
+        score.mul_(-2.0).add_(cn[None, :])
+        score[ar[: e - s], ar[: e - s] + s] = float("inf")
+        cand = torch.topk(score, kc, dim=1, largest=False, sorted=False).indices
+        del score
+        xc = cols[cand]
+        de = ((xc - rows[:, None, :]) ** 2).sum(-1)
+        de, o = torch.sort(de, dim=1)
+        cand = torch.gather(cand, 1, o)
+        out_pos[s:e] = cand[:, :k]
+        out_d[s:e] = de[:, :k]
+    return out_pos, out_d
+
+
+@torch.no_grad()
+def _heuristic(cols: torch.Tensor, cand: torch.Tensor, cand_d: torch.Tensor, cap: int, chunk: int):
+    """select_neighbors_heuristic over rows of ascending candidates (local positions, -1 / inf padded).
+    Returns ids [B,cap] (-1 padded), d [B,cap], counts [B]; kept candidates first, then the back-fill."""
+    dev = cand.device
+    if cand.shape[1] < cap:  # fewer candidates than list slots (tiny top levels): pad
+        pad = cap - cand.shape[1]
+        cand = torch.cat([cand, torch.full((cand.shape[0], pad), -1, dtype=cand.dtype, device=dev)], 1)
+        cand_d = torch.cat([cand_d, torch.full((cand_d.shape[0], pad), float("inf"), dtype=cand_d.dtype, device=dev)], 1)
+    b_all, k = cand.shape
+    out = torch.full((b_all, cap), -1, dtype=torch.int64, device=dev)
+    out_d = torch.full((b_all, cap), float("inf"), dtype=torch.float32, device=dev)
+    cnts = torch.zeros(b_all, dtype=torch.int64, device=dev)
+    jj = torch.arange(k, device=dev)[None, :]
+    for s in range(0, b_all, chunk):
+        e = min(b_all, s + chunk)
+        c = cand[s:e]
+        d = cand_d[s:e]
+        valid = c >= 0
+        xc = cols[c.clamp(min=0)]
+        nc = (xc * xc).sum(-1)
+        dcc = nc[:, :, None] + nc[:, None, :] - 2.0 * torch.bmm(xc, xc.transpose(1, 2))
+        del xc
+        kept = torch.zeros_like(valid)
+        cnt = torch.zeros(e - s, dtype=torch.int64, device=dev)
+        for j in range(k):
+            bad = ((dcc[:, j, :] < d[:, j, None]) & kept).any(1)
+            ok = valid[:, j] & ~bad & (cnt < cap)
+            kept[:, j] = ok
+            cnt += ok
+        notkept = valid & ~kept
+        fill = notkept & ((torch.cumsum(notkept, 1) - 1) < (cap - cnt)[:, None])
+        key = torch.where(kept, jj, torch.where(fill, jj + k, jj + 3 * k))
+        o = torch.argsort(key, dim=1)[:, :cap]
+        take = torch.gather(kept | fill, 1, o)
+        out[s:e] = torch.where(take, torch.gather(c, 1, o), torch.full_like(o, -1))
+        out_d[s:e] = torch.where(take, torch.gather(d, 1, o), torch.full_like(o, float("inf"), dtype=torch.float32))
+        cnts[s:e] = take.sum(1)
+    return out, out_d, cnts
+
+
+@torch.no_grad()
+def _level_lists(xf, norms, ids, cap, knn_k, rev_cap, chunk_rows, chunk_h):
+    """Neighbour lists (local positions, -1 padded) for one level."""
+    dev = xf.device
+    n_l = ids.numel()
+    if n_l <= 1:
+        return torch.full((n_l, cap), -1, dtype=torch.int64, device=dev), torch.zeros(n_l, dtype=torch.int64, device=dev)
+    whole = n_l == xf.shape[0]
+    cols = xf if whole else xf[ids]
+    k = min(knn_k, n_l - 1)
+    pos, d = _knn_level(xf, norms, ids, k, margin=16, chunk=chunk_rows)
+    f_ids, f_d, f_cnt = _heuristic(cols, pos, d, cap, chunk_h)
+    del pos, d
+    # ---- back-links: dst <- src for every forward edge src -> dst that dst does not already hold ----
+    src = torch.arange(n_l, device=dev)[:, None].expand(n_l, cap).reshape(-1)
+    dst = f_ids.reshape(-1)
+    dd = f_d.reshape(-1)
+    ok = dst >= 0
+    src, dst, dd = src[ok], dst[ok], dd[ok]
+    keep = torch.empty(src.numel(), dtype=torch.bool, device=dev)
+    step = 1 << 22
+    for s in range(0, src.numel(), step):
+        e = min(src.numel(), s + step)
+        keep[s:e] = ~(f_ids[dst[s:e]] == src[s:e, None]).any(1)
+    src, dst, dd = src[keep], dst[keep], dd[keep]
+    o = torch.argsort(dd)
+    src, dst, dd = src[o], dst[o], dd[o]
+    o = torch.argsort(dst, stable=True)
+    src, dst, dd = src[o], dst[o], dd[o]
+    counts = torch.bincount(dst, minlength=n_l)
+    starts = torch.cumsum(counts, 0) - counts
+    rank = torch.arange(dst.numel(), device=dev) - starts[dst]
+    sel = rank < rev_cap
+    r_ids = torch.full((n_l, rev_cap), -1, dtype=torch.int64, device=dev)
+    r_d = torch.full((n_l, rev_cap), float("inf"), dtype=torch.float32, device=dev)
+    r_ids[dst[sel], rank[sel]] = src[sel]
+    r_d[dst[sel], rank[sel]] = dd[sel]
+    r_cnt = torch.clamp(counts, max=rev_cap)
+    total = f_cnt + r_cnt
+    # room for every back-link: append in arrival (distance) order, as add_neighbor_at_level does
+    c_ids = torch.cat([f_ids, r_ids], 1)
+    c_d = torch.cat([f_d, r_d], 1)
+    key = torch.where(c_ids >= 0, torch.arange(cap + rev_cap, device=dev)[None, :], cap + rev_cap)
+    o = torch.argsort(key, dim=1, stable=True)[:, :cap]
+    out = torch.gather(c_ids, 1, o)
+    cnt = torch.clamp(total, max=cap)
+    # overflow: re-select over (list + back-links) sorted by distance to the owner
+    over = torch.nonzero(total > cap).squeeze(1)
+    if over.numel():
+        oc_d, oo = torch.sort(c_d[over], dim=1)
+        oc = torch.gather(c_ids[over], 1, oo)
+        sel_ids, _, sel_cnt = _heuristic(cols, oc, oc_d, cap, chunk_h)
+        out[over] = sel_ids
+        cnt[over] = sel_cnt
+    return out, cnt
+
+
+@torch.no_grad()
+def build_graph(vectors: np.ndarray, m: int = 16, seed: int = 1234, device: str | torch.device = "cuda:0",
+                knn_k: int = 64, row_ids: np.ndarray | None = None, chunk_rows: int = 4096) -> dict:
+    """vectors [n, dim] f32 -> the flattened graph dict `CudaHnswIndex.from_graph` / the oracle take."""
+    vectors = np.ascontiguousarray(vectors, dtype=np.float32)
+    n, dim = vectors.shape
+    dev = torch.device(device)
+    prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        rng = np.random.default_rng(seed)
+        levels = select_levels(1.0 - rng.random(n), m)
+        max_level = int(levels.max()) if n else 0
+        xf = torch.from_numpy(vectors).to(dev)
+        norms = (xf * xf).sum(1)
+        lv = torch.from_numpy(levels.astype(np.int64)).to(dev)
+        chunk_h = max(256, min(8192, (1 << 28) // max(1, (knn_k + 32) * dim)))
+        l0, l0_cnt = _level_lists(xf, norms, torch.arange(n, device=dev), MAX_L0, knn_k, MAX_L0, chunk_rows, chunk_h)
+        l0_adj = torch.where(l0 >= 0, l0, torch.full_like(l0, INVALID)).to(torch.int64).cpu().numpy().astype(np.uint32)
+        n_slots = int(levels.astype(np.int64).sum())
+        up_base = np.full(n, INVALID, np.uint32)
+        has_up = levels > 0
+        base = np.cumsum(levels.astype(np.int64)) - levels
+        up_base[has_up] = base[has_up].astype(np.uint32)
+        up_adj = np.full((n_slots, MAX_UP), INVALID, np.uint32)
+        up_cnt = np.zeros(n_slots, np.uint8)
+        for level in range(1, max_level + 1):
+            ids = torch.nonzero(lv >= level).squeeze(1)
+            lists, cnt = _level_lists(xf, norms, ids, MAX_UP, 2 * m, MAX_UP, chunk_rows, chunk_h)
+            glob = torch.where(lists >= 0, ids[lists.clamp(min=0)], torch.full_like(lists, INVALID))
+            ids_np = ids.cpu().numpy()
+            slots = base[ids_np] + (level - 1)
+            up_adj[slots] = glob.cpu().numpy().astype(np.uint32)
+            up_cnt[slots] = cnt.cpu().numpy().astype(np.uint8)
+        entry = int(np.flatnonzero(levels == max_level)[0]) if n else INVALID
+        return dict(
+            vectors=vectors,
+            row_ids=np.arange(n, dtype=np.uint64) if row_ids is None else np.ascontiguousarray(row_ids, np.uint64),
+            levels=levels, l0_adj=l0_adj, l0_cnt=l0_cnt.cpu().numpy().astype(np.uint8), up_base=up_base,
+            up_adj=up_adj, up_cnt=up_cnt, entry=entry, max_level=max_level, provenance="knn-heuristic")
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev_tf32

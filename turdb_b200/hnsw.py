@@ -151,6 +151,18 @@ class CudaHnswIndex:
     def set_tuning(self, warps_per_cta: int = 0, staging_slots: int = 0, hash_bits: int = 0):
         _check(_lib.load().turdb_cuda_index_set_tuning(self._h, warps_per_cta, staging_slots, hash_bits))
 
+    def profile_begin(self, capacity: int):
+        _check(_lib.load().turdb_cuda_index_profile_begin(self._h, capacity))
+
+    def profile_read(self, capacity: int):
+        """(main_ms[n], overflow_ms[n]) per-launch device times since profile_begin (sync the stream first)."""
+        a = np.zeros(capacity, np.float32)
+        b = np.zeros(capacity, np.float32)
+        n = C.c_uint32(0)
+        _check(_lib.load().turdb_cuda_index_profile_read(self._h, _ptr(a, C.c_float), _ptr(b, C.c_float), capacity,
+                                                         C.byref(n)))
+        return a[:n.value], b[:n.value]
+
     # ---- the reference's entry points ------------------------------------------------------
     def search(self, query, k: int, ctx: HnswSearchContext, metric: DistanceFunction | None = None):
         """PersistentHnswIndex::search(query, k, ctx, get_vector) -> Vec<SearchResult>."""
