@@ -120,8 +120,9 @@ int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const float* d_que
                                        float* d_out_dist, uint32_t* d_out_counts,
                                        turdb_cuda_search_stats* d_out_stats, void* stream);
 
-/* Tunables of the traversal kernel (0 = automatic).  warps_per_cta queries are resident per CTA,
- * staging_slots neighbour vectors are in flight per query, hash_bits sizes the visited table. */
+/* Tunables of the traversal kernel (0 = automatic).  warps_per_cta (1..4) warps cooperate on one
+ * query, staging_slots (8..32) neighbour vectors are in flight per query, hash_bits sizes the
+ * shared-memory visited table. */
 int32_t turdb_cuda_index_set_tuning(turdb_cuda_index* idx, uint32_t warps_per_cta,
                                     uint32_t staging_slots, uint32_t hash_bits);
 
@@ -135,6 +136,10 @@ int32_t turdb_cuda_index_set_tuning(turdb_cuda_index* idx, uint32_t warps_per_ct
 int32_t turdb_cuda_index_profile_begin(turdb_cuda_index* idx, uint32_t capacity);
 int32_t turdb_cuda_index_profile_read(turdb_cuda_index* idx, float* main_ms, float* overflow_ms,
                                       uint32_t cap, uint32_t* out_n);
+
+/* Diagnostics: enable != 0 arms 16 per-phase cycle counters inside the traversal kernel (a few
+ * clock reads per hop); out16 (nullable) receives the counters accumulated since they were armed. */
+int32_t turdb_cuda_index_debug_counters(turdb_cuda_index* idx, int32_t enable, uint64_t* out16);
 
 /*
  * ---- exact path: the SQL `ORDER BY vec <op> q LIMIT k` scan (TopKExec, ---------------------

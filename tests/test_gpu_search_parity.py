@@ -135,7 +135,7 @@ def test_visited_overflow_fallback(gpu_required, small_graph):
     idx.close()
 
 
-@pytest.mark.parametrize("slots,warps", [(8, 1), (16, 2), (32, 4)])
+@pytest.mark.parametrize("slots,warps", [(8, 1), (16, 2), (32, 4), (24, 3), (16, 4), (32, 1)])
 def test_tunings_do_not_change_results(gpu_required, small_graph, slots, warps):
     g, arrays = small_graph
     q = ds.gaussian_latent(300, 128, seed=8)

@@ -22,6 +22,7 @@ ap.add_argument("--metric", type=int, default=1)
 ap.add_argument("--latent", type=int, default=16)
 ap.add_argument("--tunings", default="0,0,0;1,8,0;1,16,0;1,24,0;1,32,0;2,16,0;1,16,12;1,24,12")
 ap.add_argument("--out", default="gpurun_out/sweep.json")
+ap.add_argument("--debug", action="store_true")
 args = ap.parse_args()
 
 norm = args.metric == 1
@@ -61,6 +62,14 @@ for tun in args.tunings.split(";"):
             run()
         torch.cuda.synchronize()
         km, om = idx.profile_read(reps)
+        if args.debug:
+            idx.debug_counters(True)
+            run(); torch.cuda.synchronize()
+            c = idx.debug_counters(False).astype(np.float64)
+            h = max(c[0], 1.0)
+            print("  dbg per-hop cycles: select %.0f adj+hash %.0f request %.0f (w0: issue %.0f wait %.0f comp %.0f) merge %.0f | "
+                  "spec-hit %.2f | per-query: total %.0f upper %.0f hops %.1f" % (c[1]/h, c[2]/h, c[3]/h, c[6]/h, c[5]/h, c[7]/h, c[4]/h,
+                   c[8]/h, c[9]/max(c[11],1), c[10]/max(c[11],1), c[0]/max(c[11],1)), flush=True)
         ms = float(km.mean())
         st = stats.cpu().numpy().astype(np.int64)
         nbytes = (st[:, 0] * args.dim * 4 + st[:, 2] * 129 + st[:, 3] * 65 + args.dim * 4 + args.k * 12).sum()

@@ -29,7 +29,7 @@ EXPORTS = [
     "turdb_cuda_abi_version", "turdb_cuda_last_error", "turdb_cuda_device_count", "turdb_cuda_index_create",
     "turdb_cuda_index_destroy", "turdb_cuda_index_info", "turdb_cuda_search_batch", "turdb_cuda_search_batch_device",
     "turdb_cuda_index_set_tuning", "turdb_cuda_index_profile_begin", "turdb_cuda_index_profile_read",
-    "turdb_cuda_bruteforce_topk", "turdb_cuda_bruteforce_topk_device",
+    "turdb_cuda_index_debug_counters", "turdb_cuda_bruteforce_topk", "turdb_cuda_bruteforce_topk_device",
     "turdb_cuda_merge_topk_device",
 ]
 
@@ -54,6 +54,7 @@ def load():
     L.turdb_cuda_index_destroy.argtypes = [vp]
     L.turdb_cuda_index_info.argtypes = [vp, pu64, pu32, pu32, pu32, pu64]
     L.turdb_cuda_index_set_tuning.argtypes = [vp, u32, u32, u32]
+    L.turdb_cuda_index_debug_counters.argtypes = [vp, i32, pu64]
     L.turdb_cuda_index_profile_begin.argtypes = [vp, u32]
     L.turdb_cuda_index_profile_read.argtypes = [vp, pf, pf, u32, pu32]
     L.turdb_cuda_search_batch.argtypes = [vp, pf, u32, u32, u32, u32, u8, pu64, pu64, pu32, pf, pu32,

@@ -81,20 +81,49 @@ __device__ __forceinline__ float quad_hsum(float2 acc) {
   return __fadd_rn(acc.x, acc.y);
 }
 
+// Packed FP32x2 math (Blackwell FADD2 / FFMA2): both halves are IEEE round-to-nearest, so each AVX
+// lane's chain is bit-identical to the scalar fmaf chain.
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ float2 unpack2(uint64_t v) {
+  float2 f;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(f.x), "=f"(f.y) : "l"(v));
+  return f;
+}
+
 // a, b: 8 B aligned float pointers (shared or global); p = lane & 3.  Returns squared L2.
 __device__ __forceinline__ float quad_l2sq(const float* a, const float* b, uint32_t dim, uint32_t p) {
-  const float2* av = reinterpret_cast<const float2*>(a) + p;
-  const float2* bv = reinterpret_cast<const float2*>(b) + p;
-  float2 acc = make_float2(0.f, 0.f);
+  const uint64_t* av = reinterpret_cast<const uint64_t*>(a) + p;
+  const uint64_t* bv = reinterpret_cast<const uint64_t*>(b) + p;
+  uint64_t acc = 0ull;
   const uint32_t steps = dim >> 3;
-#pragma unroll 4
-  for (uint32_t t = 0; t < steps; ++t) {
-    float2 x = av[4 * t], y = bv[4 * t];
-    float d0 = __fsub_rn(x.x, y.x), d1 = __fsub_rn(x.y, y.y);
-    acc.x = __fmaf_rn(d0, d0, acc.x);
-    acc.y = __fmaf_rn(d1, d1, acc.y);
+  uint32_t t = 0;
+  for (; t + 8 <= steps; t += 8, av += 32, bv += 32) {
+    uint64_t x[8], y[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      x[u] = av[4 * u];
+      y[u] = bv[4 * u];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const uint64_t d = sub2(x[u], y[u]);
+      acc = fma2(d, d, acc);
+    }
   }
-  float r = quad_hsum(acc);
+  for (; t < steps; ++t, av += 4, bv += 4) {
+    const uint64_t d = sub2(av[0], bv[0]);
+    acc = fma2(d, d, acc);
+  }
+  float r = quad_hsum(unpack2(acc));
   for (uint32_t i = steps << 3; i < dim; ++i) {  // unfused scalar tail, distance.rs:122-126
     float d = __fsub_rn(a[i], b[i]);
     r = __fadd_rn(r, __fmul_rn(d, d));
@@ -103,17 +132,23 @@ __device__ __forceinline__ float quad_l2sq(const float* a, const float* b, uint3
 }
 
 __device__ __forceinline__ float quad_dot(const float* a, const float* b, uint32_t dim, uint32_t p) {
-  const float2* av = reinterpret_cast<const float2*>(a) + p;
-  const float2* bv = reinterpret_cast<const float2*>(b) + p;
-  float2 acc = make_float2(0.f, 0.f);
+  const uint64_t* av = reinterpret_cast<const uint64_t*>(a) + p;
+  const uint64_t* bv = reinterpret_cast<const uint64_t*>(b) + p;
+  uint64_t acc = 0ull;
   const uint32_t steps = dim >> 3;
-#pragma unroll 4
-  for (uint32_t t = 0; t < steps; ++t) {
-    float2 x = av[4 * t], y = bv[4 * t];
-    acc.x = __fmaf_rn(x.x, y.x, acc.x);
-    acc.y = __fmaf_rn(x.y, y.y, acc.y);
+  uint32_t t = 0;
+  for (; t + 8 <= steps; t += 8, av += 32, bv += 32) {
+    uint64_t x[8], y[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      x[u] = av[4 * u];
+      y[u] = bv[4 * u];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc = fma2(x[u], y[u], acc);
   }
-  float r = quad_hsum(acc);
+  for (; t < steps; ++t, av += 4, bv += 4) acc = fma2(av[0], bv[0], acc);
+  float r = quad_hsum(unpack2(acc));
   for (uint32_t i = steps << 3; i < dim; ++i) r = __fadd_rn(r, __fmul_rn(a[i], b[i]));
   return r;
 }

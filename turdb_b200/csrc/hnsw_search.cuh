@@ -1,13 +1,20 @@
-// hnsw_search.cuh — the traversal kernel: greedy upper-level descent + level-0 beam search,
-// one warp per query (PersistentHnswIndex::search, src/hnsw/mod.rs:1092-1174;
-// greedy_search src/hnsw/search.rs:259-309; beam_search src/hnsw/search.rs:311-350).
+// hnsw_search.cuh — the traversal kernel: greedy upper-level descent + level-0 beam search
+// (PersistentHnswIndex::search, src/hnsw/mod.rs:1092-1174; greedy_search src/hnsw/search.rs:259-309;
+// beam_search src/hnsw/search.rs:311-350).
 //
-// Per hop the warp (1) picks the closest unexpanded entry of its sorted result list, (2) reads that
-// node's 32-wide adjacency row with one coalesced 128 B load, (3) filters it through an exact
-// visited set in shared memory, (4) gathers ALL unvisited neighbour vectors at once with one TMA
-// bulk copy each (cp.async.bulk -> shared memory, mbarrier completion), (5) reduces distances in
-// the reference's AVX2 lane order (bit-identical values), and (6) merges the <=32 new (distance,id)
-// pairs into the sorted ef-slot list by rank counting.
+// One CTA ("team" of W warps) owns one query at a time; CTAs are persistent and pull queries from an
+// atomic counter.  Warp 0 (the leader) runs the reference's control flow on one sorted ef-slot list;
+// per hop it
+//   (1) picks the closest unexpanded entry of the list (== candidates.pop() that passes d <= worst),
+//   (2) takes that node's 32-wide adjacency row (one coalesced 128 B load, usually already fetched
+//       speculatively during the previous hop),
+//   (3) filters it through an exact visited set in shared memory,
+// then ALL warps of the team
+//   (4) gather the unvisited neighbour vectors with one TMA bulk copy each (cp.async.bulk -> shared
+//       memory staging, mbarrier completion), chunks of 8 vectors dealt round-robin to the warps, and
+//   (5) reduce distances in the reference's AVX2 lane order (bit-identical values),
+// and the leader
+//   (6) merges the <=32 new (distance, id) pairs into the sorted list by rank counting.
 //
 // Single-list equivalence with the reference's two heaps: SURVEY.md Appendix D / DESIGN.md §5.
 #pragma once
@@ -16,10 +23,12 @@
 
 namespace turdb {
 
-struct WarpLayout {
-  uint32_t off_bar, off_q, off_list, off_tmp, off_hash, off_stage;
-  uint32_t warp_bytes;
-  uint32_t n_slots;    // staging slots (multiple of 8, <= 32)
+constexpr uint32_t kDone = 0xFFFFFFFFu;
+
+struct TeamLayout {
+  uint32_t off_bar, off_ctl, off_q, off_list, off_cand, off_hash, off_stage;
+  uint32_t team_bytes;
+  uint32_t n_groups;   // staging groups of 8 slots (1..4), one mbarrier each
   uint32_t stride;     // bytes between staging slots; stride/4 == 8 (mod 32) -> conflict-free quads
   uint32_t vec_bytes;  // ds * 4
   uint32_t hash_bits;  // shared visited table has 1 << hash_bits slots
@@ -32,7 +41,7 @@ struct WarpLayout {
 
 struct SearchArgs {
   DeviceIndex ix;
-  WarpLayout lay;
+  TeamLayout lay;
   const float* queries;  // [nq][dim]
   uint32_t nq, k, ef;
   uint64_t* out_row_ids;  // [nq][k]
@@ -41,65 +50,89 @@ struct SearchArgs {
   uint32_t* out_counts;   // [nq]
   uint32_t* out_stats;    // [nq][4] or null
   uint32_t* work_counter; // zeroed before launch
-  uint32_t* overflow_count;  // queries whose shared visited table filled up
+  uint32_t* overflow_count;  // queries whose shared visited table could not place a key
   uint32_t* overflow_list;   // [nq]
-  uint32_t* global_visited;  // fallback pass: [resident warps][vis_words] bitsets
+  uint32_t* global_visited;  // fallback pass: [CTAs][vis_words] bitsets
   uint32_t vis_words;
+  unsigned long long* dbg;   // optional [16] cycle counters (diagnostics), null in production
 };
 
-struct WarpCtx {
-  uint32_t lane;
-  uint32_t bar0;
-  const float* q;
+// Per-team shared state handed to every warp.
+struct Team {
+  uint32_t lane, warp, n_warps;
+  uint32_t bar0;             // shared address of mbarrier 0 (8 B apart)
+  volatile uint32_t* ctl;    // [0] = m of the current request or kDone, [1] = work item
+  const float* q;            // staged query
+  uint32_t* cand_ids;        // [32] ids whose distances are requested
+  float* cand_d;             // [32] results
   const uint8_t* stage;
   uint32_t stage_u32;
-  uint32_t stride, vec_bytes, n_slots;
-  uint32_t phases;
+  uint32_t stride, vec_bytes, n_groups;
+  uint32_t phases;           // per-warp parity bits of the groups this warp owns
   float qnorm;
+  uint32_t c_issue, c_wait, c_comp;  // diagnostics: cycles spent by this warp per phase
+  bool dbg;
 };
 
-// Distances from the query to the m vectors whose ids sit in lanes 0..m-1 (`cid`).
-// Returns d in lane j for id j; +inf in lanes >= m.
-//
-// The m vectors are gathered in chunks of 8 (one quad of lanes per vector).  Chunk c lands in staging
-// group c % G (G = n_slots / 8, one mbarrier per group); the first G chunks are requested up front and
-// group g is re-armed with chunk c + G as soon as chunk c has been reduced, so up to n_slots vectors
-// stay in flight for the whole hop.
+// Every warp of the team calls this between the two team barriers of a request: chunk c (candidates
+// 8c..8c+7) uses staging group c % G and is handled by warp (c % G) % W.  A warp first requests the
+// first chunk of each group it owns, then waits / reduces / re-arms in chunk order, so all of a hop's
+// vectors are in flight at once whenever the staging holds them.
 template <int METRIC>
-__device__ __forceinline__ float gather_distances(const DeviceIndex& ix, WarpCtx& w, uint32_t cid,
-                                                  uint32_t m) {
-  const uint32_t lane = w.lane, p = lane & 3, sub = lane & 7, my_chunk = lane >> 3;
-  const uint32_t G = w.n_slots >> 3;
+__device__ __forceinline__ void team_distances(const DeviceIndex& ix, Team& t, uint32_t m) {
+  const uint32_t lane = t.lane, p = lane & 3, G = t.n_groups, W = t.n_warps;
   const uint32_t nchunks = (m + 7) >> 3;
-  const bool have = lane < m;
-  const float* src = ix.arena + (size_t)(have ? cid : 0) * ix.ds;
-  float raw = 0.f, nb = 0.f;
-  if (METRIC == kCosine && have) nb = __ldg(ix.norm2 + cid);
-
   auto issue = [&](uint32_t c) {
     const uint32_t g = c % G;
-    const uint32_t bar = w.bar0 + 8 * g;
-    if (have && my_chunk == c && sub == 0) mbar_expect_tx(bar, min(8u, m - 8 * c) * w.vec_bytes);
+    const uint32_t bar = t.bar0 + 8 * g;
+    const uint32_t cnt = min(8u, m - 8 * c);
+    if (lane == 0) mbar_expect_tx(bar, cnt * t.vec_bytes);
     __syncwarp();
-    if (have && my_chunk == c) bulk_g2s(w.stage_u32 + (g * 8 + sub) * w.stride, src, w.vec_bytes, bar);
+    if (lane < cnt) {
+      const uint32_t id = t.cand_ids[8 * c + lane];
+      bulk_g2s(t.stage_u32 + (g * 8 + lane) * t.stride, ix.arena + (size_t)id * ix.ds, t.vec_bytes, bar);
+    }
   };
-  const uint32_t pro = min(G, nchunks);
-  for (uint32_t c = 0; c < pro; ++c) issue(c);
+  long long t0 = t.dbg ? clock64() : 0;
+  for (uint32_t c = 0; c < min(G, nchunks); ++c)
+    if ((c % G) % W == t.warp) issue(c);
+  if (t.dbg) {
+    long long t1 = clock64();
+    t.c_issue += (uint32_t)(t1 - t0);
+  }
   for (uint32_t c = 0; c < nchunks; ++c) {
     const uint32_t g = c % G;
-    mbar_wait(w.bar0 + 8 * g, (w.phases >> g) & 1u);
-    w.phases ^= (1u << g);
-    const float* b = reinterpret_cast<const float*>(w.stage + (g * 8 + (lane >> 2)) * w.stride);
-    const float r = (METRIC == kL2) ? quad_l2sq(w.q, b, ix.dim, p) : quad_dot(w.q, b, ix.dim, p);
-    const float t = __shfl_sync(kFullMask, r, sub * 4);
-    if (my_chunk == c) raw = t;
+    if (g % W != t.warp) continue;
+    const uint32_t slot = 8 * c + (lane >> 2);
+    float nb = 0.f;
+    if (METRIC == kCosine && slot < m) nb = __ldg(ix.norm2 + t.cand_ids[slot]);
+    long long w0 = t.dbg ? clock64() : 0;
+    mbar_wait(t.bar0 + 8 * g, (t.phases >> g) & 1u);
+    long long w1 = t.dbg ? clock64() : 0;
+    t.c_wait += (uint32_t)(w1 - w0);
+    t.phases ^= (1u << g);
+    const float* b = reinterpret_cast<const float*>(t.stage + (g * 8 + (lane >> 2)) * t.stride);
+    const float raw = (METRIC == kL2) ? quad_l2sq(t.q, b, ix.dim, p) : quad_dot(t.q, b, ix.dim, p);
+    if (p == 0 && slot < m) {
+      float d = raw;
+      if (METRIC == kIP) d = -raw;  // inner_product_avx2, distance.rs:240-242
+      if (METRIC == kCosine) d = cosine_finish(raw, t.qnorm, nb);
+      t.cand_d[slot] = d;
+    }
+    __syncwarp();
+    if (t.dbg) t.c_comp += (uint32_t)(clock64() - w1);
     if (c + G < nchunks) issue(c + G);
   }
-  __syncwarp();
-  if (!have) return INFINITY;
-  if (METRIC == kL2) return raw;
-  if (METRIC == kIP) return -raw;  // inner_product_avx2, distance.rs:240-242
-  return cosine_finish(raw, w.qnorm, nb);
+}
+
+// Leader side of a request: publish m, run the team's distance pass, return this lane's distance.
+template <int METRIC>
+__device__ __forceinline__ float leader_request(const DeviceIndex& ix, Team& t, uint32_t m) {
+  if (t.lane == 0) t.ctl[0] = m;
+  __syncthreads();
+  team_distances<METRIC>(ix, t, m);
+  __syncthreads();
+  return t.lane < m ? t.cand_d[t.lane] : INFINITY;
 }
 
 // Exact visited set.  Returns 1 = newly inserted, 0 = already present, 2 = table cannot place the key
@@ -109,7 +142,7 @@ __device__ __forceinline__ float gather_distances(const DeviceIndex& ix, WarpCtx
 //   shared, 16-bit entries: h = id * odd (mod 2^key_bits) is a bijection; home = top hash_bits of h, the
 //     entry stores the remaining rem_bits plus (displacement + 1), which together name h and so the id.
 template <bool GLOBAL>
-__device__ __forceinline__ uint32_t visited_insert(uint32_t* tab, uint32_t id, const WarpLayout& L) {
+__device__ __forceinline__ uint32_t visited_insert(uint32_t* tab, uint32_t id, const TeamLayout& L) {
   if (GLOBAL) {
     const uint32_t bit = 1u << (id & 31);
     return (atomicOr(tab + (id >> 5), bit) & bit) == 0 ? 1u : 0u;
@@ -138,82 +171,101 @@ __device__ __forceinline__ uint32_t visited_insert(uint32_t* tab, uint32_t id, c
 }
 
 template <int METRIC, bool GLOBAL_VISITED>
-__global__ void __launch_bounds__(256, 1) hnsw_search_kernel(const SearchArgs a) {
+__global__ void __launch_bounds__(128, 5) hnsw_search_kernel(const SearchArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const DeviceIndex& ix = a.ix;
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint8_t* ws = smem + (size_t)warp * a.lay.warp_bytes;
-  float* qs = reinterpret_cast<float*>(ws + a.lay.off_q);
-  float* A_d = reinterpret_cast<float*>(ws + a.lay.off_list);
+  const uint32_t tid = threadIdx.x, nthreads = blockDim.x;
+  const uint32_t lane = tid & 31, warp = tid >> 5;
+  float* qs = reinterpret_cast<float*>(smem + a.lay.off_q);
+  float* A_d = reinterpret_cast<float*>(smem + a.lay.off_list);
   uint32_t* A_id = reinterpret_cast<uint32_t*>(A_d + a.ef);
   float* B_d = reinterpret_cast<float*>(A_id + a.ef);
   uint32_t* B_id = reinterpret_cast<uint32_t*>(B_d + a.ef);
-  uint32_t* tmp_ids = reinterpret_cast<uint32_t*>(ws + a.lay.off_tmp);
-  uint32_t* tmp_ub = tmp_ids + 32;
-  uint32_t* vis = GLOBAL_VISITED
-                      ? a.global_visited + (size_t)(blockIdx.x * (blockDim.x >> 5) + warp) * a.vis_words
-                      : reinterpret_cast<uint32_t*>(ws + a.lay.off_hash);
+  uint32_t* cand_ids = reinterpret_cast<uint32_t*>(smem + a.lay.off_cand);
+  float* cand_d = reinterpret_cast<float*>(cand_ids + 32);
+  uint32_t* tmp_ub = cand_ids + 64;
+  uint32_t* vis = GLOBAL_VISITED ? a.global_visited + (size_t)blockIdx.x * a.vis_words
+                                 : reinterpret_cast<uint32_t*>(smem + a.lay.off_hash);
   const uint32_t hash_slots = 1u << a.lay.hash_bits;
   const uint32_t hash_limit = hash_slots - (hash_slots >> 3);  // 7/8 full -> overflow path
 
-  WarpCtx w;
-  w.lane = lane;
-  w.bar0 = smem_u32(ws + a.lay.off_bar);
-  w.q = qs;
-  w.stage = ws + a.lay.off_stage;
-  w.stage_u32 = smem_u32(w.stage);
-  w.stride = a.lay.stride;
-  w.vec_bytes = a.lay.vec_bytes;
-  w.n_slots = a.lay.n_slots;
-  w.phases = 0;
-  w.qnorm = 0.f;
+  Team t;
+  t.lane = lane;
+  t.warp = warp;
+  t.n_warps = nthreads >> 5;
+  t.bar0 = smem_u32(smem + a.lay.off_bar);
+  t.ctl = reinterpret_cast<volatile uint32_t*>(smem + a.lay.off_ctl);
+  t.q = qs;
+  t.cand_ids = cand_ids;
+  t.cand_d = cand_d;
+  t.stage = smem + a.lay.off_stage;
+  t.stage_u32 = smem_u32(t.stage);
+  t.stride = a.lay.stride;
+  t.vec_bytes = a.lay.vec_bytes;
+  t.n_groups = a.lay.n_groups;
+  t.phases = 0;
+  t.qnorm = 0.f;
+  t.c_issue = t.c_wait = t.c_comp = 0;
+  t.dbg = a.dbg != nullptr;
 
-  if (lane == 0) {
-    for (uint32_t g = 0; g < 4; ++g) mbar_init(w.bar0 + 8 * g, 1);
+  if (tid == 0) {
+    for (uint32_t g = 0; g < a.lay.n_groups; ++g) mbar_init(t.bar0 + 8 * g, 1);
     mbar_fence_init();
   }
-  __syncwarp();
+  __syncthreads();
 
   const uint32_t ef = a.ef;
   const uint32_t n_work = GLOBAL_VISITED ? *a.overflow_count : a.nq;
 
   for (;;) {
-    uint32_t wi = 0;
-    if (lane == 0) wi = atomicAdd(a.work_counter, 1u);
-    wi = __shfl_sync(kFullMask, wi, 0);
+    if (tid == 0) t.ctl[1] = atomicAdd(a.work_counter, 1u);
+    __syncthreads();
+    const uint32_t wi = t.ctl[1];
     if (wi >= n_work) break;
     const uint32_t qi = GLOBAL_VISITED ? a.overflow_list[wi] : wi;
 
-    // ---- stage the query, clear the visited set ----
+    // ---- stage the query, clear the visited set (whole team) ----
     const float* qg = a.queries + (size_t)qi * ix.dim;
-    for (uint32_t i = lane; i < ix.ds; i += 32) qs[i] = i < ix.dim ? __ldg(qg + i) : 0.f;
-    if (GLOBAL_VISITED) {
+    for (uint32_t i = tid; i < ix.ds; i += nthreads) qs[i] = i < ix.dim ? __ldg(qg + i) : 0.f;
+    {
       uint4* v4 = reinterpret_cast<uint4*>(vis);
-      for (uint32_t i = lane; i < (a.vis_words >> 2); i += 32) v4[i] = make_uint4(0, 0, 0, 0);
-    } else if (a.lay.hash16) {
-      uint4* v4 = reinterpret_cast<uint4*>(vis);
-      for (uint32_t i = lane; i < (hash_slots >> 3); i += 32) v4[i] = make_uint4(0, 0, 0, 0);
-    } else {
-      uint4* v4 = reinterpret_cast<uint4*>(vis);
-      for (uint32_t i = lane; i < (hash_slots >> 2); i += 32)
-        v4[i] = make_uint4(kInvalid, kInvalid, kInvalid, kInvalid);
+      const uint32_t n16 = GLOBAL_VISITED ? (a.vis_words >> 2) : (a.lay.hash16 ? (hash_slots >> 3) : (hash_slots >> 2));
+      const uint32_t fill = (GLOBAL_VISITED || a.lay.hash16) ? 0u : kInvalid;
+      for (uint32_t i = tid; i < n16; i += nthreads) v4[i] = make_uint4(fill, fill, fill, fill);
     }
-    __syncwarp();
-    if (METRIC == kCosine) w.qnorm = quad_dot(qs, qs, ix.dim, lane & 3);
+    __syncthreads();
+    if (METRIC == kCosine) t.qnorm = quad_dot(qs, qs, ix.dim, lane & 3);
 
+    if (warp != 0) {
+      // ---- helper warps: serve distance requests until the leader is done with this query ----
+      for (;;) {
+        __syncthreads();
+        const uint32_t m = t.ctl[0];
+        if (m == kDone) break;
+        team_distances<METRIC>(ix, t, m);
+        __syncthreads();
+      }
+      continue;
+    }
+
+    // ---- leader warp ----
+    const long long q_t0 = t.dbg ? clock64() : 0;
+    long long l0_t0 = 0;
+    uint32_t c_sel = 0, c_adj = 0, c_req = 0, c_mrg = 0, n_hops = 0, n_spec = 0;
+    t.c_issue = t.c_wait = t.c_comp = 0;
     uint32_t n_dist = 0, n_dist_upper = 0, n_expanded = 0, n_upper_hops = 0;
     uint32_t len = 0;
     bool overflow = false;
 
     if (ix.entry != kInvalid && ix.n != 0) {
-      // ---- entry distance (mod.rs:1129) ----
+      // entry distance (mod.rs:1129)
       uint32_t cur = ix.entry;
-      float cur_d = gather_distances<METRIC>(ix, w, lane == 0 ? cur : kInvalid, 1);
-      cur_d = __shfl_sync(kFullMask, cur_d, 0);
+      if (lane == 0) cand_ids[0] = cur;
+      float cur_d = __shfl_sync(kFullMask, leader_request<METRIC>(ix, t, 1), 0);
       n_dist = 1;
       n_dist_upper = 1;
 
-      // ---- greedy descent over levels max_level..1 (mod.rs:1134-1145, search.rs:259-309) ----
+      // greedy descent over levels max_level..1 (mod.rs:1134-1145, search.rs:259-309)
       for (uint32_t level = ix.max_level; level >= 1; --level) {
         for (uint32_t it = 0; it < 1000; ++it) {
           const uint32_t lv = ix.levels[cur];
@@ -224,7 +276,8 @@ __global__ void __launch_bounds__(256, 1) hnsw_search_kernel(const SearchArgs a)
           n_upper_hops += 1;
           const uint32_t m = __popc(__ballot_sync(kFullMask, nid != kInvalid));
           if (m == 0) break;
-          float d = gather_distances<METRIC>(ix, w, nid, m);
+          if (lane < m) cand_ids[lane] = nid;
+          const float d = leader_request<METRIC>(ix, t, m);
           n_dist += m;
           n_dist_upper += m;
           // arg-min, strict `<`, first stored neighbour wins ties (search.rs:272-277)
@@ -232,8 +285,8 @@ __global__ void __launch_bounds__(256, 1) hnsw_search_kernel(const SearchArgs a)
           uint32_t bl = lane;
 #pragma unroll
           for (uint32_t off = 16; off >= 1; off >>= 1) {
-            float od = __shfl_xor_sync(kFullMask, best, off);
-            uint32_t ol = __shfl_xor_sync(kFullMask, bl, off);
+            const float od = __shfl_xor_sync(kFullMask, best, off);
+            const uint32_t ol = __shfl_xor_sync(kFullMask, bl, off);
             if (od < best || (od == best && ol < bl)) {
               best = od;
               bl = ol;
@@ -245,7 +298,7 @@ __global__ void __launch_bounds__(256, 1) hnsw_search_kernel(const SearchArgs a)
         }
       }
 
-      // ---- level-0 beam search (search.rs:311-350) on one sorted list ----
+      // level-0 beam search (search.rs:311-350) on one sorted list
       if (lane == 0) {
         A_d[0] = cur_d;
         A_id[0] = cur;
@@ -255,8 +308,10 @@ __global__ void __launch_bounds__(256, 1) hnsw_search_kernel(const SearchArgs a)
       uint32_t n_visited = 1;
       uint32_t spec_node = kInvalid, spec_nid = kInvalid;  // speculatively fetched adjacency row
       __syncwarp();
+      if (t.dbg) l0_t0 = clock64();
 
       for (;;) {
+        const long long h0 = t.dbg ? clock64() : 0;
         // closest unexpanded entry == the reference's candidates.pop() that passes `d <= worst`;
         // the runner-up is the likely next hop: its adjacency row is fetched while this hop gathers.
         uint32_t i1 = 0xFFFFFFFFu, i2 = 0xFFFFFFFFu;
@@ -277,6 +332,8 @@ __global__ void __launch_bounds__(256, 1) hnsw_search_kernel(const SearchArgs a)
         if (lane == 0) A_id[idx] = c | kExpandedBit;
         __syncwarp();
         n_expanded += 1;
+        const long long h1 = t.dbg ? clock64() : 0;
+        if (t.dbg && c == spec_node) n_spec += 1;
 
         if (!GLOBAL_VISITED && n_visited + kL0 > hash_limit) {
           overflow = true;
@@ -299,11 +356,18 @@ __global__ void __launch_bounds__(256, 1) hnsw_search_kernel(const SearchArgs a)
         const uint32_t m = __popc(newmask);
         if (m == 0) continue;
         n_visited += m;
-        // compact to lanes 0..m-1 in stored order
-        if (isnew) tmp_ids[__popc(newmask & ((1u << lane) - 1))] = nid;
-        __syncwarp();
-        const uint32_t cid = lane < m ? tmp_ids[lane] : kInvalid;
-        const float d = gather_distances<METRIC>(ix, w, cid, m);
+        // compact to slots 0..m-1 in stored order
+        if (isnew) cand_ids[__popc(newmask & ((1u << lane) - 1))] = nid;
+        const long long h2 = t.dbg ? clock64() : 0;
+        const float d = leader_request<METRIC>(ix, t, m);
+        const long long h3 = t.dbg ? clock64() : 0;
+        if (t.dbg) {
+          c_sel += (uint32_t)(h1 - h0);
+          c_adj += (uint32_t)(h2 - h1);
+          c_req += (uint32_t)(h3 - h2);
+          n_hops += 1;
+        }
+        const uint32_t cid = lane < m ? cand_ids[lane] : kInvalid;
         n_dist += m;
 
         // admission (search.rs:344): d < worst || results.len() < ef, applied to the batch
@@ -318,7 +382,7 @@ __global__ void __launch_bounds__(256, 1) hnsw_search_kernel(const SearchArgs a)
         if (elig) {
           uint32_t lo = 0, hi = len;
           while (lo < hi) {
-            uint32_t mid = (lo + hi) >> 1;
+            const uint32_t mid = (lo + hi) >> 1;
             if (A_d[mid] <= d) lo = mid + 1;
             else hi = mid;
           }
@@ -353,11 +417,31 @@ __global__ void __launch_bounds__(256, 1) hnsw_search_kernel(const SearchArgs a)
         float* td = A_d; A_d = B_d; B_d = td;
         uint32_t* ti = A_id; A_id = B_id; B_id = ti;
         __syncwarp();
+        if (t.dbg) c_mrg += (uint32_t)(clock64() - h3);
       }
     }
+    if (t.dbg && lane == 0) {
+      const long long q_t1 = clock64();
+      atomicAdd(a.dbg + 0, (unsigned long long)n_hops);
+      atomicAdd(a.dbg + 1, (unsigned long long)c_sel);
+      atomicAdd(a.dbg + 2, (unsigned long long)c_adj);
+      atomicAdd(a.dbg + 3, (unsigned long long)c_req);
+      atomicAdd(a.dbg + 4, (unsigned long long)c_mrg);
+      atomicAdd(a.dbg + 5, (unsigned long long)t.c_wait);
+      atomicAdd(a.dbg + 6, (unsigned long long)t.c_issue);
+      atomicAdd(a.dbg + 7, (unsigned long long)t.c_comp);
+      atomicAdd(a.dbg + 8, (unsigned long long)n_spec);
+      atomicAdd(a.dbg + 9, (unsigned long long)(q_t1 - q_t0));
+      atomicAdd(a.dbg + 10, (unsigned long long)(l0_t0 - q_t0));
+      atomicAdd(a.dbg + 11, 1ull);
+    }
+
+    // release the helper warps
+    if (lane == 0) t.ctl[0] = kDone;
+    __syncthreads();
 
     if (overflow) {
-      // shared visited table filled: hand the query to the global-bitset pass (exact, rare)
+      // shared visited table cannot take more keys: hand the query to the global-bitset pass (exact, rare)
       if (lane == 0) a.overflow_list[atomicAdd(a.overflow_count, 1u)] = qi;
       continue;
     }
@@ -387,7 +471,6 @@ __global__ void __launch_bounds__(256, 1) hnsw_search_kernel(const SearchArgs a)
         s[3] = n_upper_hops;
       }
     }
-    __syncwarp();
   }
 }
 

@@ -70,6 +70,7 @@ struct turdb_cuda_index {
   // profiling ring: 3 events per call (before main, after main, after overflow pass)
   std::vector<cudaEvent_t> prof_events;
   uint32_t prof_capacity = 0, prof_used = 0;
+  unsigned long long* d_dbg = nullptr;  // diagnostics: per-phase cycle counters of the traversal kernel
   std::mutex mu;
 };
 
@@ -141,6 +142,7 @@ int32_t turdb_cuda_index_destroy(turdb_cuda_index* idx) {
     cudaFree(idx->d_levels);
     cudaFree(idx->d_arena_bf16);
     for (cudaEvent_t ev : idx->prof_events) cudaEventDestroy(ev);
+    cudaFree(idx->d_dbg);
     if (idx->pool) cudaMemPoolDestroy(idx->pool);
   }
   delete idx;
@@ -296,13 +298,32 @@ int32_t turdb_cuda_index_info(const turdb_cuda_index* idx, uint64_t* n, uint32_t
 int32_t turdb_cuda_index_set_tuning(turdb_cuda_index* idx, uint32_t warps_per_cta, uint32_t staging_slots,
                                     uint32_t hash_bits) {
   if (!idx) return fail(TURDB_ERR_INVALID_ARGUMENT, "idx is null");
-  if (warps_per_cta > 8) return fail(TURDB_ERR_INVALID_ARGUMENT, "warps_per_cta must be <= 8");
+  if (warps_per_cta > 4) return fail(TURDB_ERR_INVALID_ARGUMENT, "warps_per_cta must be <= 4");
   if (staging_slots > 32 || (staging_slots & 7)) return fail(TURDB_ERR_INVALID_ARGUMENT, "staging_slots must be 0, 8, 16, 24 or 32");
   if (hash_bits != 0 && (hash_bits < 8 || hash_bits > 15)) return fail(TURDB_ERR_INVALID_ARGUMENT, "hash_bits must be 0 or 8..15");
   std::lock_guard<std::mutex> lk(idx->mu);
   idx->tune_warps = warps_per_cta;
   idx->tune_slots = staging_slots;
   idx->tune_hash_bits = hash_bits;
+  return TURDB_OK;
+}
+
+int32_t turdb_cuda_index_debug_counters(turdb_cuda_index* idx, int32_t enable, uint64_t* out16) {
+  if (!idx) return fail(TURDB_ERR_INVALID_ARGUMENT, "idx is null");
+  DeviceGuard guard(idx->device);
+  std::lock_guard<std::mutex> lk(idx->mu);
+  if (out16 && idx->d_dbg) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(out16, idx->d_dbg, 16 * 8, cudaMemcpyDeviceToHost));
+  } else if (out16) {
+    memset(out16, 0, 16 * 8);
+  }
+  if (enable && !idx->d_dbg) CUDA_TRY(cudaMalloc(&idx->d_dbg, 16 * 8));
+  if (enable) CUDA_TRY(cudaMemset(idx->d_dbg, 0, 16 * 8));
+  if (!enable && idx->d_dbg) {
+    cudaFree(idx->d_dbg);
+    idx->d_dbg = nullptr;
+  }
   return TURDB_OK;
 }
 
@@ -345,26 +366,27 @@ int32_t turdb_cuda_index_profile_read(turdb_cuda_index* idx, float* main_ms, flo
 // ------------------------------------------------------------------------------------------
 // traversal launch
 // ------------------------------------------------------------------------------------------
-static WarpLayout make_layout(uint32_t ds, uint32_t ef, uint32_t hash_bits, uint32_t n_slots, bool global_visited,
+static TeamLayout make_layout(uint32_t ds, uint32_t ef, uint32_t hash_bits, uint32_t n_slots, bool global_visited,
                               uint64_t n_nodes) {
-  WarpLayout L{};
+  TeamLayout L{};
   L.vec_bytes = ds * 4;
   const uint32_t pad_words = (8 + 32 - (ds & 31)) & 31;
   L.stride = (ds + pad_words) * 4;
   L.hash_bits = hash_bits;
-  L.n_slots = n_slots;
+  L.n_groups = n_slots / 8;
   L.key_bits = std::max(hash_bits, ceil_log2((uint32_t)std::max<uint64_t>(n_nodes, 2)));
   L.rem_bits = L.key_bits - hash_bits;
   L.hash16 = (!global_visited && L.rem_bits <= 11) ? 1u : 0u;  // displacement field >= 5 bits
   uint32_t off = 0;
-  L.off_bar = off;   off += 64;
+  L.off_bar = off;   off += 32;
+  L.off_ctl = off;   off += 32;
   L.off_q = off;     off += (ds * 4 + 15) & ~15u;
   L.off_list = off;  off += ef * 16;
-  L.off_tmp = off;   off += 256;
+  L.off_cand = off;  off += 384;  // cand_ids[32], cand_d[32], tmp_ub[32]
   L.off_hash = off;  off += global_visited ? 0 : ((L.hash16 ? 2u : 4u) << hash_bits);
   off = (off + 127) & ~127u;
   L.off_stage = off; off += n_slots * L.stride;
-  L.warp_bytes = (off + 127) & ~127u;
+  L.team_bytes = (off + 127) & ~127u;
   return L;
 }
 
@@ -372,7 +394,7 @@ template <int METRIC, bool GV>
 static cudaError_t launch_search(const SearchArgs& a, uint32_t warps, int num_sms, uint32_t max_ctas,
                                  cudaStream_t stream, uint32_t* resident_warps) {
   auto kern = hnsw_search_kernel<METRIC, GV>;
-  const size_t smem = (size_t)a.lay.warp_bytes * warps;
+  const size_t smem = (size_t)a.lay.team_bytes;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int occ = 0;
@@ -382,7 +404,7 @@ static cudaError_t launch_search(const SearchArgs& a, uint32_t warps, int num_sm
   uint32_t grid = (uint32_t)occ * num_sms;
   if (max_ctas && grid > max_ctas) grid = max_ctas;
   if (grid < 1) grid = 1;
-  if (resident_warps) *resident_warps = grid * warps;
+  if (resident_warps) *resident_warps = grid;
   kern<<<grid, 32 * warps, smem, stream>>>(a);
   return cudaGetLastError();
 }
@@ -446,7 +468,7 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
   }
   const uint32_t ds = idx->ix.ds;
   uint32_t hash_bits = th ? th : std::min(15u, std::max(9u, ceil_log2(ef * 64)));
-  uint32_t warps = tw ? tw : 1;
+  const uint32_t warps = tw ? std::min(tw, 4u) : 4u;  // team size: warps cooperating on one query
   const uint32_t budget = (uint32_t)idx->max_smem_optin;
   const uint64_t nn = idx->ix.n;
   uint32_t slots = ts;
@@ -456,9 +478,9 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
     const uint32_t sm_bytes = budget + 1024;
     uint32_t best = 0;
     for (uint32_t cand = 8; cand <= 32; cand += 8) {
-      WarpLayout L = make_layout(ds, ef, hash_bits, cand, false, nn);
-      if (L.warp_bytes > budget) break;
-      uint32_t occ = std::min(32u, sm_bytes / (L.warp_bytes + 1024));
+      TeamLayout L = make_layout(ds, ef, hash_bits, cand, false, nn);
+      if (L.team_bytes > budget) break;
+      uint32_t occ = std::min(16u, sm_bytes / (L.team_bytes + 1024));
       uint32_t score = occ * std::min(cand, 24u);
       if (score >= best) {
         best = score;
@@ -467,12 +489,11 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
     }
     if (!slots) slots = 8;
   }
-  WarpLayout lay = make_layout(ds, ef, hash_bits, slots, false, nn);
-  while (lay.warp_bytes * warps > budget && warps > 1) --warps;
-  while (lay.warp_bytes > budget && lay.n_slots > 8) lay = make_layout(ds, ef, hash_bits, lay.n_slots - 8, false, nn);
-  while (lay.warp_bytes > budget && hash_bits > 8) lay = make_layout(ds, ef, --hash_bits, lay.n_slots, false, nn);
-  if (lay.warp_bytes > budget)
-    return fail(TURDB_ERR_UNSUPPORTED, "dim %u / ef %u need %u B of shared memory per query (> %u)", idx->ix.dim, ef, lay.warp_bytes, budget);
+  TeamLayout lay = make_layout(ds, ef, hash_bits, slots, false, nn);
+  while (lay.team_bytes > budget && lay.n_groups > 1) lay = make_layout(ds, ef, hash_bits, lay.n_groups * 8 - 8, false, nn);
+  while (lay.team_bytes > budget && hash_bits > 8) lay = make_layout(ds, ef, --hash_bits, lay.n_groups * 8, false, nn);
+  if (lay.team_bytes > budget)
+    return fail(TURDB_ERR_UNSUPPORTED, "dim %u / ef %u need %u B of shared memory per query (> %u)", idx->ix.dim, ef, lay.team_bytes, budget);
 
   uint32_t* d_scratch = nullptr;  // [0] work counter, [1] overflow count, [2] fallback work counter, [4..] overflow list
   CUDA_TRY(cudaMallocFromPoolAsync(&d_scratch, (size_t)(4 + nq) * 4, idx->pool, stream));
@@ -495,13 +516,14 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
   a.overflow_list = d_scratch + 4;
   a.global_visited = nullptr;
   a.vis_words = 0;
+  a.dbg = idx->d_dbg;
   cudaEvent_t* pev = nullptr;
   {
     std::lock_guard<std::mutex> lk(idx->mu);
     if (idx->prof_used < idx->prof_capacity) pev = &idx->prof_events[3 * idx->prof_used++];
   }
   if (pev) cudaEventRecord(pev[0], stream);
-  cudaError_t e = launch_metric<false>(metric, a, warps, idx->num_sms, (nq + warps - 1) / warps, stream, nullptr);
+  cudaError_t e = launch_metric<false>(metric, a, warps, idx->num_sms, nq, stream, nullptr);
   if (pev) cudaEventRecord(pev[1], stream);
   if (e != cudaSuccess) {
     cudaFreeAsync(d_scratch, stream);
@@ -511,7 +533,7 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
   // exact fallback for queries whose shared visited table filled: same kernel, one bit per node in
   // global memory.  Always enqueued (no host sync); exits immediately when the list is empty.
   {
-    WarpLayout glay = make_layout(ds, ef, 8, lay.n_slots, true, nn);
+    TeamLayout glay = make_layout(ds, ef, 8, lay.n_groups * 8, true, nn);
     SearchArgs b = a;
     b.lay = glay;
     b.work_counter = d_scratch + 2;
@@ -521,7 +543,7 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
     e = cudaMallocFromPoolAsync(&d_gv, (size_t)fb_ctas * b.vis_words * 4, idx->pool, stream);
     if (e == cudaSuccess) {
       b.global_visited = d_gv;
-      e = launch_metric<true>(metric, b, 1, idx->num_sms, fb_ctas, stream, nullptr);
+      e = launch_metric<true>(metric, b, warps, idx->num_sms, fb_ctas, stream, nullptr);
       if (pev) cudaEventRecord(pev[2], stream);
       cudaFreeAsync(d_gv, stream);
     }

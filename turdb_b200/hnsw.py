@@ -151,6 +151,12 @@ class CudaHnswIndex:
     def set_tuning(self, warps_per_cta: int = 0, staging_slots: int = 0, hash_bits: int = 0):
         _check(_lib.load().turdb_cuda_index_set_tuning(self._h, warps_per_cta, staging_slots, hash_bits))
 
+    def debug_counters(self, enable: bool = True):
+        """Diagnostics: returns the 16 per-phase cycle counters accumulated so far and (re)arms or disarms them."""
+        out = np.zeros(16, np.uint64)
+        _check(_lib.load().turdb_cuda_index_debug_counters(self._h, 1 if enable else 0, _ptr(out, C.c_uint64)))
+        return out
+
     def profile_begin(self, capacity: int):
         _check(_lib.load().turdb_cuda_index_profile_begin(self._h, capacity))
 
