@@ -191,6 +191,7 @@ def main():
     from turdb_b200 import _lib
     from turdb_b200.graph_build import build_graph
     from turdb_b200.hnsw import CudaHnswIndex, DistanceFunction, merge_topk_device
+    from turdb_b200.sharding import ShardedSearch
 
     _lib.load()  # fail loudly if the CUDA library is missing
     torch.cuda.set_device(local_rank)
@@ -218,25 +219,26 @@ def main():
     nodes = torch.empty((nq, k), dtype=torch.int32, device=dev)
     cnt = torch.empty(nq, dtype=torch.int32, device=dev)
     stats = torch.empty((nq, 4), dtype=torch.int32, device=dev)
-    if world > 1:
-        g_rows = torch.empty((world, nq, k), dtype=torch.int64, device=dev)
-        g_dd = torch.empty((world, nq, k), dtype=torch.float32, device=dev)
-        g_cnt = torch.empty((world, nq), dtype=torch.int32, device=dev)
-        m_rows = torch.empty((nq, k), dtype=torch.int64, device=dev)
-        m_dd = torch.empty((nq, k), dtype=torch.float32, device=dev)
-        m_cnt = torch.empty(nq, dtype=torch.int32, device=dev)
+    m_rows = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    m_dd = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    m_cnt = torch.empty(nq, dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
     launches_per_step = 2 + (1 if world > 1 else 0)  # traversal + overflow pass (+ merge)
 
-    def step(i):
-        idx.search_batch_device(dq[i % nb].data_ptr(), nq, k, ef, DistanceFunction.Cosine, rows.data_ptr(),
+    def local_search(dq_batch):
+        idx.search_batch_device(dq_batch.data_ptr(), nq, k, ef, DistanceFunction.Cosine, rows.data_ptr(),
                                 dd.data_ptr(), cnt.data_ptr(), nodes.data_ptr(), stats.data_ptr(), 0, stream)
-        if world > 1:
-            dist.all_gather_into_tensor(g_rows, rows)
-            dist.all_gather_into_tensor(g_dd, dd)
-            dist.all_gather_into_tensor(g_cnt, cnt)
-            merge_topk_device(local_rank, g_rows.data_ptr(), g_dd.data_ptr(), g_cnt.data_ptr(), world, nq, k,
-                              m_rows.data_ptr(), m_dd.data_ptr(), m_cnt.data_ptr(), stream)
+        return rows, dd, cnt
+
+    def merge(g_rows, g_dd, g_cnt):
+        merge_topk_device(local_rank, g_rows.data_ptr(), g_dd.data_ptr(), g_cnt.data_ptr(), world, nq, k,
+                          m_rows.data_ptr(), m_dd.data_ptr(), m_cnt.data_ptr(), stream)
+        return m_rows, m_dd, m_cnt
+
+    sharded = ShardedSearch(dist, world, local_search, merge)
+
+    def step(i):
+        sharded.search_batch(dq[i % nb])
 
     def barrier():
         if world > 1:
@@ -303,14 +305,11 @@ def main():
             rows.copy_(h_rows, non_blocking=True)
             dd.copy_(h_dd, non_blocking=True)
             cnt.copy_(h_cnt, non_blocking=True)
-            dist.all_gather_into_tensor(g_rows, rows)
-            dist.all_gather_into_tensor(g_dd, dd)
-            dist.all_gather_into_tensor(g_cnt, cnt)
-            merge_topk_device(local_rank, g_rows.data_ptr(), g_dd.data_ptr(), g_cnt.data_ptr(), world, nq, k,
-                              m_rows.data_ptr(), m_dd.data_ptr(), m_cnt.data_ptr(), stream)
+            e2e_sharded.search_batch(None)
             h_rows.copy_(m_rows, non_blocking=True)
             torch.cuda.synchronize()
 
+    e2e_sharded = ShardedSearch(dist, world, lambda _q: (rows, dd, cnt), merge)
     for i in range(args.warmup):
         e2e_step(i)
     barrier()
