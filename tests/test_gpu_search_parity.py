@@ -146,3 +146,23 @@ def test_tunings_do_not_change_results(gpu_required, small_graph, slots, warps):
     same_ids, same_dist = compare(gpu, cpu, 10)
     assert same_ids.mean() >= 0.999 and same_dist.mean() >= 0.999
     idx.close()
+
+
+def test_duplicate_neighbours_in_a_row(gpu_required):
+    """A row that repeats an id: the reference's visited set skips the repeat (search.rs:338); the index
+    de-duplicates rows at upload.  Results and counters must agree."""
+    x = ds.gaussian_latent(2000, 32, seed=11)
+    q = ds.gaussian_latent(100, 32, seed=12)
+    a = ob.OracleGraph.build(x, seed=4).export()
+    for i in range(0, 2000, 7):
+        if a["l0_cnt"][i] >= 4:
+            a["l0_adj"][i][3] = a["l0_adj"][i][0]
+            a["l0_adj"][i][1] = a["l0_adj"][i][0]
+    g = ob.OracleGraph.from_arrays(a)
+    idx = CudaHnswIndex.from_graph(a)
+    gpu = idx.search_batch(q, 10, 48)
+    cpu = g.search(q, 10, 48)
+    same_ids, same_dist = compare(gpu, cpu, 10)
+    assert same_ids.all() and same_dist.all()
+    assert np.array_equal(gpu[4], cpu[4])
+    idx.close()

@@ -73,6 +73,11 @@ def test_merge_topk_host_orders_by_distance_then_row():
     cnt = np.array([[2], [2]], np.uint32)
     r, d, c = merge_topk_host(rows, dist, cnt, 3)
     assert r[0].tolist() == [5, 7, 2] and c[0] == 3
+    # lists are consumed in their given order: a tie inside one shard is not re-sorted by row id
+    rows = np.array([[[9, 5]], [[7, 7]]], np.uint64)
+    dist = np.array([[[1.0, 1.0]], [[1.0, 2.0]]], np.float32)
+    r, d, c = merge_topk_host(rows, dist, np.array([[2], [2]], np.uint32), 3)
+    assert r[0].tolist() == [7, 9, 5]
     assert shard_bounds(10, 3, 0) == (0, 3) and shard_bounds(10, 3, 2) == (6, 10)
 
 

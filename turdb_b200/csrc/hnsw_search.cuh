@@ -135,39 +135,84 @@ __device__ __forceinline__ float leader_request(const DeviceIndex& ix, Team& t, 
   return t.lane < m ? t.cand_d[t.lane] : INFINITY;
 }
 
-// Exact visited set.  Returns 1 = newly inserted, 0 = already present, 2 = table cannot place the key
+// Exact visited set, called by all 32 lanes of the leader with one (distinct) id per active lane.
+// Returns 1 = newly inserted, 0 = already present (or inactive lane), 2 = table cannot place the key
 // (the query is then redone by the global-bitset pass).
-//   GLOBAL : one bit per node in global memory.
-//   shared, 32-bit entries: open addressing on the full id.
-//   shared, 16-bit entries: h = id * odd (mod 2^key_bits) is a bijection; home = top hash_bits of h, the
-//     entry stores the remaining rem_bits plus (displacement + 1), which together name h and so the id.
+//   GLOBAL : one bit per node in global memory (atomicOr).
+//   shared : open addressing, linear probing, no atomics: only this warp touches the table, so a round is
+//            "read slot; if empty write my entry; re-read: did my write survive?".  All reads of a round
+//            precede its writes (same instruction), and rows never repeat an id (deduplicated at upload), so
+//            two lanes can only collide with DIFFERENT entries and the loser simply probes on.
+//     32-bit entries hold the id.  16-bit entries: h = id * odd (mod 2^key_bits) is a bijection; home = top
+//     hash_bits of h; the entry stores the low rem_bits of h plus (displacement + 1), which together name h
+//     and therefore the id — an exact set in half the bytes.
 template <bool GLOBAL>
-__device__ __forceinline__ uint32_t visited_insert(uint32_t* tab, uint32_t id, const TeamLayout& L) {
+__device__ __forceinline__ uint32_t visited_insert(uint32_t* tab, uint32_t id, bool active, const TeamLayout& L) {
   if (GLOBAL) {
+    if (!active) return 0u;
     const uint32_t bit = 1u << (id & 31);
     return (atomicOr(tab + (id >> 5), bit) & bit) == 0 ? 1u : 0u;
   }
   const uint32_t mask = (1u << L.hash_bits) - 1;
+  constexpr uint32_t kPending = 3u;
+  uint32_t res = active ? kPending : 0u;
   if (L.hash16) {
-    unsigned short* t16 = reinterpret_cast<unsigned short*>(tab);
+    volatile unsigned short* t16 = reinterpret_cast<volatile unsigned short*>(tab);
     const uint32_t h = (id * 0x9E3779B1u) & ((1u << L.key_bits) - 1);
     const uint32_t home = h >> L.rem_bits, rem = h & ((1u << L.rem_bits) - 1);
     const uint32_t max_disp = (1u << (16 - L.rem_bits)) - 1;  // displacement+1 must fit
-    for (uint32_t disp = 0; disp < max_disp; ++disp) {
-      const unsigned short want = (unsigned short)(((disp + 1) << L.rem_bits) | rem);
-      const unsigned short old = atomicCAS(t16 + ((home + disp) & mask), (unsigned short)0, want);
-      if (old == 0) return 1u;
-      if (old == want) return 0u;
+    uint32_t disp = 0;
+    while (__any_sync(kFullMask, res == kPending)) {
+      bool wrote = false;
+      uint32_t slot = 0;
+      unsigned short want = 0;
+      if (res == kPending) {
+        if (disp >= max_disp) {
+          res = 2u;
+        } else {
+          slot = (home + disp) & mask;
+          want = (unsigned short)(((disp + 1) << L.rem_bits) | rem);
+          const unsigned short e = t16[slot];
+          if (e == want) res = 0u;
+          else if (e == 0) {
+            t16[slot] = want;
+            wrote = true;
+          } else {
+            ++disp;
+          }
+        }
+      }
+      __syncwarp();
+      if (wrote) {
+        if (t16[slot] == want) res = 1u;
+        else ++disp;
+      }
+      __syncwarp();
     }
-    return 2u;
+    return res;
   }
+  volatile uint32_t* t32 = tab;
   uint32_t slot = (id * 0x9E3779B1u) >> (32 - L.hash_bits);
-  for (;;) {
-    const uint32_t old = atomicCAS(tab + slot, kInvalid, id);
-    if (old == kInvalid) return 1u;
-    if (old == id) return 0u;
-    slot = (slot + 1) & mask;
+  while (__any_sync(kFullMask, res == kPending)) {
+    bool wrote = false;
+    if (res == kPending) {
+      const uint32_t e = t32[slot];
+      if (e == id) res = 0u;
+      else if (e == kInvalid) {
+        t32[slot] = id;
+        wrote = true;
+      } else {
+        slot = (slot + 1) & mask;
+      }
+    }
+    __syncwarp();
+    if (wrote) {
+      if (t32[slot] == id) res = 1u;
+      else slot = (slot + 1) & mask;
+    }
+    __syncwarp();
   }
+  return res;
 }
 
 template <int METRIC, bool GLOBAL_VISITED>
@@ -302,11 +347,12 @@ __global__ void __launch_bounds__(128, 5) hnsw_search_kernel(const SearchArgs a)
       if (lane == 0) {
         A_d[0] = cur_d;
         A_id[0] = cur;
-        (void)visited_insert<GLOBAL_VISITED>(vis, cur, a.lay);
       }
+      (void)visited_insert<GLOBAL_VISITED>(vis, cur, lane == 0, a.lay);
       len = 1;
       uint32_t n_visited = 1;
       uint32_t spec_node = kInvalid, spec_nid = kInvalid;  // speculatively fetched adjacency row
+      uint32_t scan_from = 0;                               // list entries below this index are expanded
       __syncwarp();
       if (t.dbg) l0_t0 = clock64();
 
@@ -314,18 +360,19 @@ __global__ void __launch_bounds__(128, 5) hnsw_search_kernel(const SearchArgs a)
         const long long h0 = t.dbg ? clock64() : 0;
         // closest unexpanded entry == the reference's candidates.pop() that passes `d <= worst`;
         // the runner-up is the likely next hop: its adjacency row is fetched while this hop gathers.
-        uint32_t i1 = 0xFFFFFFFFu, i2 = 0xFFFFFFFFu;
-        for (uint32_t i = lane; i < len; i += 32)
-          if (!(A_id[i] & kExpandedBit)) {
-            if (i1 == 0xFFFFFFFFu) i1 = i;
-            else {
-              i2 = i;
-              break;
-            }
+        // Everything below `scan_from` is known to be expanded, so one 32-wide probe usually suffices.
+        uint32_t idx = 0xFFFFFFFFu, idx2 = 0xFFFFFFFFu;
+        for (uint32_t base = scan_from; base < len; base += 32) {
+          const uint32_t i = base + lane;
+          uint32_t um = __ballot_sync(kFullMask, i < len && !(A_id[i] & kExpandedBit));
+          if (um) {
+            idx = base + __ffs(um) - 1;
+            um &= um - 1;
+            if (um) idx2 = base + __ffs(um) - 1;
+            break;
           }
-        const uint32_t idx = __reduce_min_sync(kFullMask, i1);
+        }
         if (idx >= len) break;
-        const uint32_t idx2 = __reduce_min_sync(kFullMask, i1 == idx ? i2 : i1);
         const uint32_t c = A_id[idx];
         const uint32_t c2 = idx2 < len ? A_id[idx2] : kInvalid;
         __syncwarp();
@@ -346,7 +393,8 @@ __global__ void __launch_bounds__(128, 5) hnsw_search_kernel(const SearchArgs a)
         } else {
           spec_node = kInvalid;
         }
-        const uint32_t ins = (nid != kInvalid) ? visited_insert<GLOBAL_VISITED>(vis, nid, a.lay) : 0u;
+        scan_from = idx + 1;
+        const uint32_t ins = visited_insert<GLOBAL_VISITED>(vis, nid, nid != kInvalid, a.lay);
         if (__any_sync(kFullMask, ins == 2u)) {
           overflow = true;
           break;
@@ -406,13 +454,16 @@ __global__ void __launch_bounds__(128, 5) hnsw_search_kernel(const SearchArgs a)
             B_id[np] = A_id[i];
           }
         }
+        uint32_t my_np = 0xFFFFFFFFu;
         if (elig) {
           const uint32_t np = ub + rank;
           if (np < ef) {
             B_d[np] = d;
             B_id[np] = cid;
+            my_np = np;
           }
         }
+        scan_from = min(scan_from, __reduce_min_sync(kFullMask, my_np));
         len = min(len + mp, ef);
         float* td = A_d; A_d = B_d; B_d = td;
         uint32_t* ti = A_id; A_id = B_id; B_id = ti;

@@ -86,20 +86,30 @@ struct DeviceGuard {
   }
 };
 
-// adjacency rows arrive with counts; entries >= count become INVALID and ids are range-checked
+// One warp per adjacency row: entries >= count become INVALID, ids are range-checked, and a repeated id
+// keeps only its first occurrence (the reference's visited set skips the repeats, search.rs:338, so the
+// traversal is unchanged; the kernel's lock-free visited table relies on rows without repeats).  The row is
+// re-packed to a prefix in stored order.
 __global__ void sanitize_adj_kernel(uint32_t* adj, const uint8_t* cnt, uint64_t rows, uint32_t width,
                                     uint64_t n, uint32_t* bad) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * width) return;
-  uint64_t r = i / width;
-  uint32_t c = i % width;
-  uint32_t limit = min((uint32_t)cnt[r], width);
-  if (c >= limit) {
-    adj[i] = kInvalid;
-  } else if (adj[i] >= n) {
+  const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const uint32_t limit = min((uint32_t)cnt[r], width);
+  uint32_t v = (lane < limit) ? adj[r * width + lane] : kInvalid;
+  if (v != kInvalid && v >= n) {
     atomicAdd(bad, 1u);
-    adj[i] = kInvalid;
+    v = kInvalid;
   }
+  bool keep = v != kInvalid;
+  for (uint32_t j = 0; j < width; ++j) {
+    const uint32_t o = __shfl_sync(kFullMask, v, j);
+    if (j < lane && o == v) keep = false;
+  }
+  const uint32_t km = __ballot_sync(kFullMask, keep);
+  if (lane < width) adj[r * width + lane] = kInvalid;
+  __syncwarp();
+  if (keep) adj[r * width + __popc(km & ((1u << lane) - 1))] = v;
 }
 
 // dot(b, b) per arena row in the reference's AVX2 lane order (cosine_avx2's norm_b chain)
@@ -253,13 +263,11 @@ int32_t turdb_cuda_index_create(const turdb_cuda_graph* g, int32_t device, turdb
     IDX_TRY(cudaMemset(d_bad, 0, 4));
     IDX_TRY(cudaMemcpy(d_cnt, g->l0_cnt, n, cudaMemcpyHostToDevice));
     {
-      uint64_t total = n * kL0;
-      sanitize_adj_kernel<<<(unsigned)((total + 255) / 256), 256>>>(idx->d_l0_adj, d_cnt, n, kL0, n, d_bad);
+      sanitize_adj_kernel<<<(unsigned)((n * 32 + 255) / 256), 256>>>(idx->d_l0_adj, d_cnt, n, kL0, n, d_bad);
     }
     if (slots) {
       IDX_TRY(cudaMemcpy(d_cnt, g->up_cnt, slots, cudaMemcpyHostToDevice));
-      uint64_t total = slots * kUp;
-      sanitize_adj_kernel<<<(unsigned)((total + 255) / 256), 256>>>(idx->d_up_adj, d_cnt, slots, kUp, n, d_bad);
+      sanitize_adj_kernel<<<(unsigned)((slots * 32 + 255) / 256), 256>>>(idx->d_up_adj, d_cnt, slots, kUp, n, d_bad);
     }
     norm2_kernel<<<(unsigned)((n * 4 + 255) / 256), 256>>>(idx->d_arena, dim, ds, n, idx->d_norm2);
     uint32_t bad = 0;

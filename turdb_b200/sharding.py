@@ -17,21 +17,31 @@ def shard_bounds(n_total: int, world: int, rank: int) -> tuple[int, int]:
 
 
 def merge_topk_host(rows: np.ndarray, dist: np.ndarray, counts: np.ndarray, k: int):
-    """Host mirror of merge_topk_kernel for [n_shards, nq, k] arrays: k smallest by (distance, row_id).
-    Used by the CPU tests and as the specification of the device merge."""
+    """Host mirror (and specification) of merge_topk_kernel for [n_shards, nq, k] arrays: a k-way merge of the
+    per-shard lists, each consumed in its given (ascending-distance) order; at every step the head with the
+    smallest (distance, row_id, shard) is taken."""
     n_shards, nq, kk = rows.shape
     out_rows = np.full((nq, k), np.uint64(2**64 - 1), np.uint64)
     out_dist = np.full((nq, k), np.inf, np.float32)
     out_cnt = np.zeros(nq, np.uint32)
     for q in range(nq):
-        items = [(float(dist[s, q, i]), int(rows[s, q, i]), s) for s in range(n_shards)
-                 for i in range(min(int(counts[s, q]), kk))]
-        items.sort(key=lambda t: (t[0], t[1], t[2]))
-        items = items[:k]
-        out_cnt[q] = len(items)
-        for i, (d, r, _) in enumerate(items):
-            out_rows[q, i] = r
-            out_dist[q, i] = d
+        head = [0] * n_shards
+        lim = [min(int(counts[s, q]), kk) for s in range(n_shards)]
+        n_out = 0
+        while n_out < k:
+            best = None
+            for s in range(n_shards):
+                if head[s] < lim[s]:
+                    key = (float(dist[s, q, head[s]]), int(rows[s, q, head[s]]), s)
+                    if best is None or key < best:
+                        best = key
+            if best is None:
+                break
+            out_dist[q, n_out] = best[0]
+            out_rows[q, n_out] = best[1]
+            head[best[2]] += 1
+            n_out += 1
+        out_cnt[q] = n_out
     return out_rows, out_dist, out_cnt
 
 
