@@ -19,20 +19,245 @@ extern "C" int32_t turdb_cuda_merge_topk_device(int32_t device, const uint64_t* 
   return TURDB_OK;
 }
 
+// ---- TMA descriptors: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+// rows x kp BF16, row-major; box = 64 (K) x 128 (rows), 128-byte swizzle, out-of-range rows read as zero
+static bool make_bf16_map(CUtensorMap* map, const void* base, uint64_t rows, uint32_t kp) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {kp, rows};
+  cuuint64_t strides[1] = {(cuuint64_t)kp * 2};
+  cuuint32_t box[2] = {kChunkK, kTileM};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+__global__ void exact_init_kernel(float* thresh, uint32_t* cand_cnt, uint32_t nq, uint32_t* overflow_flag) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nq) {
+    thresh[i] = -INFINITY;
+    cand_cnt[i] = 0;
+  }
+  if (i == 0) *overflow_flag = 0;
+}
+
+__global__ void exact_overflow_mark_kernel(const uint32_t* overflow_flag, uint32_t* out_counts, uint32_t nq) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (*overflow_flag && i < nq) out_counts[i] = 0xFFFFFFFFu;  // candidate buffer overflowed: result invalid
+}
+
 extern "C" int32_t turdb_cuda_bruteforce_topk_device(turdb_cuda_index* idx, const float* d_queries, uint32_t query_dim,
                                                      uint32_t nq, uint32_t k, uint8_t metric, uint32_t rerank_factor,
                                                      uint64_t* d_out_row_ids, uint32_t* d_out_node_ids,
                                                      float* d_out_dist, uint32_t* d_out_counts, void* stream_) {
-  (void)idx; (void)d_queries; (void)query_dim; (void)nq; (void)k; (void)metric; (void)rerank_factor;
-  (void)d_out_row_ids; (void)d_out_node_ids; (void)d_out_dist; (void)d_out_counts; (void)stream_;
-  return fail(TURDB_ERR_UNSUPPORTED, "bruteforce_topk: not built yet");
+  if (!idx) return fail(TURDB_ERR_INVALID_ARGUMENT, "idx is null");
+  if (query_dim != idx->ix.dim)
+    return fail(TURDB_ERR_DIMENSION_MISMATCH, "query dimension %u does not match index dimension %u", query_dim, idx->ix.dim);
+  if (metric > 2) return fail(TURDB_ERR_INVALID_ARGUMENT, "metric %u unknown", metric);
+  if (nq == 0) return TURDB_OK;
+  if (!d_queries || !d_out_counts || (k && (!d_out_row_ids || !d_out_dist)))
+    return fail(TURDB_ERR_INVALID_ARGUMENT, "null query/output pointer");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DeviceGuard guard(idx->device);
+  if (!guard.ok) return fail(TURDB_ERR_CUDA, "cudaSetDevice(%d) failed", idx->device);
+  const uint64_t n = idx->ix.n;
+  if (n == 0 || k == 0) {
+    uint64_t total = std::max<uint64_t>((uint64_t)nq * std::max(k, 1u), nq);
+    fill_empty_results_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_out_row_ids, d_out_node_ids, d_out_dist,
+                                                                                   d_out_counts, nullptr, nq, k);
+    CUDA_TRY(cudaGetLastError());
+    return TURDB_OK;
+  }
+  const uint32_t dim = idx->ix.dim, ds = idx->ix.ds;
+  const uint32_t kp = (dim + kChunkK - 1) / kChunkK * kChunkK;
+  const uint32_t k_chunks = kp / kChunkK;
+  if (k_chunks > 8) return fail(TURDB_ERR_UNSUPPORTED, "bruteforce_topk supports dim <= 512 in this build (dim %u)", dim);
+  if (!rerank_factor) rerank_factor = 4;
+  const uint64_t kprime64 = std::min<uint64_t>((uint64_t)k * rerank_factor, n);
+  if (kprime64 > 4096) return fail(TURDB_ERR_UNSUPPORTED, "k * rerank_factor = %llu > 4096", (unsigned long long)kprime64);
+  const uint32_t kprime = (uint32_t)std::max<uint64_t>(kprime64, std::min<uint64_t>(k, n));
+  uint32_t cap = 2048;
+  while (cap < 8 * kprime) cap <<= 1;
+
+  // BF16 copy of the arena: built once per index
+  {
+    std::lock_guard<std::mutex> lk(idx->mu);
+    if (!idx->d_arena_bf16) {
+      CUDA_TRY(cudaMalloc(&idx->d_arena_bf16, (size_t)n * kp * 2));
+      const uint64_t total = n * kp;
+      to_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(idx->d_arena, dim, ds, kp, n, idx->d_arena_bf16);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      idx->device_bytes += (size_t)n * kp * 2;
+    }
+  }
+
+  // scratch: Qb | col_ab | thresh | cand_cnt | overflow | cand_id | cand_key
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = (off + bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  const size_t o_qb = take((size_t)nq * kp * 2), o_ab = take((size_t)n * 8), o_th = take((size_t)nq * 4),
+               o_cnt = take((size_t)nq * 4), o_ovf = take(4), o_id = take((size_t)nq * cap * 4),
+               o_key = take((size_t)nq * cap * 4);
+  uint8_t* scr = nullptr;
+  CUDA_TRY(cudaMallocFromPoolAsync(&scr, off, idx->pool, stream));
+  __nv_bfloat16* d_qb = (__nv_bfloat16*)(scr + o_qb);
+  float2* d_ab = (float2*)(scr + o_ab);
+  float* d_th = (float*)(scr + o_th);
+  uint32_t* d_cnt = (uint32_t*)(scr + o_cnt);
+  uint32_t* d_ovf = (uint32_t*)(scr + o_ovf);
+  uint32_t* d_cid = (uint32_t*)(scr + o_id);
+  float* d_ckey = (float*)(scr + o_key);
+  auto bail = [&](int32_t rc) {
+    cudaFreeAsync(scr, stream);
+    return rc;
+  };
+
+  {
+    const uint64_t total = (uint64_t)nq * kp;
+    to_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_queries, dim, dim, kp, nq, d_qb);
+    col_ab_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(idx->d_norm2, n, metric, d_ab);
+    exact_init_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(d_th, d_cnt, nq, d_ovf);
+  }
+  CUtensorMap map_q, map_x;
+  if (!make_bf16_map(&map_q, d_qb, nq, kp) || !make_bf16_map(&map_x, idx->d_arena_bf16, n, kp))
+    return bail(fail(TURDB_ERR_CUDA, "cuTensorMapEncodeTiled failed"));
+
+  const size_t gemm_smem = (size_t)k_chunks * kChunkBytes + kStages * kChunkBytes + 2 * kTileN * 8 + 16 * 8 + 16;
+  cudaError_t e = cudaFuncSetAttribute(exact_gemm_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(exact_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cap * 8));
+  if (e != cudaSuccess) return bail(fail(TURDB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)));
+
+  const uint32_t n_tiles = (uint32_t)((n + kTileN - 1) / kTileN);
+  const uint32_t n_qblocks = (nq + kTileM - 1) / kTileM;
+  uint32_t lo = 0, span = std::max(1u, (cap / 2) / kTileN);  // first slice: every column becomes a candidate
+  while (lo < n_tiles) {
+    const uint32_t hi = std::min(n_tiles, lo + span);
+    ExactArgs a{};
+    a.n_vec = (uint32_t)n;
+    a.nq = nq;
+    a.k_chunks = k_chunks;
+    a.tile_lo = lo;
+    a.tile_hi = hi;
+    const uint32_t tiles = hi - lo;
+    uint32_t tpi = (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(1, ((uint64_t)tiles * n_qblocks) / (4ull * idx->num_sms)));
+    a.tiles_per_item = tpi;
+    a.n_qblocks = n_qblocks;
+    a.n_items = n_qblocks * ((tiles + tpi - 1) / tpi);
+    a.col_ab = d_ab;
+    a.thresh = d_th;
+    a.cand_cnt = d_cnt;
+    a.cand_id = d_cid;
+    a.cand_key = d_ckey;
+    a.cap = cap;
+    a.overflow_flag = d_ovf;
+    const uint32_t grid = std::min<uint32_t>(a.n_items, (uint32_t)idx->num_sms);
+    exact_gemm_filter_kernel<<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
+    exact_threshold_kernel<<<nq, 256, cap * 8, stream>>>(nq, kprime, cap, d_cnt, d_cid, d_ckey, d_th);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return bail(fail(TURDB_ERR_CUDA, "exact pass launch failed: %s", cudaGetErrorString(e)));
+    lo = hi;
+    span = hi * 3;  // the next slice is 3x everything seen so far: ~3 * kprime new candidates per query
+  }
+
+  uint32_t n2 = 1;
+  while (n2 < kprime) n2 <<= 1;
+  const size_t rr_smem = (size_t)ds * 4 + (size_t)n2 * 8;
+  switch (metric) {
+    case kCosine:
+      exact_rerank_kernel<kCosine><<<nq, 128, rr_smem, stream>>>(idx->ix, d_queries, nq, k, cap, d_cnt, d_cid, d_out_row_ids,
+                                                                 d_out_node_ids, d_out_dist, d_out_counts);
+      break;
+    case kIP:
+      exact_rerank_kernel<kIP><<<nq, 128, rr_smem, stream>>>(idx->ix, d_queries, nq, k, cap, d_cnt, d_cid, d_out_row_ids,
+                                                             d_out_node_ids, d_out_dist, d_out_counts);
+      break;
+    default:
+      exact_rerank_kernel<kL2><<<nq, 128, rr_smem, stream>>>(idx->ix, d_queries, nq, k, cap, d_cnt, d_cid, d_out_row_ids,
+                                                             d_out_node_ids, d_out_dist, d_out_counts);
+  }
+  exact_overflow_mark_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(d_ovf, d_out_counts, nq);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return bail(fail(TURDB_ERR_CUDA, "rerank launch failed: %s", cudaGetErrorString(e)));
+  CUDA_TRY(cudaFreeAsync(scr, stream));
+  return TURDB_OK;
 }
 
 extern "C" int32_t turdb_cuda_bruteforce_topk(turdb_cuda_index* idx, const float* queries, uint32_t query_dim,
                                               uint32_t nq, uint32_t k, uint8_t metric, uint32_t rerank_factor,
                                               uint64_t* out_row_ids, uint32_t* out_node_ids, float* out_dist,
                                               uint32_t* out_counts) {
-  (void)idx; (void)queries; (void)query_dim; (void)nq; (void)k; (void)metric; (void)rerank_factor;
-  (void)out_row_ids; (void)out_node_ids; (void)out_dist; (void)out_counts;
-  return fail(TURDB_ERR_UNSUPPORTED, "bruteforce_topk: not built yet");
+  if (!idx) return fail(TURDB_ERR_INVALID_ARGUMENT, "idx is null");
+  if (query_dim != idx->ix.dim)
+    return fail(TURDB_ERR_DIMENSION_MISMATCH, "query dimension %u does not match index dimension %u", query_dim, idx->ix.dim);
+  if (nq == 0) return TURDB_OK;
+  if (!queries || !out_counts || (k && (!out_row_ids || !out_dist)))
+    return fail(TURDB_ERR_INVALID_ARGUMENT, "null query/output pointer");
+  DeviceGuard guard(idx->device);
+  if (!guard.ok) return fail(TURDB_ERR_CUDA, "cudaSetDevice(%d) failed", idx->device);
+  cudaStream_t stream;
+  CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  const size_t kk = std::max(k, 1u);
+  const size_t qbytes = (size_t)nq * query_dim * 4;
+  size_t off_rows = (qbytes + 255) & ~(size_t)255, off_dist = off_rows + nq * kk * 8, off_nodes = off_dist + nq * kk * 4,
+         off_counts = off_nodes + nq * kk * 4, total = off_counts + (size_t)nq * 4;
+  uint8_t* slab = nullptr;
+  cudaError_t e = cudaMallocFromPoolAsync(&slab, total, idx->pool, stream);
+  if (e != cudaSuccess) {
+    cudaStreamDestroy(stream);
+    return fail(TURDB_ERR_OUT_OF_MEMORY, "cudaMallocFromPoolAsync(%zu) failed: %s", total, cudaGetErrorString(e));
+  }
+  auto cleanup = [&]() {
+    cudaFreeAsync(slab, stream);
+    cudaStreamSynchronize(stream);
+    cudaStreamDestroy(stream);
+  };
+  e = cudaMemcpyAsync(slab, queries, qbytes, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) {
+    cleanup();
+    return fail(TURDB_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+  }
+  int32_t rc = turdb_cuda_bruteforce_topk_device(idx, (const float*)slab, query_dim, nq, k, metric, rerank_factor,
+                                                 (uint64_t*)(slab + off_rows), (uint32_t*)(slab + off_nodes),
+                                                 (float*)(slab + off_dist), (uint32_t*)(slab + off_counts), stream);
+  if (rc != TURDB_OK) {
+    cleanup();
+    return rc;
+  }
+  if (k) {
+    e = cudaMemcpyAsync(out_row_ids, slab + off_rows, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_dist, slab + off_dist, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && out_node_ids)
+      e = cudaMemcpyAsync(out_node_ids, slab + off_nodes, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, stream);
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_counts, slab + off_counts, (size_t)nq * 4, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  cleanup();
+  if (e != cudaSuccess) return fail(TURDB_ERR_CUDA, "bruteforce_topk failed: %s", cudaGetErrorString(e));
+  for (uint32_t i = 0; i < nq; ++i)
+    if (out_counts[i] == 0xFFFFFFFFu)
+      return fail(TURDB_ERR_UNSUPPORTED, "bruteforce_topk: candidate buffer overflow (corpus ordered by distance?); raise rerank_factor");
+  return TURDB_OK;
 }

@@ -1,14 +1,28 @@
-// exact_search.cuh — exact (brute-force) top-k path and the multi-shard top-k merge.
+// exact_search.cuh — the exact (brute-force) path and the multi-shard top-k merge.
+//
+// Exact path = the SQL `ORDER BY vec <op> q LIMIT k` scan (TopKExec, src/sql/executor.rs:2239-2392) as
+//   (1) a BF16 tensor-core pass  S = Q · X^T  (tcgen05.mma, accumulators in TMEM, operands staged by TMA),
+//       whose epilogue turns each score into a ranking key (key = s * a[col] + b[col]; larger = closer) and
+//       keeps only keys above the query's running threshold (rare) in a per-query candidate buffer;
+//   (2) a threshold update between passes over geometrically growing slices of the corpus
+//       (k' = rerank_factor * k best keys so far -> new threshold);
+//   (3) an FP32 rerank of the k' survivors in the reference's AVX2 lane order (bit-identical to
+//       select_squared_distance_fn, src/hnsw/distance.rs:438-444) and the final ascending top-k.
+// The dense contraction is the only tensor-core use in this library.
 #pragma once
 
+#include <cuda.h>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
 
 namespace turdb {
 
-// One warp per query: k-way merge of n_shards ascending lists, ties by (distance, row_id).
-// gathered_* are [n_shards][nq][k]; lane s walks shard s (n_shards <= 32).
+// ------------------------------------------------------------------------------------------------
+// shard merge
+// ------------------------------------------------------------------------------------------------
+// One warp per query: k-way merge of n_shards ascending lists; at every step the head with the smallest
+// (distance, row_id, shard) wins.  gathered_* are [n_shards][nq][k]; lane s walks shard s (n_shards <= 32).
 __global__ void merge_topk_kernel(const uint64_t* __restrict__ g_rows, const float* __restrict__ g_dist,
                                   const uint32_t* __restrict__ g_counts, uint32_t n_shards, uint32_t nq,
                                   uint32_t k, uint64_t* __restrict__ out_rows, float* __restrict__ out_dist,
@@ -59,6 +73,389 @@ __global__ void merge_topk_kernel(const uint64_t* __restrict__ g_rows, const flo
     out_dist[(size_t)q * k + i] = INFINITY;
   }
   if (lane == 0) out_counts[q] = produced;
+}
+
+// ------------------------------------------------------------------------------------------------
+// operand preparation
+// ------------------------------------------------------------------------------------------------
+// FP32 rows [rows][ds] -> BF16 rows [rows][kp] (kp = dim rounded up to 64, zero padded).
+__global__ void to_bf16_kernel(const float* __restrict__ src, uint32_t dim, uint32_t ds, uint32_t kp,
+                               uint64_t rows, __nv_bfloat16* __restrict__ dst) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * kp) return;
+  const uint64_t r = i / kp;
+  const uint32_t c = (uint32_t)(i % kp);
+  dst[i] = __float2bfloat16_rn(c < dim ? src[r * ds + c] : 0.f);
+}
+
+// Ranking key of a BF16 score s for column (vector) j: key = s * a + b, larger = closer.
+//   L2: 2 s - |x|^2      cosine: s / |x|      IP: s          (the query's own norm does not change ranks)
+__global__ void col_ab_kernel(const float* __restrict__ norm2, uint64_t n, int metric, float2* __restrict__ ab) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float n2 = norm2[i];
+  float2 v;
+  if (metric == kL2) v = make_float2(2.f, -n2);
+  else if (metric == kCosine) v = make_float2(n2 > 0.f ? rsqrtf(n2) : 0.f, 0.f);
+  else v = make_float2(1.f, 0.f);
+  ab[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, BF16 inputs, FP32 accumulate, M = 128
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, 128-byte swizzle, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, version 1 = Blackwell)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);  // start address
+  d |= (uint64_t)1 << 16;                      // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;            // stride byte offset
+  d |= (uint64_t)1 << 46;                      // descriptor version
+  d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass (1): GEMM + threshold filter
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kTileM = 128;   // queries per CTA tile (UMMA M)
+constexpr uint32_t kTileN = 128;   // vectors per MMA tile (UMMA N)
+constexpr uint32_t kChunkK = 64;   // BF16 elements per 128 B swizzle row
+constexpr uint32_t kChunkBytes = kTileM * kChunkK * 2;  // 16 KB per operand chunk
+constexpr uint32_t kStages = 4;    // B pipeline depth
+constexpr uint32_t kExactThreads = 192;  // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
+
+struct ExactArgs {
+  uint32_t n_vec, nq, k_chunks;
+  uint32_t tile_lo, tile_hi;      // vector tiles of this pass
+  uint32_t tiles_per_item;        // consecutive tiles one CTA handles for one query block
+  uint32_t n_qblocks, n_items;
+  const float2* col_ab;           // [n_vec]
+  const float* thresh;            // [nq] keep keys >= thresh
+  uint32_t* cand_cnt;             // [nq]
+  uint32_t* cand_id;              // [nq][cap]
+  float* cand_key;                // [nq][cap]
+  uint32_t cap;
+  uint32_t* overflow_flag;
+};
+
+// smem: [A: k_chunks x 16 KB][B: kStages x 16 KB][col_ab: 2 x 128 float2][barriers][tmem ptr]
+__global__ void __launch_bounds__(kExactThreads, 1)
+exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
+                         const ExactArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + (size_t)a.k_chunks * kChunkBytes;
+  float2* s_ab = reinterpret_cast<float2*>(sB + kStages * kChunkBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ab + 2 * kTileN);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const uint32_t bar_a_full = smem_u32(bars + 0), bar_a_empty = smem_u32(bars + 1);
+  const uint32_t bar_b_full = smem_u32(bars + 2), bar_b_empty = smem_u32(bars + 2 + kStages);
+  const uint32_t bar_t_full = smem_u32(bars + 2 + 2 * kStages), bar_t_empty = smem_u32(bars + 4 + 2 * kStages);
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_a_full, 1);
+    mbar_init(bar_a_empty, 1);
+    for (uint32_t s = 0; s < kStages; ++s) {
+      mbar_init(bar_b_full + 8 * s, 1);
+      mbar_init(bar_b_empty + 8 * s, 1);
+    }
+    for (uint32_t s = 0; s < 2; ++s) {
+      mbar_init(bar_t_full + 8 * s, 1);
+      mbar_init(bar_t_empty + 8 * s, 4);  // one arrive per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {  // 2 accumulator buffers x 128 FP32 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, a_phase = 0;
+      for (uint32_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+        const uint32_t qb = item % a.n_qblocks;
+        const uint32_t t0 = a.tile_lo + (item / a.n_qblocks) * a.tiles_per_item;
+        const uint32_t t1 = min(a.tile_hi, t0 + a.tiles_per_item);
+        mbar_wait(bar_a_empty, a_phase ^ 1);  // previous item's MMAs have drained A
+        mbar_expect_tx(bar_a_full, a.k_chunks * kChunkBytes);
+        for (uint32_t kc = 0; kc < a.k_chunks; ++kc)
+          tma_load_2d(smem_u32(sA + (size_t)kc * kChunkBytes), &map_q, (int32_t)(kc * kChunkK), (int32_t)(qb * kTileM), bar_a_full);
+        a_phase ^= 1;
+        for (uint32_t t = t0; t < t1; ++t) {
+          for (uint32_t kc = 0; kc < a.k_chunks; ++kc) {
+            mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
+            mbar_expect_tx(bar_b_full + 8 * stage, kChunkBytes);
+            tma_load_2d(smem_u32(sB + (size_t)stage * kChunkBytes), &map_x, (int32_t)(kc * kChunkK), (int32_t)(t * kTileN),
+                        bar_b_full + 8 * stage);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one elected lane) =====
+    if (lane == 0) {
+      // instruction descriptor: D=F32, A=B=BF16, both K-major, N=128, M=128 (cute::UMMA::InstrDescriptor)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((kTileN >> 3) << 17) | ((kTileM >> 4) << 24);
+      uint32_t stage = 0, phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
+      for (uint32_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+        const uint32_t t0 = a.tile_lo + (item / a.n_qblocks) * a.tiles_per_item;
+        const uint32_t t1 = min(a.tile_hi, t0 + a.tiles_per_item);
+        mbar_wait(bar_a_full, a_phase);
+        a_phase ^= 1;
+        tc_fence_after();
+        for (uint32_t t = t0; t < t1; ++t) {
+          mbar_wait(bar_t_empty + 8 * acc, acc_phase ^ 1);  // epilogue has drained this accumulator
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * kTileN;
+          for (uint32_t kc = 0; kc < a.k_chunks; ++kc) {
+            mbar_wait(bar_b_full + 8 * stage, phase);
+            tc_fence_after();
+            const uint64_t da = umma_desc_sw128(smem_u32(sA + (size_t)kc * kChunkBytes));
+            const uint64_t db = umma_desc_sw128(smem_u32(sB + (size_t)stage * kChunkBytes));
+#pragma unroll
+            for (uint32_t k4 = 0; k4 < kChunkK / 16; ++k4)  // UMMA_K = 16 BF16 = 32 B inside the swizzle row
+              tc_mma_bf16(d_tmem, da + 2 * k4, db + 2 * k4, idesc, (kc | k4) != 0 ? 1u : 0u);
+            tc_commit(bar_b_empty + 8 * stage);  // frees the B stage when these MMAs retire
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          tc_commit(bar_t_full + 8 * acc);
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
+        }
+        tc_commit(bar_a_empty);
+      }
+    }
+  } else {
+    // ===== epilogue: 4 warps, thread = one query row, 128 scores per tile =====
+    const uint32_t quarter = warp & 3;               // TMEM lane quarter this warp may read
+    const uint32_t row = quarter * 32 + lane;
+    const uint32_t et = threadIdx.x - 64;            // 0..127 among epilogue threads
+    uint32_t acc = 0, acc_phase = 0;
+    for (uint32_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+      const uint32_t qb = item % a.n_qblocks;
+      const uint32_t t0 = a.tile_lo + (item / a.n_qblocks) * a.tiles_per_item;
+      const uint32_t t1 = min(a.tile_hi, t0 + a.tiles_per_item);
+      const uint32_t q = qb * kTileM + row;
+      const bool q_ok = q < a.nq;
+      const float tau = q_ok ? a.thresh[q] : INFINITY;
+      for (uint32_t t = t0; t < t1; ++t) {
+        {  // stage this tile's per-column (a, b); out-of-range columns never pass
+          const uint64_t col = (uint64_t)t * kTileN + et;
+          s_ab[acc * kTileN + et] = col < a.n_vec ? a.col_ab[col] : make_float2(0.f, __int_as_float(0x7fc00000));  // NaN key never passes
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        mbar_wait(bar_t_full + 8 * acc, acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (uint32_t cb = 0; cb < kTileN / 32; ++cb) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + ((quarter * 32) << 16) + acc * kTileN + cb * 32, v);
+#pragma unroll
+          for (uint32_t j = 0; j < 32; ++j) {
+            const float2 ab = s_ab[acc * kTileN + cb * 32 + j];
+            const float key = fmaf(__uint_as_float(v[j]), ab.x, ab.y);
+            if (key >= tau) {
+              const uint32_t pos = atomicAdd(a.cand_cnt + q, 1u);
+              if (pos < a.cap) {
+                a.cand_id[(size_t)q * a.cap + pos] = t * kTileN + cb * 32 + j;
+                a.cand_key[(size_t)q * a.cap + pos] = key;
+              } else {
+                *a.overflow_flag = 1u;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_t_empty + 8 * acc);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass (2): keep the kprime best keys per query, publish the kprime-th as the new threshold
+// ------------------------------------------------------------------------------------------------
+// One CTA per query; bitonic sort (descending key, ascending id on ties) of up to `cap` candidates in smem.
+__global__ void __launch_bounds__(256) exact_threshold_kernel(uint32_t nq, uint32_t kprime, uint32_t cap,
+                                                              uint32_t* cand_cnt, uint32_t* cand_id, float* cand_key,
+                                                              float* thresh) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float* sk = reinterpret_cast<float*>(smem_raw);
+  uint32_t* si = reinterpret_cast<uint32_t*>(sk + cap);
+  const uint32_t q = blockIdx.x;
+  if (q >= nq) return;
+  const uint32_t cnt = min(cand_cnt[q], cap);
+  uint32_t n2 = 1;
+  while (n2 < cnt) n2 <<= 1;
+  for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) {
+    sk[i] = i < cnt ? cand_key[(size_t)q * cap + i] : -INFINITY;
+    si[i] = i < cnt ? cand_id[(size_t)q * cap + i] : 0xFFFFFFFFu;
+  }
+  __syncthreads();
+  for (uint32_t size = 2; size <= n2; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) {
+        const uint32_t j = i ^ stride;
+        if (j > i) {
+          const bool desc = (i & size) == 0;  // first half of each block sorted "better first"
+          const float ki = sk[i], kj = sk[j];
+          const uint32_t ii = si[i], ij = si[j];
+          const bool i_better = ki > kj || (ki == kj && ii < ij);
+          if (i_better != desc) {
+            sk[i] = kj; sk[j] = ki;
+            si[i] = ij; si[j] = ii;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const uint32_t keep = min(cnt, kprime);
+  for (uint32_t i = threadIdx.x; i < keep; i += blockDim.x) {
+    cand_key[(size_t)q * cap + i] = sk[i];
+    cand_id[(size_t)q * cap + i] = si[i];
+  }
+  if (threadIdx.x == 0) {
+    cand_cnt[q] = keep;
+    thresh[q] = keep == kprime ? sk[kprime - 1] : -INFINITY;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass (3): FP32 rerank in the reference's lane order + final ascending top-k
+// ------------------------------------------------------------------------------------------------
+// One CTA (128 threads = 32 quads) per query.  Distances follow select_squared_distance_fn; ties order by node id.
+template <int METRIC>
+__global__ void __launch_bounds__(128) exact_rerank_kernel(DeviceIndex ix, const float* __restrict__ queries, uint32_t nq,
+                                                           uint32_t k, uint32_t cap, const uint32_t* __restrict__ cand_cnt,
+                                                           const uint32_t* __restrict__ cand_id, uint64_t* out_rows,
+                                                           uint32_t* out_nodes, float* out_dist, uint32_t* out_counts) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const uint32_t q = blockIdx.x;
+  if (q >= nq) return;
+  const uint32_t cnt = min(cand_cnt[q], cap);
+  uint32_t n2 = 1;
+  while (n2 < cnt) n2 <<= 1;
+  float* qs = reinterpret_cast<float*>(smem_raw);           // [ds]
+  float* sd = qs + ix.ds;                                   // [n2]
+  uint32_t* si = reinterpret_cast<uint32_t*>(sd + n2);      // [n2]
+  for (uint32_t i = threadIdx.x; i < ix.ds; i += blockDim.x) qs[i] = i < ix.dim ? queries[(size_t)q * ix.dim + i] : 0.f;
+  __syncthreads();
+  const uint32_t p = threadIdx.x & 3, quad = threadIdx.x >> 2;
+  const float qn = (METRIC == kCosine) ? quad_dot(qs, qs, ix.dim, p) : 0.f;
+  for (uint32_t base = 0; base < n2; base += 32) {
+    const uint32_t c = base + quad;
+    const uint32_t id = c < cnt ? cand_id[(size_t)q * cap + c] : 0u;
+    const float* b = ix.arena + (size_t)id * ix.ds;
+    float raw = (METRIC == kL2) ? quad_l2sq(qs, b, ix.dim, p) : quad_dot(qs, b, ix.dim, p);
+    if (p == 0 && c < n2) {
+      float d = raw;
+      if (METRIC == kIP) d = -raw;
+      if (METRIC == kCosine) d = cosine_finish(raw, qn, ix.norm2[id]);
+      sd[c] = c < cnt ? d : INFINITY;
+      si[c] = c < cnt ? id : 0xFFFFFFFFu;
+    }
+  }
+  __syncthreads();
+  for (uint32_t size = 2; size <= n2; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) {
+        const uint32_t j = i ^ stride;
+        if (j > i) {
+          const bool asc = (i & size) == 0;
+          const float di = sd[i], dj = sd[j];
+          const uint32_t ii = si[i], ij = si[j];
+          const bool i_first = di < dj || (di == dj && ii < ij);
+          if (i_first != asc) {
+            sd[i] = dj; sd[j] = di;
+            si[i] = ij; si[j] = ii;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const uint32_t count = min(cnt, k);
+  for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
+    const size_t o = (size_t)q * k + i;
+    if (i < count) {
+      out_rows[o] = ix.row_ids[si[i]];
+      if (out_nodes) out_nodes[o] = si[i];
+      out_dist[o] = sd[i];
+    } else {
+      out_rows[o] = 0xFFFFFFFFFFFFFFFFull;
+      if (out_nodes) out_nodes[o] = kInvalid;
+      out_dist[o] = INFINITY;
+    }
+  }
+  if (threadIdx.x == 0) out_counts[q] = count;
 }
 
 }  // namespace turdb

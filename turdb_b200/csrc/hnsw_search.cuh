@@ -217,7 +217,7 @@ __device__ __forceinline__ uint32_t visited_insert(uint32_t* tab, uint32_t id, b
 
 template <int METRIC, bool GLOBAL_VISITED>
 __global__ void __launch_bounds__(128, 5) hnsw_search_kernel(const SearchArgs a) {
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ __align__(1024) uint8_t smem[];
   const DeviceIndex& ix = a.ix;
   const uint32_t tid = threadIdx.x, nthreads = blockDim.x;
   const uint32_t lane = tid & 31, warp = tid >> 5;
