@@ -144,7 +144,10 @@ extern "C" int32_t turdb_cuda_bruteforce_topk_device(turdb_cuda_index* idx, cons
   if (!make_bf16_map(&map_q, d_qb, nq, kp) || !make_bf16_map(&map_x, idx->d_arena_bf16, n, kp))
     return bail(fail(TURDB_ERR_CUDA, "cuTensorMapEncodeTiled failed"));
 
-  const size_t gemm_smem = (size_t)k_chunks * kChunkBytes + kStages * kChunkBytes + 2 * kTileN * 8 + 16 * 8 + 16;
+  const size_t fixed_smem = (size_t)k_chunks * kChunkBytes + 2 * kTileN * 8 + 24 * 8 + 16;
+  const uint32_t n_stages = (uint32_t)std::min<size_t>(kMaxStages, ((size_t)idx->max_smem_optin - fixed_smem) / kChunkBytes);
+  if (n_stages < 2) return bail(fail(TURDB_ERR_UNSUPPORTED, "not enough shared memory for the exact path at dim %u", dim));
+  const size_t gemm_smem = fixed_smem + (size_t)n_stages * kChunkBytes;
   cudaError_t e = cudaFuncSetAttribute(exact_gemm_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(exact_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cap * 8));
@@ -159,6 +162,7 @@ extern "C" int32_t turdb_cuda_bruteforce_topk_device(turdb_cuda_index* idx, cons
     a.n_vec = (uint32_t)n;
     a.nq = nq;
     a.k_chunks = k_chunks;
+    a.n_stages = n_stages;
     a.tile_lo = lo;
     a.tile_hi = hi;
     const uint32_t tiles = hi - lo;

@@ -159,11 +159,12 @@ constexpr uint32_t kTileM = 128;   // queries per CTA tile (UMMA M)
 constexpr uint32_t kTileN = 128;   // vectors per MMA tile (UMMA N)
 constexpr uint32_t kChunkK = 64;   // BF16 elements per 128 B swizzle row
 constexpr uint32_t kChunkBytes = kTileM * kChunkK * 2;  // 16 KB per operand chunk
-constexpr uint32_t kStages = 4;    // B pipeline depth
+constexpr uint32_t kMaxStages = 8; // B pipeline depth is chosen at launch (as many 16 KB stages as fit)
 constexpr uint32_t kExactThreads = 192;  // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
 
 struct ExactArgs {
   uint32_t n_vec, nq, k_chunks;
+  uint32_t n_stages;              // B pipeline stages (2..kMaxStages)
   uint32_t tile_lo, tile_hi;      // vector tiles of this pass
   uint32_t tiles_per_item;        // consecutive tiles one CTA handles for one query block
   uint32_t n_qblocks, n_items;
@@ -176,7 +177,7 @@ struct ExactArgs {
   uint32_t* overflow_flag;
 };
 
-// smem: [A: k_chunks x 16 KB][B: kStages x 16 KB][col_ab: 2 x 128 float2][barriers][tmem ptr]
+// smem: [A: k_chunks x 16 KB][B: n_stages x 16 KB][col_ab: 2 x 128 float2][barriers][tmem ptr]
 __global__ void __launch_bounds__(kExactThreads, 1)
 exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                          const ExactArgs a) {
@@ -184,12 +185,13 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* sA = smem;
   uint8_t* sB = sA + (size_t)a.k_chunks * kChunkBytes;
-  float2* s_ab = reinterpret_cast<float2*>(sB + kStages * kChunkBytes);
+  const uint32_t kStages = a.n_stages;
+  float2* s_ab = reinterpret_cast<float2*>(sB + (size_t)kStages * kChunkBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_ab + 2 * kTileN);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
   const uint32_t bar_a_full = smem_u32(bars + 0), bar_a_empty = smem_u32(bars + 1);
-  const uint32_t bar_b_full = smem_u32(bars + 2), bar_b_empty = smem_u32(bars + 2 + kStages);
-  const uint32_t bar_t_full = smem_u32(bars + 2 + 2 * kStages), bar_t_empty = smem_u32(bars + 4 + 2 * kStages);
+  const uint32_t bar_b_full = smem_u32(bars + 2), bar_b_empty = smem_u32(bars + 2 + kMaxStages);
+  const uint32_t bar_t_full = smem_u32(bars + 2 + 2 * kMaxStages), bar_t_empty = smem_u32(bars + 4 + 2 * kMaxStages);
 
   if (threadIdx.x == 0) {
     mbar_init(bar_a_full, 1);
@@ -305,17 +307,31 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
         for (uint32_t cb = 0; cb < kTileN / 32; ++cb) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(tmem_base + ((quarter * 32) << 16) + acc * kTileN + cb * 32, v);
+          // keys first (pure register/shared-memory work the scheduler can pipeline), appends after: a key
+          // that beats the running threshold is rare once the first slices have been seen
+          const float4* ab4 = reinterpret_cast<const float4*>(s_ab + acc * kTileN + cb * 32);
+          uint32_t pass = 0;
 #pragma unroll
-          for (uint32_t j = 0; j < 32; ++j) {
-            const float2 ab = s_ab[acc * kTileN + cb * 32 + j];
-            const float key = fmaf(__uint_as_float(v[j]), ab.x, ab.y);
-            if (key >= tau) {
-              const uint32_t pos = atomicAdd(a.cand_cnt + q, 1u);
-              if (pos < a.cap) {
-                a.cand_id[(size_t)q * a.cap + pos] = t * kTileN + cb * 32 + j;
-                a.cand_key[(size_t)q * a.cap + pos] = key;
-              } else {
-                *a.overflow_flag = 1u;
+          for (uint32_t j = 0; j < 32; j += 2) {
+            const float4 ab = ab4[j >> 1];
+            const float k0 = fmaf(__uint_as_float(v[j]), ab.x, ab.y);
+            const float k1 = fmaf(__uint_as_float(v[j + 1]), ab.z, ab.w);
+            v[j] = __float_as_uint(k0);
+            v[j + 1] = __float_as_uint(k1);
+            pass |= (k0 >= tau ? 1u : 0u) << j;
+            pass |= (k1 >= tau ? 1u : 0u) << (j + 1);
+          }
+          if (pass) {
+#pragma unroll
+            for (uint32_t j = 0; j < 32; ++j) {
+              if (pass & (1u << j)) {
+                const uint32_t pos = atomicAdd(a.cand_cnt + q, 1u);
+                if (pos < a.cap) {
+                  a.cand_id[(size_t)q * a.cap + pos] = t * kTileN + cb * 32 + j;
+                  a.cand_key[(size_t)q * a.cap + pos] = __uint_as_float(v[j]);
+                } else {
+                  *a.overflow_flag = 1u;
+                }
               }
             }
           }
