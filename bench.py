@@ -79,6 +79,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """Samples before this point (warm-up) are discarded."""
+        self.lines = []
+
     def stop(self) -> dict:
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -246,12 +250,15 @@ def main():
         torch.cuda.synchronize()
 
     # ---- value: device-resident inputs ----
-    for i in range(args.warmup):
-        step(i)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.5)  # nvidia-smi needs a moment before its first sample
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    if rank == 0:
+        sampler.mark()
     idx.profile_begin(args.steps)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -262,6 +269,13 @@ def main():
     barrier()
     elapsed_ms = e0.elapsed_time(e1)
     kern_ms, over_ms = idx.profile_read(args.steps)
+    if rank == 0 and elapsed_ms < 400:  # keep the GPU under the same load until the sampler has a few readings
+        t_end = time.time() + 0.45
+        i = 0
+        while time.time() < t_end:
+            step(i)
+            i += 1
+        torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([elapsed_ms], device=dev)

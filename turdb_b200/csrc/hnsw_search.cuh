@@ -26,7 +26,7 @@ namespace turdb {
 constexpr uint32_t kDone = 0xFFFFFFFFu;
 
 struct TeamLayout {
-  uint32_t off_bar, off_ctl, off_q, off_list, off_cand, off_hash, off_stage;
+  uint32_t off_bar, off_ctl, off_q, off_list, off_clist, off_cand, off_hash, off_stage;
   uint32_t team_bytes;
   uint32_t n_groups;   // staging groups of 8 slots (1..4), one mbarrier each
   uint32_t stride;     // bytes between staging slots; stride/4 == 8 (mod 32) -> conflict-free quads
@@ -55,6 +55,10 @@ struct SearchArgs {
   uint32_t* global_visited;  // fallback pass: [CTAs][vis_words] bitsets
   uint32_t vis_words;
   unsigned long long* dbg;   // optional [16] cycle counters (diagnostics), null in production
+  // search_filtered (search.rs:352-398): one bit per node; candidates that do not fit the shared window
+  const uint64_t* visible;   // null => unfiltered search
+  uint2* f_ovf;              // [CTAs][f_ocap] (distance bits, id) overflow of the candidate window
+  uint32_t f_ocap;
 };
 
 // Per-team shared state handed to every warp.
@@ -215,7 +219,79 @@ __device__ __forceinline__ uint32_t visited_insert(uint32_t* tab, uint32_t id, b
   return res;
 }
 
-template <int METRIC, bool GLOBAL_VISITED>
+// Merge up to 32 new (d, id) pairs (one per `elig` lane) into the ascending list src[head, len) -> dst[0, ..),
+// keeping at most `cap` entries.  Old entries win distance ties; new ones tie-break by lane (stored order).
+// EVICT: entries pushed past `cap` are appended to the global overflow `ovf` (they stay candidates) unless
+// `drop_above` says they can never be expanded (d > drop_above); *o_min tracks the smallest overflowed distance.
+// Returns the new length; *min_new = smallest position taken by a new entry (0xFFFFFFFF if none).
+template <bool EVICT>
+__device__ __forceinline__ uint32_t rank_merge(const float* src_d, const uint32_t* src_id, uint32_t head, uint32_t len,
+                                               float* dst_d, uint32_t* dst_id, uint32_t cap, bool elig, float d,
+                                               uint32_t id, uint32_t* tmp_ub, uint32_t lane, uint32_t* min_new,
+                                               uint2* ovf, uint32_t* o_cnt, uint32_t o_cap, float* o_min,
+                                               float drop_above, bool* o_overflow) {
+  const uint32_t n_old = len - head;
+  const uint32_t emask = __ballot_sync(kFullMask, elig);
+  const uint32_t mp = __popc(emask);
+  uint32_t ub = 0;
+  if (elig) {
+    uint32_t lo = 0, hi = n_old;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (src_d[head + mid] <= d) lo = mid + 1;
+      else hi = mid;
+    }
+    ub = lo;
+    tmp_ub[__popc(emask & ((1u << lane) - 1))] = ub;
+  }
+  uint32_t rank = 0;
+  for (uint32_t e = emask; e; e &= e - 1) {
+    const uint32_t bsrc = __ffs(e) - 1;
+    const float db = __shfl_sync(kFullMask, d, bsrc);
+    rank += (db < d || (db == d && bsrc < lane)) ? 1u : 0u;
+  }
+  __syncwarp();
+  const uint32_t o_base = EVICT ? *o_cnt : 0u;
+  uint32_t kept_evicted = 0;
+  float ev_min = INFINITY;
+  auto place = [&](uint32_t np, float pd, uint32_t pid) {
+    if (np < cap) {
+      dst_d[np] = pd;
+      dst_id[np] = pid;
+    } else if (EVICT && !(pd > drop_above)) {
+      const uint32_t o = o_base + (np - cap);
+      if (o < o_cap) ovf[o] = make_uint2(__float_as_uint(pd), pid);
+      else *o_overflow = true;
+      kept_evicted += 1;
+      ev_min = fminf(ev_min, pd);
+    }
+  };
+  for (uint32_t i = lane; i < n_old; i += 32) {
+    uint32_t sft = 0;
+    for (uint32_t j = 0; j < mp; ++j) sft += (tmp_ub[j] <= i) ? 1u : 0u;
+    place(i + sft, src_d[head + i], src_id[head + i]);
+  }
+  uint32_t my_np = 0xFFFFFFFFu;
+  if (elig) {
+    my_np = ub + rank;
+    place(my_np, d, id);
+    if (my_np >= cap) my_np = 0xFFFFFFFFu;
+  }
+  *min_new = __reduce_min_sync(kFullMask, my_np);
+  if (EVICT) {
+    // evicted entries are the largest of the merged sequence and the dropped ones its tail, so the kept
+    // ones occupy consecutive overflow slots
+    *o_cnt = o_base + __reduce_add_sync(kFullMask, kept_evicted);
+#pragma unroll
+    for (uint32_t off = 16; off >= 1; off >>= 1) ev_min = fminf(ev_min, __shfl_xor_sync(kFullMask, ev_min, off));
+    *o_min = fminf(*o_min, ev_min);
+    if (__any_sync(kFullMask, *o_overflow)) *o_overflow = true;
+  }
+  __syncwarp();
+  return min(n_old + mp, cap);
+}
+
+template <int METRIC, bool GLOBAL_VISITED, bool FILTERED>
 __global__ void __launch_bounds__(128, 5) hnsw_search_kernel(const SearchArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const DeviceIndex& ix = a.ix;
@@ -226,6 +302,10 @@ __global__ void __launch_bounds__(128, 5) hnsw_search_kernel(const SearchArgs a)
   uint32_t* A_id = reinterpret_cast<uint32_t*>(A_d + a.ef);
   float* B_d = reinterpret_cast<float*>(A_id + a.ef);
   uint32_t* B_id = reinterpret_cast<uint32_t*>(B_d + a.ef);
+  float* C_d = reinterpret_cast<float*>(smem + a.lay.off_clist);  // filtered search: candidate window (x2)
+  uint32_t* C_id = reinterpret_cast<uint32_t*>(C_d + a.ef);
+  float* D_d = reinterpret_cast<float*>(C_id + a.ef);
+  uint32_t* D_id = reinterpret_cast<uint32_t*>(D_d + a.ef);
   uint32_t* cand_ids = reinterpret_cast<uint32_t*>(smem + a.lay.off_cand);
   float* cand_d = reinterpret_cast<float*>(cand_ids + 32);
   uint32_t* tmp_ub = cand_ids + 64;
@@ -343,6 +423,130 @@ __global__ void __launch_bounds__(128, 5) hnsw_search_kernel(const SearchArgs a)
         }
       }
 
+      if (FILTERED) {
+        // ---- beam_search_filtered (search.rs:352-398) ----
+        // results R (visible nodes only, cap ef) = A/B lists; candidates = EVERY visited node: the closest
+        // ones sit in the sorted window C/D (cap ef), the rest in the global overflow `ovf`.  Invariant:
+        // max(window) <= o_min = min(overflow), so the window head is the global minimum; when the window
+        // runs dry it is refilled with the smallest overflow entries.
+        auto is_visible = [&](uint32_t id) { return ((a.visible[id >> 6] >> (id & 63)) & 1ull) != 0; };
+        uint2* ovf = a.f_ovf + (size_t)blockIdx.x * a.f_ocap;
+        uint32_t o_cnt = 0, c_head = 0, c_len = 1, r_len = 0, dummy = 0;
+        float o_min = INFINITY;
+        bool o_overflow = false;
+        const bool entry_vis = is_visible(cur);
+        if (lane == 0) {
+          C_d[0] = cur_d;
+          C_id[0] = cur;
+          if (entry_vis) {
+            A_d[0] = cur_d;
+            A_id[0] = cur;
+          }
+        }
+        r_len = entry_vis ? 1u : 0u;
+        (void)visited_insert<GLOBAL_VISITED>(vis, cur, lane == 0, a.lay);
+        uint32_t n_visited = 1;
+        uint32_t spec_node = kInvalid, spec_nid = kInvalid;
+        __syncwarp();
+        for (;;) {
+          if (c_head == c_len) {
+            if (o_cnt == 0) break;
+            // refill: stream the overflow through the window; what does not fit is compacted back in place
+            const float worst_now = r_len ? A_d[r_len - 1] : INFINITY;
+            const float drop = (r_len == ef) ? worst_now : INFINITY;
+            const uint32_t total = o_cnt;
+            uint32_t w = 0;
+            o_min = INFINITY;
+            c_head = 0;
+            c_len = 0;
+            for (uint32_t r = 0; r < total; r += 32) {
+              const bool have = r + lane < total;
+              const uint2 e = have ? ovf[r + lane] : make_uint2(0u, 0u);
+              const float ed = __uint_as_float(e.x);
+              __syncwarp();
+              const bool el = have && !(ed > drop);
+              c_len = rank_merge<true>(C_d, C_id, 0, c_len, D_d, D_id, ef, el, ed, e.y, tmp_ub, lane, &dummy, ovf, &w,
+                                       a.f_ocap, &o_min, drop, &o_overflow);
+              float* td = C_d; C_d = D_d; D_d = td;
+              uint32_t* ti = C_id; C_id = D_id; D_id = ti;
+            }
+            o_cnt = w;
+            if (c_len == 0) break;
+          }
+          const uint32_t c = C_id[c_head];
+          const float cd = C_d[c_head];
+          const float worst0 = r_len ? A_d[r_len - 1] : INFINITY;  // worst_result_distance(), search.rs:238-243
+          if (cd > worst0) break;                                   // search.rs:374-376
+          c_head += 1;
+          n_expanded += 1;
+          const uint32_t c2 = c_head < c_len ? C_id[c_head] : kInvalid;
+          if (!GLOBAL_VISITED && n_visited + kL0 > hash_limit) {
+            overflow = true;
+            break;
+          }
+          const uint32_t nid = (c == spec_node) ? spec_nid : __ldg(ix.l0_adj + (size_t)c * kL0 + lane);
+          if (c2 != kInvalid) {
+            spec_node = c2;
+            spec_nid = __ldg(ix.l0_adj + (size_t)c2 * kL0 + lane);
+          } else {
+            spec_node = kInvalid;
+          }
+          const uint32_t ins = visited_insert<GLOBAL_VISITED>(vis, nid, nid != kInvalid, a.lay);
+          if (__any_sync(kFullMask, ins == 2u)) {
+            overflow = true;
+            break;
+          }
+          const bool isnew = ins == 1u;
+          const uint32_t newmask = __ballot_sync(kFullMask, isnew);
+          const uint32_t m = __popc(newmask);
+          if (m == 0) continue;
+          n_visited += m;
+          if (isnew) cand_ids[__popc(newmask & ((1u << lane) - 1))] = nid;
+          const float d = leader_request<METRIC>(ix, t, m);
+          const uint32_t cid = lane < m ? cand_ids[lane] : kInvalid;
+          n_dist += m;
+          // results: visible && (d < worst || |R| < ef), search.rs:391-395 (batch form)
+          const bool vis_ok = lane < m && is_visible(cid);
+          const bool r_elig = vis_ok && (r_len < ef || d < worst0);
+          if (__any_sync(kFullMask, r_elig)) {
+            r_len = rank_merge<false>(A_d, A_id, 0, r_len, B_d, B_id, ef, r_elig, d, cid, tmp_ub, lane, &dummy, nullptr,
+                                      nullptr, 0, nullptr, INFINITY, nullptr);
+            float* td = A_d; A_d = B_d; B_d = td;
+            uint32_t* ti = A_id; A_id = B_id; B_id = ti;
+          }
+          // candidates: every new node (search.rs:389).  Once R is full `worst` only shrinks, so a candidate
+          // beyond it can never pass the break test and is dropped.
+          const float drop = (r_len == ef) ? A_d[r_len - 1] : INFINITY;
+          const bool keep = lane < m && !(d > drop);
+          const bool to_win = keep && d < o_min;
+          const bool to_ovf = keep && !to_win;
+          if (__any_sync(kFullMask, to_win) || c_head != 0) {
+            c_len = rank_merge<true>(C_d, C_id, c_head, c_len, D_d, D_id, ef, to_win, d, cid, tmp_ub, lane, &dummy, ovf,
+                                     &o_cnt, a.f_ocap, &o_min, drop, &o_overflow);
+            c_head = 0;
+            float* td = C_d; C_d = D_d; D_d = td;
+            uint32_t* ti = C_id; C_id = D_id; D_id = ti;
+          }
+          const uint32_t omask = __ballot_sync(kFullMask, to_ovf);
+          if (omask) {
+            if (to_ovf) {
+              const uint32_t o = o_cnt + __popc(omask & ((1u << lane) - 1));
+              if (o < a.f_ocap) ovf[o] = make_uint2(__float_as_uint(d), cid);
+              else o_overflow = true;
+            }
+            o_cnt += __popc(omask);
+            float dm = to_ovf ? d : INFINITY;
+#pragma unroll
+            for (uint32_t off = 16; off >= 1; off >>= 1) dm = fminf(dm, __shfl_xor_sync(kFullMask, dm, off));
+            o_min = fminf(o_min, dm);
+            if (__any_sync(kFullMask, o_overflow)) o_overflow = true;
+          }
+          __syncwarp();
+          if (o_overflow) break;
+        }
+        len = r_len;
+        if (o_overflow) len = 0xFFFFFFFEu;  // candidate overflow buffer exhausted: reported through out_counts
+      } else {
       // level-0 beam search (search.rs:311-350) on one sorted list
       if (lane == 0) {
         A_d[0] = cur_d;
@@ -470,6 +674,7 @@ __global__ void __launch_bounds__(128, 5) hnsw_search_kernel(const SearchArgs a)
         __syncwarp();
         if (t.dbg) c_mrg += (uint32_t)(clock64() - h3);
       }
+      }  // !FILTERED
     }
     if (t.dbg && lane == 0) {
       const long long q_t1 = clock64();
@@ -498,6 +703,8 @@ __global__ void __launch_bounds__(128, 5) hnsw_search_kernel(const SearchArgs a)
     }
 
     // ---- finalize_results(k) (search.rs:245-252) + SearchResult mapping (mod.rs:1159-1171) ----
+    const bool f_fail = FILTERED && len == 0xFFFFFFFEu;
+    if (f_fail) len = 0;
     const uint32_t count = min(len, a.k);
     for (uint32_t i = lane; i < a.k; i += 32) {
       const size_t o = (size_t)qi * a.k + i;
@@ -513,7 +720,7 @@ __global__ void __launch_bounds__(128, 5) hnsw_search_kernel(const SearchArgs a)
       }
     }
     if (lane == 0) {
-      a.out_counts[qi] = count;
+      a.out_counts[qi] = f_fail ? 0xFFFFFFFEu : count;
       if (a.out_stats) {
         uint32_t* s = a.out_stats + (size_t)qi * 4;
         s[0] = n_dist;

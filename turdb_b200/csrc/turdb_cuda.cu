@@ -375,7 +375,7 @@ int32_t turdb_cuda_index_profile_read(turdb_cuda_index* idx, float* main_ms, flo
 // traversal launch
 // ------------------------------------------------------------------------------------------
 static TeamLayout make_layout(uint32_t ds, uint32_t ef, uint32_t hash_bits, uint32_t n_slots, bool global_visited,
-                              uint64_t n_nodes) {
+                              uint64_t n_nodes, bool filtered = false) {
   TeamLayout L{};
   L.vec_bytes = ds * 4;
   const uint32_t pad_words = (8 + 32 - (ds & 31)) & 31;
@@ -390,6 +390,7 @@ static TeamLayout make_layout(uint32_t ds, uint32_t ef, uint32_t hash_bits, uint
   L.off_ctl = off;   off += 32;
   L.off_q = off;     off += (ds * 4 + 15) & ~15u;
   L.off_list = off;  off += ef * 16;
+  L.off_clist = off; off += filtered ? ef * 16 : 0;  // search_filtered: candidate window (double-buffered)
   L.off_cand = off;  off += 384;  // cand_ids[32], cand_d[32], tmp_ub[32]
   L.off_hash = off;  off += global_visited ? 0 : ((L.hash16 ? 2u : 4u) << hash_bits);
   off = (off + 127) & ~127u;
@@ -398,10 +399,10 @@ static TeamLayout make_layout(uint32_t ds, uint32_t ef, uint32_t hash_bits, uint
   return L;
 }
 
-template <int METRIC, bool GV>
+template <int METRIC, bool GV, bool FILT>
 static cudaError_t launch_search(const SearchArgs& a, uint32_t warps, int num_sms, uint32_t max_ctas,
                                  cudaStream_t stream, uint32_t* resident_warps) {
-  auto kern = hnsw_search_kernel<METRIC, GV>;
+  auto kern = hnsw_search_kernel<METRIC, GV, FILT>;
   const size_t smem = (size_t)a.lay.team_bytes;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -417,14 +418,20 @@ static cudaError_t launch_search(const SearchArgs& a, uint32_t warps, int num_sm
   return cudaGetLastError();
 }
 
+template <bool GV, bool FILT>
+static cudaError_t launch_metric2(int metric, const SearchArgs& a, uint32_t warps, int num_sms, uint32_t max_ctas,
+                                  cudaStream_t stream, uint32_t* rw) {
+  switch (metric) {
+    case kCosine: return launch_search<kCosine, GV, FILT>(a, warps, num_sms, max_ctas, stream, rw);
+    case kIP: return launch_search<kIP, GV, FILT>(a, warps, num_sms, max_ctas, stream, rw);
+    default: return launch_search<kL2, GV, FILT>(a, warps, num_sms, max_ctas, stream, rw);
+  }
+}
 template <bool GV>
 static cudaError_t launch_metric(int metric, const SearchArgs& a, uint32_t warps, int num_sms, uint32_t max_ctas,
                                  cudaStream_t stream, uint32_t* rw) {
-  switch (metric) {
-    case kCosine: return launch_search<kCosine, GV>(a, warps, num_sms, max_ctas, stream, rw);
-    case kIP: return launch_search<kIP, GV>(a, warps, num_sms, max_ctas, stream, rw);
-    default: return launch_search<kL2, GV>(a, warps, num_sms, max_ctas, stream, rw);
-  }
+  return a.visible ? launch_metric2<GV, true>(metric, a, warps, num_sms, max_ctas, stream, rw)
+                   : launch_metric2<GV, false>(metric, a, warps, num_sms, max_ctas, stream, rw);
 }
 
 __global__ void fill_empty_results_kernel(uint64_t* rows, uint32_t* nodes, float* dist, uint32_t* counts,
@@ -454,7 +461,6 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
   if (nq == 0) return TURDB_OK;
   if (!d_queries || !d_out_counts || (k && (!d_out_row_ids || !d_out_dist)))
     return fail(TURDB_ERR_INVALID_ARGUMENT, "null query/output pointer");
-  if (d_visible) return fail(TURDB_ERR_UNSUPPORTED, "search_filtered is not implemented on the device yet");
   cudaStream_t stream = (cudaStream_t)stream_;
   DeviceGuard guard(idx->device);
   if (!guard.ok) return fail(TURDB_ERR_CUDA, "cudaSetDevice(%d) failed", idx->device);
@@ -486,7 +492,7 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
     const uint32_t sm_bytes = budget + 1024;
     uint32_t best = 0;
     for (uint32_t cand = 8; cand <= 32; cand += 8) {
-      TeamLayout L = make_layout(ds, ef, hash_bits, cand, false, nn);
+      TeamLayout L = make_layout(ds, ef, hash_bits, cand, false, nn, d_visible != nullptr);
       if (L.team_bytes > budget) break;
       uint32_t occ = std::min(16u, sm_bytes / (L.team_bytes + 1024));
       uint32_t score = occ * std::min(cand, 24u);
@@ -497,9 +503,10 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
     }
     if (!slots) slots = 8;
   }
-  TeamLayout lay = make_layout(ds, ef, hash_bits, slots, false, nn);
-  while (lay.team_bytes > budget && lay.n_groups > 1) lay = make_layout(ds, ef, hash_bits, lay.n_groups * 8 - 8, false, nn);
-  while (lay.team_bytes > budget && hash_bits > 8) lay = make_layout(ds, ef, --hash_bits, lay.n_groups * 8, false, nn);
+  const bool filt = d_visible != nullptr;
+  TeamLayout lay = make_layout(ds, ef, hash_bits, slots, false, nn, filt);
+  while (lay.team_bytes > budget && lay.n_groups > 1) lay = make_layout(ds, ef, hash_bits, lay.n_groups * 8 - 8, false, nn, filt);
+  while (lay.team_bytes > budget && hash_bits > 8) lay = make_layout(ds, ef, --hash_bits, lay.n_groups * 8, false, nn, filt);
   if (lay.team_bytes > budget)
     return fail(TURDB_ERR_UNSUPPORTED, "dim %u / ef %u need %u B of shared memory per query (> %u)", idx->ix.dim, ef, lay.team_bytes, budget);
 
@@ -525,13 +532,28 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
   a.global_visited = nullptr;
   a.vis_words = 0;
   a.dbg = idx->d_dbg;
+  a.visible = d_visible;
+  a.f_ovf = nullptr;
+  a.f_ocap = 0;
+  uint2* d_fovf = nullptr;
+  if (filt) {
+    // candidate overflow of search_filtered: one buffer per resident CTA (at most 8 per SM at any layout)
+    a.f_ocap = (uint32_t)std::min<uint64_t>(idx->ix.n, 262144);
+    const size_t ctas = (size_t)idx->num_sms * 8;
+    cudaError_t fe = cudaMallocFromPoolAsync(&d_fovf, ctas * a.f_ocap * sizeof(uint2), idx->pool, stream);
+    if (fe != cudaSuccess) {
+      cudaFreeAsync(d_scratch, stream);
+      return fail(TURDB_ERR_OUT_OF_MEMORY, "filtered-search scratch: %s", cudaGetErrorString(fe));
+    }
+    a.f_ovf = d_fovf;
+  }
   cudaEvent_t* pev = nullptr;
   {
     std::lock_guard<std::mutex> lk(idx->mu);
     if (idx->prof_used < idx->prof_capacity) pev = &idx->prof_events[3 * idx->prof_used++];
   }
   if (pev) cudaEventRecord(pev[0], stream);
-  cudaError_t e = launch_metric<false>(metric, a, warps, idx->num_sms, nq, stream, nullptr);
+  cudaError_t e = launch_metric<false>(metric, a, warps, idx->num_sms, filt ? std::min<uint32_t>(nq, idx->num_sms * 8) : nq, stream, nullptr);
   if (pev) cudaEventRecord(pev[1], stream);
   if (e != cudaSuccess) {
     cudaFreeAsync(d_scratch, stream);
@@ -541,7 +563,7 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
   // exact fallback for queries whose shared visited table filled: same kernel, one bit per node in
   // global memory.  Always enqueued (no host sync); exits immediately when the list is empty.
   {
-    TeamLayout glay = make_layout(ds, ef, 8, lay.n_groups * 8, true, nn);
+    TeamLayout glay = make_layout(ds, ef, 8, lay.n_groups * 8, true, nn, filt);
     SearchArgs b = a;
     b.lay = glay;
     b.work_counter = d_scratch + 2;
@@ -560,6 +582,7 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
       return fail(TURDB_ERR_CUDA, "fallback traversal launch failed: %s", cudaGetErrorString(e));
     }
   }
+  if (d_fovf) cudaFreeAsync(d_fovf, stream);
   CUDA_TRY(cudaFreeAsync(d_scratch, stream));
   return TURDB_OK;
 }
@@ -628,6 +651,11 @@ extern "C" int32_t turdb_cuda_search_batch(turdb_cuda_index* idx, const float* q
   cudaStreamSynchronize(stream);
   cudaStreamDestroy(stream);
   if (e != cudaSuccess) return fail(TURDB_ERR_CUDA, "search failed: %s", cudaGetErrorString(e));
+  if (visible)
+    for (uint32_t i = 0; i < nq; ++i)
+      if (out_counts[i] == 0xFFFFFFFEu)
+        return fail(TURDB_ERR_UNSUPPORTED, "search_filtered: candidate overflow buffer exhausted for query %u "
+                    "(filter leaves too few visible nodes); use bruteforce_topk", i);
   return TURDB_OK;
 }
 
