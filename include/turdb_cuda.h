@@ -122,9 +122,9 @@ int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const float* d_que
 
 /* Tunables of the traversal kernel (0 = automatic).  warps_per_cta (1..4) warps cooperate on one
  * query, staging_slots (8..32) neighbour vectors are in flight per query, hash_bits sizes the
- * shared-memory visited table. */
+ * shared-memory visited table, segments = pieces a vector is streamed in through its staging slot. */
 int32_t turdb_cuda_index_set_tuning(turdb_cuda_index* idx, uint32_t warps_per_cta,
-                                    uint32_t staging_slots, uint32_t hash_bits);
+                                    uint32_t staging_slots, uint32_t hash_bits, uint32_t segments);
 
 /*
  * ---- measurement: per-launch device times of the traversal kernel --------------------------

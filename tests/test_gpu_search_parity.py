@@ -69,6 +69,7 @@ def test_shapes(gpu_required, dim, n, ef, k):
     g = ob.OracleGraph.build(x, seed=dim)
     idx = CudaHnswIndex.from_graph(g.export())
     for metric in (ob.L2, ob.COSINE, ob.IP):
+        idx.set_tuning(segments=(0, 3, 2)[metric])  # also exercise explicit piece counts on odd dims
         gpu = idx.search_batch(q, k, ef, DistanceFunction(metric))
         cpu = g.search(q, k, ef, metric)
         same_ids, same_dist = compare(gpu, cpu, k)
@@ -135,12 +136,13 @@ def test_visited_overflow_fallback(gpu_required, small_graph):
     idx.close()
 
 
-@pytest.mark.parametrize("slots,warps", [(8, 1), (16, 2), (32, 4), (24, 3), (16, 4), (32, 1)])
-def test_tunings_do_not_change_results(gpu_required, small_graph, slots, warps):
+@pytest.mark.parametrize("slots,warps,segs", [(8, 1, 1), (16, 2, 1), (32, 4, 1), (24, 3, 2), (16, 4, 4), (32, 1, 3),
+                                              (32, 4, 2), (32, 2, 16), (8, 4, 5)])
+def test_tunings_do_not_change_results(gpu_required, small_graph, slots, warps, segs):
     g, arrays = small_graph
     q = ds.gaussian_latent(300, 128, seed=8)
     idx = CudaHnswIndex.from_graph(arrays)
-    idx.set_tuning(warps_per_cta=warps, staging_slots=slots)
+    idx.set_tuning(warps_per_cta=warps, staging_slots=slots, segments=segs)
     gpu = idx.search_batch(q, 10, 64)
     cpu = g.search(q, 10, 64, n_threads=8)
     same_ids, same_dist = compare(gpu, cpu, 10)

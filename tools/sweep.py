@@ -47,9 +47,9 @@ del xd
 res = []
 ref_nodes = None
 for tun in args.tunings.split(";"):
-    warps, slots, hb = [int(v) for v in tun.split(",")]
+    warps, slots, hb, segs = ([int(v) for v in tun.split(",")] + [0])[:4]
     try:
-        idx.set_tuning(warps, slots, hb)
+        idx.set_tuning(warps, slots, hb, segs)
         def run():
             idx.search_batch_device(dq.data_ptr(), args.nq, args.k, args.ef, args.metric, rows.data_ptr(), dist.data_ptr(),
                                     cnt.data_ptr(), nodes.data_ptr(), stats.data_ptr(), 0, stream)
@@ -79,7 +79,7 @@ for tun in args.tunings.split(";"):
         rec = None
         if gt is not None:
             rec = float(np.mean([len(set(nd[i].tolist()) & set(gt[i].tolist())) / args.k for i in range(1000)]))
-        r = dict(warps=warps, slots=slots, hash_bits=hb, kernel_ms=ms, overflow_ms=float(om.mean()), qps=args.nq / ms * 1e3,
+        r = dict(warps=warps, slots=slots, hash_bits=hb, segs=segs, kernel_ms=ms, overflow_ms=float(om.mean()), qps=args.nq / ms * 1e3,
                  gbs=nbytes / ms / 1e6, n_dist=float(st[:, 0].mean()), n_exp=float(st[:, 2].mean()), recall=rec,
                  same_as_first=bool(np.array_equal(nd, ref_nodes)))
         print(json.dumps(r), flush=True)

@@ -53,7 +53,7 @@ def load():
     L.turdb_cuda_index_create.argtypes = [C.POINTER(Graph), i32, C.POINTER(vp)]
     L.turdb_cuda_index_destroy.argtypes = [vp]
     L.turdb_cuda_index_info.argtypes = [vp, pu64, pu32, pu32, pu32, pu64]
-    L.turdb_cuda_index_set_tuning.argtypes = [vp, u32, u32, u32]
+    L.turdb_cuda_index_set_tuning.argtypes = [vp, u32, u32, u32, u32]
     L.turdb_cuda_index_debug_counters.argtypes = [vp, i32, pu64]
     L.turdb_cuda_index_profile_begin.argtypes = [vp, u32]
     L.turdb_cuda_index_profile_read.argtypes = [vp, pf, pf, u32, pu32]

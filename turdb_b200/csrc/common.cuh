@@ -99,14 +99,12 @@ __device__ __forceinline__ float2 unpack2(uint64_t v) {
   return f;
 }
 
-// a, b: 8 B aligned float pointers (shared or global); p = lane & 3.  Returns squared L2.
-__device__ __forceinline__ float quad_l2sq(const float* a, const float* b, uint32_t dim, uint32_t p) {
-  const uint64_t* av = reinterpret_cast<const uint64_t*>(a) + p;
-  const uint64_t* bv = reinterpret_cast<const uint64_t*>(b) + p;
-  uint64_t acc = 0ull;
-  const uint32_t steps = dim >> 3;
+// Accumulate `nsteps` AVX steps (8 elements each) of a quad's chain.  av/bv already point at this lane's
+// float2 of the first step (base + 8*step0 + 2p floats); consecutive steps are 4 uint64 apart.
+template <bool L2>
+__device__ __forceinline__ uint64_t quad_accum(uint64_t acc, const uint64_t* av, const uint64_t* bv, uint32_t nsteps) {
   uint32_t t = 0;
-  for (; t + 8 <= steps; t += 8, av += 32, bv += 32) {
+  for (; t + 8 <= nsteps; t += 8, av += 32, bv += 32) {
     uint64_t x[8], y[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
@@ -115,42 +113,53 @@ __device__ __forceinline__ float quad_l2sq(const float* a, const float* b, uint3
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const uint64_t d = sub2(x[u], y[u]);
-      acc = fma2(d, d, acc);
+      if (L2) {
+        const uint64_t d = sub2(x[u], y[u]);
+        acc = fma2(d, d, acc);
+      } else {
+        acc = fma2(x[u], y[u], acc);
+      }
     }
   }
-  for (; t < steps; ++t, av += 4, bv += 4) {
-    const uint64_t d = sub2(av[0], bv[0]);
-    acc = fma2(d, d, acc);
+  for (; t < nsteps; ++t, av += 4, bv += 4) {
+    if (L2) {
+      const uint64_t d = sub2(av[0], bv[0]);
+      acc = fma2(d, d, acc);
+    } else {
+      acc = fma2(av[0], bv[0], acc);
+    }
   }
+  return acc;
+}
+
+// horizontal sum + the unfused scalar tail (distance.rs:120-126 / 225-229); a_tail/b_tail point at element 8*steps
+template <bool L2>
+__device__ __forceinline__ float quad_finish(uint64_t acc, const float* a_tail, const float* b_tail, uint32_t ntail) {
   float r = quad_hsum(unpack2(acc));
-  for (uint32_t i = steps << 3; i < dim; ++i) {  // unfused scalar tail, distance.rs:122-126
-    float d = __fsub_rn(a[i], b[i]);
-    r = __fadd_rn(r, __fmul_rn(d, d));
+  for (uint32_t i = 0; i < ntail; ++i) {
+    if (L2) {
+      const float d = __fsub_rn(a_tail[i], b_tail[i]);
+      r = __fadd_rn(r, __fmul_rn(d, d));
+    } else {
+      r = __fadd_rn(r, __fmul_rn(a_tail[i], b_tail[i]));
+    }
   }
   return r;
 }
 
-__device__ __forceinline__ float quad_dot(const float* a, const float* b, uint32_t dim, uint32_t p) {
-  const uint64_t* av = reinterpret_cast<const uint64_t*>(a) + p;
-  const uint64_t* bv = reinterpret_cast<const uint64_t*>(b) + p;
-  uint64_t acc = 0ull;
+// a, b: 8 B aligned float pointers (shared or global); p = lane & 3.  Returns squared L2.
+__device__ __forceinline__ float quad_l2sq(const float* a, const float* b, uint32_t dim, uint32_t p) {
   const uint32_t steps = dim >> 3;
-  uint32_t t = 0;
-  for (; t + 8 <= steps; t += 8, av += 32, bv += 32) {
-    uint64_t x[8], y[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      x[u] = av[4 * u];
-      y[u] = bv[4 * u];
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) acc = fma2(x[u], y[u], acc);
-  }
-  for (; t < steps; ++t, av += 4, bv += 4) acc = fma2(av[0], bv[0], acc);
-  float r = quad_hsum(unpack2(acc));
-  for (uint32_t i = steps << 3; i < dim; ++i) r = __fadd_rn(r, __fmul_rn(a[i], b[i]));
-  return r;
+  const uint64_t acc = quad_accum<true>(0ull, reinterpret_cast<const uint64_t*>(a) + p,
+                                        reinterpret_cast<const uint64_t*>(b) + p, steps);
+  return quad_finish<true>(acc, a + (steps << 3), b + (steps << 3), dim & 7);
+}
+
+__device__ __forceinline__ float quad_dot(const float* a, const float* b, uint32_t dim, uint32_t p) {
+  const uint32_t steps = dim >> 3;
+  const uint64_t acc = quad_accum<false>(0ull, reinterpret_cast<const uint64_t*>(a) + p,
+                                         reinterpret_cast<const uint64_t*>(b) + p, steps);
+  return quad_finish<false>(acc, a + (steps << 3), b + (steps << 3), dim & 7);
 }
 
 // cosine_avx2's epilogue, distance.rs:279-284

@@ -31,6 +31,9 @@ struct TeamLayout {
   uint32_t n_groups;   // staging groups of 8 slots (1..4), one mbarrier each
   uint32_t stride;     // bytes between staging slots; stride/4 == 8 (mod 32) -> conflict-free quads
   uint32_t vec_bytes;  // ds * 4
+  // a vector streams through its slot in n_segs pieces of seg_steps AVX steps (32 B each); the last piece
+  // also carries the < 8-element tail.  The quad's accumulators live in registers across pieces.
+  uint32_t n_segs, seg_steps;
   uint32_t hash_bits;  // shared visited table has 1 << hash_bits slots
   // compact table (hash16 != 0): 16-bit entries = (displacement+1) << rem_bits | remainder of a
   // bijective hash of the id, so an entry still identifies exactly one node (exact set, half the bytes)
@@ -71,7 +74,7 @@ struct Team {
   float* cand_d;             // [32] results
   const uint8_t* stage;
   uint32_t stage_u32;
-  uint32_t stride, vec_bytes, n_groups;
+  uint32_t stride, vec_bytes, n_groups, n_segs, seg_steps;
   uint32_t phases;           // per-warp parity bits of the groups this warp owns
   float qnorm;
   uint32_t c_issue, c_wait, c_comp;  // diagnostics: cycles spent by this warp per phase
@@ -79,53 +82,69 @@ struct Team {
 };
 
 // Every warp of the team calls this between the two team barriers of a request: chunk c (candidates
-// 8c..8c+7) uses staging group c % G and is handled by warp (c % G) % W.  A warp first requests the
-// first chunk of each group it owns, then waits / reduces / re-arms in chunk order, so all of a hop's
-// vectors are in flight at once whenever the staging holds them.
+// 8c..8c+7) uses staging group c % G and is handled by warp (c % G) % W.  A chunk's vectors stream through
+// their slots in n_segs pieces; a warp keeps one piece of every group it owns in flight, reduces a piece as
+// soon as it lands and immediately requests the next one (of the same chunk, or the first piece of the next
+// chunk mapped to that group).
 template <int METRIC>
 __device__ __forceinline__ void team_distances(const DeviceIndex& ix, Team& t, uint32_t m) {
-  const uint32_t lane = t.lane, p = lane & 3, G = t.n_groups, W = t.n_warps;
+  const uint32_t lane = t.lane, p = lane & 3, G = t.n_groups, W = t.n_warps, S = t.n_segs;
   const uint32_t nchunks = (m + 7) >> 3;
-  auto issue = [&](uint32_t c) {
+  const uint32_t steps = ix.dim >> 3;
+  auto seg_lo = [&](uint32_t sgm) { return min(steps, sgm * t.seg_steps); };
+  auto issue = [&](uint32_t c, uint32_t sgm) {
     const uint32_t g = c % G;
     const uint32_t bar = t.bar0 + 8 * g;
     const uint32_t cnt = min(8u, m - 8 * c);
-    if (lane == 0) mbar_expect_tx(bar, cnt * t.vec_bytes);
+    const uint32_t b0 = seg_lo(sgm) * 32;
+    const uint32_t b1 = (sgm + 1 == S) ? t.vec_bytes : seg_lo(sgm + 1) * 32;
+    if (lane == 0) mbar_expect_tx(bar, cnt * (b1 - b0));
     __syncwarp();
-    if (lane < cnt) {
+    if (lane < cnt && b1 > b0) {
       const uint32_t id = t.cand_ids[8 * c + lane];
-      bulk_g2s(t.stage_u32 + (g * 8 + lane) * t.stride, ix.arena + (size_t)id * ix.ds, t.vec_bytes, bar);
+      bulk_g2s(t.stage_u32 + (g * 8 + lane) * t.stride, reinterpret_cast<const uint8_t*>(ix.arena + (size_t)id * ix.ds) + b0,
+               b1 - b0, bar);
     }
   };
   long long t0 = t.dbg ? clock64() : 0;
   for (uint32_t c = 0; c < min(G, nchunks); ++c)
-    if ((c % G) % W == t.warp) issue(c);
-  if (t.dbg) {
-    long long t1 = clock64();
-    t.c_issue += (uint32_t)(t1 - t0);
-  }
+    if ((c % G) % W == t.warp) issue(c, 0);
+  if (t.dbg) t.c_issue += (uint32_t)(clock64() - t0);
   for (uint32_t c = 0; c < nchunks; ++c) {
     const uint32_t g = c % G;
     if (g % W != t.warp) continue;
     const uint32_t slot = 8 * c + (lane >> 2);
     float nb = 0.f;
     if (METRIC == kCosine && slot < m) nb = __ldg(ix.norm2 + t.cand_ids[slot]);
-    long long w0 = t.dbg ? clock64() : 0;
-    mbar_wait(t.bar0 + 8 * g, (t.phases >> g) & 1u);
-    long long w1 = t.dbg ? clock64() : 0;
-    t.c_wait += (uint32_t)(w1 - w0);
-    t.phases ^= (1u << g);
-    const float* b = reinterpret_cast<const float*>(t.stage + (g * 8 + (lane >> 2)) * t.stride);
-    const float raw = (METRIC == kL2) ? quad_l2sq(t.q, b, ix.dim, p) : quad_dot(t.q, b, ix.dim, p);
+    const uint8_t* sb = t.stage + (g * 8 + (lane >> 2)) * t.stride;
+    uint64_t acc = 0ull;
+    float raw = 0.f;
+    for (uint32_t sgm = 0; sgm < S; ++sgm) {
+      long long w0 = t.dbg ? clock64() : 0;
+      mbar_wait(t.bar0 + 8 * g, (t.phases >> g) & 1u);
+      long long w1 = t.dbg ? clock64() : 0;
+      t.c_wait += (uint32_t)(w1 - w0);
+      t.phases ^= (1u << g);
+      const uint32_t s0 = seg_lo(sgm), s1 = (sgm + 1 == S) ? steps : seg_lo(sgm + 1);
+      const uint64_t* av = reinterpret_cast<const uint64_t*>(t.q + 8 * s0) + p;
+      const uint64_t* bv = reinterpret_cast<const uint64_t*>(sb) + p;
+      acc = (METRIC == kL2) ? quad_accum<true>(acc, av, bv, s1 - s0) : quad_accum<false>(acc, av, bv, s1 - s0);
+      if (sgm + 1 == S) {
+        const float* bt = reinterpret_cast<const float*>(sb) + 8 * (s1 - s0);
+        raw = (METRIC == kL2) ? quad_finish<true>(acc, t.q + 8 * steps, bt, ix.dim & 7)
+                              : quad_finish<false>(acc, t.q + 8 * steps, bt, ix.dim & 7);
+      }
+      __syncwarp();
+      if (t.dbg) t.c_comp += (uint32_t)(clock64() - w1);
+      if (sgm + 1 < S) issue(c, sgm + 1);
+      else if (c + G < nchunks) issue(c + G, 0);
+    }
     if (p == 0 && slot < m) {
       float d = raw;
       if (METRIC == kIP) d = -raw;  // inner_product_avx2, distance.rs:240-242
       if (METRIC == kCosine) d = cosine_finish(raw, t.qnorm, nb);
       t.cand_d[slot] = d;
     }
-    __syncwarp();
-    if (t.dbg) t.c_comp += (uint32_t)(clock64() - w1);
-    if (c + G < nchunks) issue(c + G);
   }
 }
 
@@ -298,9 +317,9 @@ __global__ void __launch_bounds__(128, 5) hnsw_search_kernel(const SearchArgs a)
   const uint32_t tid = threadIdx.x, nthreads = blockDim.x;
   const uint32_t lane = tid & 31, warp = tid >> 5;
   float* qs = reinterpret_cast<float*>(smem + a.lay.off_q);
-  float* A_d = reinterpret_cast<float*>(smem + a.lay.off_list);
+  float* A_d = reinterpret_cast<float*>(smem + a.lay.off_list);  // result list (sorted, ef slots)
   uint32_t* A_id = reinterpret_cast<uint32_t*>(A_d + a.ef);
-  float* B_d = reinterpret_cast<float*>(A_id + a.ef);
+  float* B_d = reinterpret_cast<float*>(A_id + a.ef);             // second buffer: filtered search only
   uint32_t* B_id = reinterpret_cast<uint32_t*>(B_d + a.ef);
   float* C_d = reinterpret_cast<float*>(smem + a.lay.off_clist);  // filtered search: candidate window (x2)
   uint32_t* C_id = reinterpret_cast<uint32_t*>(C_d + a.ef);
@@ -328,6 +347,8 @@ __global__ void __launch_bounds__(128, 5) hnsw_search_kernel(const SearchArgs a)
   t.stride = a.lay.stride;
   t.vec_bytes = a.lay.vec_bytes;
   t.n_groups = a.lay.n_groups;
+  t.n_segs = a.lay.n_segs;
+  t.seg_steps = a.lay.seg_steps;
   t.phases = 0;
   t.qnorm = 0.f;
   t.c_issue = t.c_wait = t.c_comp = 0;
@@ -649,28 +670,37 @@ __global__ void __launch_bounds__(128, 5) hnsw_search_kernel(const SearchArgs a)
           rank += (db < d || (db == d && bsrc < lane)) ? 1u : 0u;
         }
         __syncwarp();
-        for (uint32_t i = lane; i < len; i += 32) {
-          uint32_t s = 0;
-          for (uint32_t j = 0; j < mp; ++j) s += (tmp_ub[j] <= i) ? 1u : 0u;
-          const uint32_t np = i + s;
-          if (np < ef) {
-            B_d[np] = A_d[i];
-            B_id[np] = A_id[i];
+        // in place: an old entry moves right by the number of new entries inserted at or before it, so
+        // 32-entry blocks are moved from the top down (read block, sync, write block)
+        for (int32_t blk = (int32_t)((len - 1) >> 5); blk >= 0; --blk) {
+          const uint32_t i = (uint32_t)blk * 32 + lane;
+          float od = 0.f;
+          uint32_t oi = 0, np = 0xFFFFFFFFu;
+          if (i < len) {
+            od = A_d[i];
+            oi = A_id[i];
+            uint32_t sft = 0;
+            for (uint32_t j = 0; j < mp; ++j) sft += (tmp_ub[j] <= i) ? 1u : 0u;
+            np = i + sft;
           }
+          __syncwarp();
+          if (np < ef) {
+            A_d[np] = od;
+            A_id[np] = oi;
+          }
+          __syncwarp();
         }
         uint32_t my_np = 0xFFFFFFFFu;
         if (elig) {
           const uint32_t np = ub + rank;
           if (np < ef) {
-            B_d[np] = d;
-            B_id[np] = cid;
+            A_d[np] = d;
+            A_id[np] = cid;
             my_np = np;
           }
         }
         scan_from = min(scan_from, __reduce_min_sync(kFullMask, my_np));
         len = min(len + mp, ef);
-        float* td = A_d; A_d = B_d; B_d = td;
-        uint32_t* ti = A_id; A_id = B_id; B_id = ti;
         __syncwarp();
         if (t.dbg) c_mrg += (uint32_t)(clock64() - h3);
       }

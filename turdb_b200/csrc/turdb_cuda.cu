@@ -66,7 +66,7 @@ struct turdb_cuda_index {
   __nv_bfloat16* d_arena_bf16 = nullptr;  // exact path operand, built lazily
   cudaMemPool_t pool = nullptr;            // per-index stream-ordered scratch pool (never trimmed)
   uint64_t device_bytes = 0;
-  uint32_t tune_warps = 0, tune_slots = 0, tune_hash_bits = 0;
+  uint32_t tune_warps = 0, tune_slots = 0, tune_hash_bits = 0, tune_segs = 0;
   // profiling ring: 3 events per call (before main, after main, after overflow pass)
   std::vector<cudaEvent_t> prof_events;
   uint32_t prof_capacity = 0, prof_used = 0;
@@ -304,15 +304,17 @@ int32_t turdb_cuda_index_info(const turdb_cuda_index* idx, uint64_t* n, uint32_t
 }
 
 int32_t turdb_cuda_index_set_tuning(turdb_cuda_index* idx, uint32_t warps_per_cta, uint32_t staging_slots,
-                                    uint32_t hash_bits) {
+                                    uint32_t hash_bits, uint32_t segments) {
   if (!idx) return fail(TURDB_ERR_INVALID_ARGUMENT, "idx is null");
   if (warps_per_cta > 4) return fail(TURDB_ERR_INVALID_ARGUMENT, "warps_per_cta must be <= 4");
   if (staging_slots > 32 || (staging_slots & 7)) return fail(TURDB_ERR_INVALID_ARGUMENT, "staging_slots must be 0, 8, 16, 24 or 32");
   if (hash_bits != 0 && (hash_bits < 8 || hash_bits > 15)) return fail(TURDB_ERR_INVALID_ARGUMENT, "hash_bits must be 0 or 8..15");
+  if (segments > 16) return fail(TURDB_ERR_INVALID_ARGUMENT, "segments must be <= 16");
   std::lock_guard<std::mutex> lk(idx->mu);
   idx->tune_warps = warps_per_cta;
   idx->tune_slots = staging_slots;
   idx->tune_hash_bits = hash_bits;
+  idx->tune_segs = segments;
   return TURDB_OK;
 }
 
@@ -374,12 +376,17 @@ int32_t turdb_cuda_index_profile_read(turdb_cuda_index* idx, float* main_ms, flo
 // ------------------------------------------------------------------------------------------
 // traversal launch
 // ------------------------------------------------------------------------------------------
-static TeamLayout make_layout(uint32_t ds, uint32_t ef, uint32_t hash_bits, uint32_t n_slots, bool global_visited,
-                              uint64_t n_nodes, bool filtered = false) {
+static TeamLayout make_layout(uint32_t dim, uint32_t ds, uint32_t ef, uint32_t hash_bits, uint32_t n_slots, uint32_t n_segs,
+                              bool global_visited, uint64_t n_nodes, bool filtered = false) {
   TeamLayout L{};
   L.vec_bytes = ds * 4;
-  const uint32_t pad_words = (8 + 32 - (ds & 31)) & 31;
-  L.stride = (ds + pad_words) * 4;
+  const uint32_t steps = dim >> 3;
+  n_segs = std::max(1u, std::min(n_segs, std::max(1u, steps)));
+  L.seg_steps = steps ? (steps + n_segs - 1) / n_segs : 0;
+  L.n_segs = L.seg_steps ? (steps + L.seg_steps - 1) / L.seg_steps : 1;
+  const uint32_t slot_words = L.seg_steps * 8 + (ds - steps * 8);  // one piece + the < 8-element tail
+  const uint32_t pad_words = (8 + 32 - (slot_words & 31)) & 31;
+  L.stride = (slot_words + pad_words) * 4;
   L.hash_bits = hash_bits;
   L.n_groups = n_slots / 8;
   L.key_bits = std::max(hash_bits, ceil_log2((uint32_t)std::max<uint64_t>(n_nodes, 2)));
@@ -389,8 +396,8 @@ static TeamLayout make_layout(uint32_t ds, uint32_t ef, uint32_t hash_bits, uint
   L.off_bar = off;   off += 32;
   L.off_ctl = off;   off += 32;
   L.off_q = off;     off += (ds * 4 + 15) & ~15u;
-  L.off_list = off;  off += ef * 16;
-  L.off_clist = off; off += filtered ? ef * 16 : 0;  // search_filtered: candidate window (double-buffered)
+  L.off_list = off;  off += filtered ? ef * 16 : ef * 8;  // result list (double-buffered only when filtered)
+  L.off_clist = off; off += filtered ? ef * 16 : 0;       // search_filtered: candidate window (double-buffered)
   L.off_cand = off;  off += 384;  // cand_ids[32], cand_d[32], tmp_ub[32]
   L.off_hash = off;  off += global_visited ? 0 : ((L.hash16 ? 2u : 4u) << hash_bits);
   off = (off + 127) & ~127u;
@@ -473,40 +480,56 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
     return TURDB_OK;
   }
 
-  uint32_t tw, ts, th;
+  uint32_t tw, ts, th, tg;
   {
     std::lock_guard<std::mutex> lk(idx->mu);
     tw = idx->tune_warps;
     ts = idx->tune_slots;
     th = idx->tune_hash_bits;
+    tg = idx->tune_segs;
   }
-  const uint32_t ds = idx->ix.ds;
+  const uint32_t ds = idx->ix.ds, dim = idx->ix.dim;
   uint32_t hash_bits = th ? th : std::min(15u, std::max(9u, ceil_log2(ef * 64)));
   const uint32_t warps = tw ? std::min(tw, 4u) : 4u;  // team size: warps cooperating on one query
   const uint32_t budget = (uint32_t)idx->max_smem_optin;
   const uint64_t nn = idx->ix.n;
-  uint32_t slots = ts;
-  if (!slots) {
-    // most neighbour vectors in flight per SM: resident queries x staging slots (a hop rarely has
-    // more than ~24 unvisited neighbours); ties go to the deeper staging
-    const uint32_t sm_bytes = budget + 1024;
-    uint32_t best = 0;
-    for (uint32_t cand = 8; cand <= 32; cand += 8) {
-      TeamLayout L = make_layout(ds, ef, hash_bits, cand, false, nn, d_visible != nullptr);
-      if (L.team_bytes > budget) break;
-      uint32_t occ = std::min(16u, sm_bytes / (L.team_bytes + 1024));
-      uint32_t score = occ * std::min(cand, 24u);
-      if (score >= best) {
-        best = score;
-        slots = cand;
-      }
-    }
-    if (!slots) slots = 8;
-  }
   const bool filt = d_visible != nullptr;
-  TeamLayout lay = make_layout(ds, ef, hash_bits, slots, false, nn, filt);
-  while (lay.team_bytes > budget && lay.n_groups > 1) lay = make_layout(ds, ef, hash_bits, lay.n_groups * 8 - 8, false, nn, filt);
-  while (lay.team_bytes > budget && hash_bits > 8) lay = make_layout(ds, ef, --hash_bits, lay.n_groups * 8, false, nn, filt);
+  uint32_t slots = ts, segs = tg;
+  if (!slots || !segs) {
+    // Measured at 1M x 384 (tools/sweep.py): whole vectors (1 piece) through 16 slots with 5 resident queries
+    // per SM beat every split; pieces only pay when a whole vector leaves fewer than 4 queries resident
+    // (large dim / large ef).  Within a piece count: most vectors in flight per SM = resident queries x slots
+    // (a hop rarely has more than ~24 unvisited neighbours), ties to the deeper staging.
+    const uint32_t sm_bytes = budget + 1024;
+    double best = -1.0;
+    uint32_t bs = 8, bg = 1;
+    for (uint32_t cg = tg ? tg : 1; cg <= (tg ? tg : 8); ++cg) {
+      uint32_t best_occ = 0;
+      for (uint32_t cs = ts ? ts : 8; cs <= (ts ? ts : 32); cs += 8) {
+        TeamLayout L = make_layout(dim, ds, ef, hash_bits, cs, cg, false, nn, filt);
+        if (L.n_segs != cg || L.team_bytes > budget) continue;
+        if (cg > 1 && L.seg_steps * 32 < 512) continue;
+        const uint32_t occ = std::min(8u, sm_bytes / (L.team_bytes + 1024));
+        const double score = (double)occ * std::min(cs, 24u) / cg + 1e-6 * cs;
+        if (score > best) {
+          best = score;
+          bs = cs;
+          bg = cg;
+        }
+        best_occ = std::max(best_occ, occ);
+      }
+      if (best_occ >= 4) break;  // enough resident queries without (further) splitting
+    }
+    slots = bs;
+    segs = bg;
+  }
+  TeamLayout lay = make_layout(dim, ds, ef, hash_bits, slots, segs, false, nn, filt);
+  while (lay.team_bytes > budget && lay.n_segs < 16 && lay.seg_steps > 8)
+    lay = make_layout(dim, ds, ef, hash_bits, lay.n_groups * 8, lay.n_segs + 1, false, nn, filt);
+  while (lay.team_bytes > budget && lay.n_groups > 1)
+    lay = make_layout(dim, ds, ef, hash_bits, lay.n_groups * 8 - 8, lay.n_segs, false, nn, filt);
+  while (lay.team_bytes > budget && hash_bits > 8)
+    lay = make_layout(dim, ds, ef, --hash_bits, lay.n_groups * 8, lay.n_segs, false, nn, filt);
   if (lay.team_bytes > budget)
     return fail(TURDB_ERR_UNSUPPORTED, "dim %u / ef %u need %u B of shared memory per query (> %u)", idx->ix.dim, ef, lay.team_bytes, budget);
 
@@ -563,7 +586,7 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
   // exact fallback for queries whose shared visited table filled: same kernel, one bit per node in
   // global memory.  Always enqueued (no host sync); exits immediately when the list is empty.
   {
-    TeamLayout glay = make_layout(ds, ef, 8, lay.n_groups * 8, true, nn, filt);
+    TeamLayout glay = make_layout(dim, ds, ef, 8, lay.n_groups * 8, lay.n_segs, true, nn, filt);
     SearchArgs b = a;
     b.lay = glay;
     b.work_counter = d_scratch + 2;

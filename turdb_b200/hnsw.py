@@ -148,8 +148,8 @@ class CudaHnswIndex:
         return dict(n=n.value, dim=dim.value, max_level=ml.value,
                     entry=None if entry.value == INVALID_NODE else entry.value, device_bytes=nbytes.value)
 
-    def set_tuning(self, warps_per_cta: int = 0, staging_slots: int = 0, hash_bits: int = 0):
-        _check(_lib.load().turdb_cuda_index_set_tuning(self._h, warps_per_cta, staging_slots, hash_bits))
+    def set_tuning(self, warps_per_cta: int = 0, staging_slots: int = 0, hash_bits: int = 0, segments: int = 0):
+        _check(_lib.load().turdb_cuda_index_set_tuning(self._h, warps_per_cta, staging_slots, hash_bits, segments))
 
     def debug_counters(self, enable: bool = True):
         """Diagnostics: returns the 16 per-phase cycle counters accumulated so far and (re)arms or disarms them."""
