@@ -49,13 +49,18 @@ def clustered(n: int, dim: int, seed: int, n_centres: int | None = None, sigma: 
     return out
 
 
-def sift_like(n: int, dim: int, seed: int, n_centres: int = 256, centre_seed: int = 13) -> np.ndarray:
-    """SIFT-shaped: non-negative integer-valued floats in 0..218 with cluster structure."""
-    centres = np.abs(np.random.default_rng(centre_seed).standard_normal((n_centres, dim))) * 40.0
+def sift_like(n: int, dim: int, seed: int, latent: int = 16, basis_seed: int = 13, chunk: int = 1 << 18) -> np.ndarray:
+    """SIFT-shaped: non-negative integer-valued floats in 0..218 with SIFT-like low intrinsic dimension
+    (a latent-Gaussian manifold quantised to integers, so squared distances are exact integers with ties)."""
+    a = np.random.default_rng(basis_seed).normal(0.0, 1.0 / np.sqrt(latent), (latent, dim)).astype(np.float32)
     rng = np.random.default_rng(seed)
-    c = rng.integers(0, n_centres, n)
-    x = centres[c] + 15.0 * rng.standard_normal((n, dim))
-    return np.clip(np.rint(np.abs(x)), 0, 218).astype(np.float32)
+    out = np.empty((n, dim), np.float32)
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        z = rng.standard_normal((e - s, latent), dtype=np.float32)
+        y = z @ a + 0.05 * rng.standard_normal((e - s, dim), dtype=np.float32)
+        out[s:e] = np.clip(np.rint(60.0 + 40.0 * y), 0, 218)
+    return out
 
 
 GENERATORS = {

@@ -4,11 +4,14 @@ The reference builds its graph one insert at a time (`insert_with_callback`, src
 ~1.2 ms per insert single-threaded, i.e. hours for the 1M-100M corpora BASELINE.json names.  Benches
 need those graphs in seconds, so this module builds a graph with the SAME structure the reference
 stores — levels drawn by `select_level` (operations.rs:76-83), level-0 lists capped at 32, upper lists
-at 16 (mod.rs:126-127), entry = first node of the top level — but fills the lists from an exact
-k-nearest-neighbour pass per level followed by the reference's own `select_neighbors_heuristic`
-(operations.rs:181-233) and its back-link rule (append if room, re-select on overflow: the
-"reference-intent" mode of SURVEY.md §7).  Distances are squared L2 on the raw vectors, as in the
-reference's insert path (mod.rs:1031,1046).
+at 16 (mod.rs:126-127), entry = first node of the top level — and fills the lists the way insertion
+would, minus the sequential search: node i's forward candidates are its exact nearest neighbours AMONG
+ITS PREDECESSORS (ids < i; insert_connection_phase searches the graph as it stood before i,
+operations.rs:135-171 — this is what gives early nodes the long-range links that keep clusters connected),
+selected with the reference's own `select_neighbors_heuristic` (operations.rs:181-233), then every
+forward edge is offered back (append if room, re-select on overflow: the "reference-intent" mode of
+SURVEY.md §7).  Distances are squared L2 on the raw vectors, as in the reference's insert path
+(mod.rs:1031,1046).
 
 Result files label this provenance "knn-heuristic"; graphs from the oracle's sequential restatement of
 the insert path are labelled "reference-intent" / "verbatim".  Search parity (GPU kernel vs CPU
@@ -35,29 +38,38 @@ def select_levels(randoms: np.ndarray, m: int = 16) -> np.ndarray:
 
 @torch.no_grad()
 def _knn_level(xf: torch.Tensor, norms: torch.Tensor, ids: torch.Tensor, k: int, margin: int, chunk: int):
-    """Exact k-NN (squared L2) of every node in `ids` among `ids`.  Returns local positions [n_l,k], d [n_l,k]."""
+    """Exact k-NN (squared L2) of every node in `ids` among the nodes that precede it in `ids` (insertion order).
+    Returns local positions [n_l,k] (-1 padded) and distances [n_l,k] (inf padded), ascending."""
     n_l = ids.numel()
     whole = n_l == xf.shape[0]
     cols = xf if whole else xf[ids]
     cn = norms if whole else norms[ids]
-    kc = min(k + margin, n_l - 1)
-    out_pos = torch.empty((n_l, k), dtype=torch.int64, device=xf.device)
-    out_d = torch.empty((n_l, k), dtype=torch.float32, device=xf.device)
+    out_pos = torch.full((n_l, k), -1, dtype=torch.int64, device=xf.device)
+    out_d = torch.full((n_l, k), float("inf"), dtype=torch.float32, device=xf.device)
     ar = torch.arange(chunk, device=xf.device)
     for s in range(0, n_l, chunk):
         e = min(n_l, s + chunk)
+        if e <= 1:
+            continue
         rows = cols[s:e]
-        score = rows @ cols.T  # TF32 tensor-core pass (candidates only; re-evaluated in FP32 below)
-        score.mul_(-2.0).add_(cn[None, :])
-        score[ar[: e - s], ar[: e - s] + s] = float("inf")
-        cand = torch.topk(score, kc, dim=1, largest=False, sorted=False).indices
+        pred = cols[: e - 1]  # the last row of the chunk has e-1 predecessors
+        score = rows @ pred.T  # TF32 tensor-core pass (candidates only; re-evaluated in FP32 below)
+        score.mul_(-2.0).add_(cn[None, : e - 1])
+        # row i (global position s+i) may only see columns < s+i
+        score.masked_fill_(torch.arange(e - 1, device=xf.device)[None, :] >= (ar[: e - s, None] + s), float("inf"))
+        kc = min(k + margin, e - 1)
+        cs, cand = torch.topk(score, kc, dim=1, largest=False, sorted=False)
         del score
+        valid = torch.isfinite(cs)
         xc = cols[cand]
         de = ((xc - rows[:, None, :]) ** 2).sum(-1)
+        de = torch.where(valid, de, torch.full_like(de, float("inf")))
         de, o = torch.sort(de, dim=1)
         cand = torch.gather(cand, 1, o)
-        out_pos[s:e] = cand[:, :k]
-        out_d[s:e] = de[:, :k]
+        cand = torch.where(torch.isfinite(de), cand, torch.full_like(cand, -1))
+        kk = min(k, kc)
+        out_pos[s:e, :kk] = cand[:, :kk]
+        out_d[s:e, :kk] = de[:, :kk]
     return out_pos, out_d
 
 
@@ -112,7 +124,7 @@ def _level_lists(xf, norms, ids, cap, knn_k, rev_cap, chunk_rows, chunk_h):
     whole = n_l == xf.shape[0]
     cols = xf if whole else xf[ids]
     k = min(knn_k, n_l - 1)
-    pos, d = _knn_level(xf, norms, ids, k, margin=16, chunk=chunk_rows)
+    pos, d = _knn_level(xf, norms, ids, k, margin=16, chunk=chunk_rows)  # forward candidates: predecessors only
     f_ids, f_d, f_cnt = _heuristic(cols, pos, d, cap, chunk_h)
     del pos, d
     # ---- back-links: dst <- src for every forward edge src -> dst that dst does not already hold ----
@@ -161,7 +173,8 @@ def _level_lists(xf, norms, ids, cap, knn_k, rev_cap, chunk_rows, chunk_h):
 
 @torch.no_grad()
 def build_graph(vectors: np.ndarray, m: int = 16, seed: int = 1234, device: str | torch.device = "cuda:0",
-                knn_k: int = 64, row_ids: np.ndarray | None = None, chunk_rows: int = 4096) -> dict:
+                knn_k: int = 64, row_ids: np.ndarray | None = None, chunk_rows: int = 4096,
+                l0_rev: int = MAX_L0, up_rev: int = 64) -> dict:
     """vectors [n, dim] f32 -> the flattened graph dict `CudaHnswIndex.from_graph` / the oracle take."""
     vectors = np.ascontiguousarray(vectors, dtype=np.float32)
     n, dim = vectors.shape
@@ -175,8 +188,8 @@ def build_graph(vectors: np.ndarray, m: int = 16, seed: int = 1234, device: str 
         xf = torch.from_numpy(vectors).to(dev)
         norms = (xf * xf).sum(1)
         lv = torch.from_numpy(levels.astype(np.int64)).to(dev)
-        chunk_h = max(256, min(8192, (1 << 28) // max(1, (knn_k + 32) * dim)))
-        l0, l0_cnt = _level_lists(xf, norms, torch.arange(n, device=dev), MAX_L0, knn_k, MAX_L0, chunk_rows, chunk_h)
+        chunk_h = max(256, min(8192, (1 << 28) // max(1, (knn_k + max(l0_rev, up_rev)) * dim)))
+        l0, l0_cnt = _level_lists(xf, norms, torch.arange(n, device=dev), MAX_L0, knn_k, l0_rev, chunk_rows, chunk_h)
         l0_adj = torch.where(l0 >= 0, l0, torch.full_like(l0, INVALID)).to(torch.int64).cpu().numpy().astype(np.uint32)
         n_slots = int(levels.astype(np.int64).sum())
         up_base = np.full(n, INVALID, np.uint32)
@@ -187,7 +200,7 @@ def build_graph(vectors: np.ndarray, m: int = 16, seed: int = 1234, device: str 
         up_cnt = np.zeros(n_slots, np.uint8)
         for level in range(1, max_level + 1):
             ids = torch.nonzero(lv >= level).squeeze(1)
-            lists, cnt = _level_lists(xf, norms, ids, MAX_UP, 2 * m, MAX_UP, chunk_rows, chunk_h)
+            lists, cnt = _level_lists(xf, norms, ids, MAX_UP, 2 * m, up_rev, chunk_rows, chunk_h)
             glob = torch.where(lists >= 0, ids[lists.clamp(min=0)], torch.full_like(lists, INVALID))
             ids_np = ids.cpu().numpy()
             slots = base[ids_np] + (level - 1)
@@ -198,6 +211,6 @@ def build_graph(vectors: np.ndarray, m: int = 16, seed: int = 1234, device: str 
             vectors=vectors,
             row_ids=np.arange(n, dtype=np.uint64) if row_ids is None else np.ascontiguousarray(row_ids, np.uint64),
             levels=levels, l0_adj=l0_adj, l0_cnt=l0_cnt.cpu().numpy().astype(np.uint8), up_base=up_base,
-            up_adj=up_adj, up_cnt=up_cnt, entry=entry, max_level=max_level, provenance="knn-heuristic")
+            up_adj=up_adj, up_cnt=up_cnt, entry=entry, max_level=max_level, provenance="predecessor-knn-heuristic")
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev_tf32
