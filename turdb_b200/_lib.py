@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libturdb_cuda.so")
+LIB_PATH = os.environ.get("TURDB_CUDA_LIB") or os.path.join(HERE, "libturdb_cuda.so")  # override: A/B builds
 
 OK, ERR_INVALID_ARGUMENT, ERR_DIMENSION_MISMATCH, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED, ERR_NO_DEVICE = range(7)
 

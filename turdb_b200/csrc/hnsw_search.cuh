@@ -21,6 +21,12 @@
 
 #include "common.cuh"
 
+// 0: double-buffered list merge (2 x 8 B x ef of shared memory); 1: in-place merge (half the list memory,
+// one more warp sync per 32 entries).  Measured on 1M x 384: see DESIGN.md.
+#ifndef TURDB_MERGE_MODE
+#define TURDB_MERGE_MODE 0
+#endif
+
 namespace turdb {
 
 constexpr uint32_t kDone = 0xFFFFFFFFu;
@@ -87,7 +93,7 @@ struct Team {
 // soon as it lands and immediately requests the next one (of the same chunk, or the first piece of the next
 // chunk mapped to that group).
 template <int METRIC>
-__device__ __forceinline__ void team_distances(const DeviceIndex& ix, Team& t, uint32_t m) {
+__device__ __forceinline__ void team_distances_pieces(const DeviceIndex& ix, Team& t, uint32_t m) {
   const uint32_t lane = t.lane, p = lane & 3, G = t.n_groups, W = t.n_warps, S = t.n_segs;
   const uint32_t nchunks = (m + 7) >> 3;
   const uint32_t steps = ix.dim >> 3;
@@ -146,6 +152,57 @@ __device__ __forceinline__ void team_distances(const DeviceIndex& ix, Team& t, u
       t.cand_d[slot] = d;
     }
   }
+}
+
+// Whole-vector form (n_segs == 1): same dealing of chunks to groups and warps, one bulk copy per vector.
+template <int METRIC>
+__device__ __forceinline__ void team_distances_whole(const DeviceIndex& ix, Team& t, uint32_t m) {
+  const uint32_t lane = t.lane, p = lane & 3, G = t.n_groups, W = t.n_warps;
+  const uint32_t nchunks = (m + 7) >> 3;
+  auto issue = [&](uint32_t c) {
+    const uint32_t g = c % G;
+    const uint32_t bar = t.bar0 + 8 * g;
+    const uint32_t cnt = min(8u, m - 8 * c);
+    if (lane == 0) mbar_expect_tx(bar, cnt * t.vec_bytes);
+    __syncwarp();
+    if (lane < cnt) {
+      const uint32_t id = t.cand_ids[8 * c + lane];
+      bulk_g2s(t.stage_u32 + (g * 8 + lane) * t.stride, ix.arena + (size_t)id * ix.ds, t.vec_bytes, bar);
+    }
+  };
+  long long t0 = t.dbg ? clock64() : 0;
+  for (uint32_t c = 0; c < min(G, nchunks); ++c)
+    if ((c % G) % W == t.warp) issue(c);
+  if (t.dbg) t.c_issue += (uint32_t)(clock64() - t0);
+  for (uint32_t c = 0; c < nchunks; ++c) {
+    const uint32_t g = c % G;
+    if (g % W != t.warp) continue;
+    const uint32_t slot = 8 * c + (lane >> 2);
+    float nb = 0.f;
+    if (METRIC == kCosine && slot < m) nb = __ldg(ix.norm2 + t.cand_ids[slot]);
+    long long w0 = t.dbg ? clock64() : 0;
+    mbar_wait(t.bar0 + 8 * g, (t.phases >> g) & 1u);
+    long long w1 = t.dbg ? clock64() : 0;
+    t.c_wait += (uint32_t)(w1 - w0);
+    t.phases ^= (1u << g);
+    const float* b = reinterpret_cast<const float*>(t.stage + (g * 8 + (lane >> 2)) * t.stride);
+    const float raw = (METRIC == kL2) ? quad_l2sq(t.q, b, ix.dim, p) : quad_dot(t.q, b, ix.dim, p);
+    if (p == 0 && slot < m) {
+      float d = raw;
+      if (METRIC == kIP) d = -raw;  // inner_product_avx2, distance.rs:240-242
+      if (METRIC == kCosine) d = cosine_finish(raw, t.qnorm, nb);
+      t.cand_d[slot] = d;
+    }
+    __syncwarp();
+    if (t.dbg) t.c_comp += (uint32_t)(clock64() - w1);
+    if (c + G < nchunks) issue(c + G);
+  }
+}
+
+template <int METRIC>
+__device__ __forceinline__ void team_distances(const DeviceIndex& ix, Team& t, uint32_t m) {
+  if (t.n_segs == 1) team_distances_whole<METRIC>(ix, t, m);
+  else team_distances_pieces<METRIC>(ix, t, m);
 }
 
 // Leader side of a request: publish m, run the team's distance pass, return this lane's distance.
@@ -670,8 +727,32 @@ __global__ void __launch_bounds__(128, 5) hnsw_search_kernel(const SearchArgs a)
           rank += (db < d || (db == d && bsrc < lane)) ? 1u : 0u;
         }
         __syncwarp();
-        // in place: an old entry moves right by the number of new entries inserted at or before it, so
-        // 32-entry blocks are moved from the top down (read block, sync, write block)
+#if TURDB_MERGE_MODE == 0
+        // double-buffered: every old entry moves right by the number of new entries inserted at or before it
+        for (uint32_t i = lane; i < len; i += 32) {
+          uint32_t sft = 0;
+          for (uint32_t j = 0; j < mp; ++j) sft += (tmp_ub[j] <= i) ? 1u : 0u;
+          const uint32_t np = i + sft;
+          if (np < ef) {
+            B_d[np] = A_d[i];
+            B_id[np] = A_id[i];
+          }
+        }
+        uint32_t my_np = 0xFFFFFFFFu;
+        if (elig) {
+          const uint32_t np = ub + rank;
+          if (np < ef) {
+            B_d[np] = d;
+            B_id[np] = cid;
+            my_np = np;
+          }
+        }
+        {
+          float* td = A_d; A_d = B_d; B_d = td;
+          uint32_t* ti = A_id; A_id = B_id; B_id = ti;
+        }
+#else
+        // in place: 32-entry blocks move from the top down (read block, sync, write block)
         for (int32_t blk = (int32_t)((len - 1) >> 5); blk >= 0; --blk) {
           const uint32_t i = (uint32_t)blk * 32 + lane;
           float od = 0.f;
@@ -699,6 +780,7 @@ __global__ void __launch_bounds__(128, 5) hnsw_search_kernel(const SearchArgs a)
             my_np = np;
           }
         }
+#endif
         scan_from = min(scan_from, __reduce_min_sync(kFullMask, my_np));
         len = min(len + mp, ef);
         __syncwarp();

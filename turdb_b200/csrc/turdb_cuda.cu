@@ -396,7 +396,7 @@ static TeamLayout make_layout(uint32_t dim, uint32_t ds, uint32_t ef, uint32_t h
   L.off_bar = off;   off += 32;
   L.off_ctl = off;   off += 32;
   L.off_q = off;     off += (ds * 4 + 15) & ~15u;
-  L.off_list = off;  off += filtered ? ef * 16 : ef * 8;  // result list (double-buffered only when filtered)
+  L.off_list = off;  off += (filtered || TURDB_MERGE_MODE == 0) ? ef * 16 : ef * 8;  // result list (x2 when double-buffered)
   L.off_clist = off; off += filtered ? ef * 16 : 0;       // search_filtered: candidate window (double-buffered)
   L.off_cand = off;  off += 384;  // cand_ids[32], cand_d[32], tmp_ub[32]
   L.off_hash = off;  off += global_visited ? 0 : ((L.hash16 ? 2u : 4u) << hash_bits);
@@ -498,8 +498,8 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
   if (!slots || !segs) {
     // Measured at 1M x 384 (tools/sweep.py): whole vectors (1 piece) through 16 slots with 5 resident queries
     // per SM beat every split; pieces only pay when a whole vector leaves fewer than 4 queries resident
-    // (large dim / large ef).  Within a piece count: most vectors in flight per SM = resident queries x slots
-    // (a hop rarely has more than ~24 unvisited neighbours), ties to the deeper staging.
+    // (large dim / large ef).  Within a piece count: resident queries x min(slots, 16) — beyond 16 slots the
+    // lost residency costs more than the saved second gather round (measured) —, ties to the deeper staging.
     const uint32_t sm_bytes = budget + 1024;
     double best = -1.0;
     uint32_t bs = 8, bg = 1;
@@ -510,7 +510,7 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
         if (L.n_segs != cg || L.team_bytes > budget) continue;
         if (cg > 1 && L.seg_steps * 32 < 512) continue;
         const uint32_t occ = std::min(8u, sm_bytes / (L.team_bytes + 1024));
-        const double score = (double)occ * std::min(cs, 24u) / cg + 1e-6 * cs;
+        const double score = (double)occ * std::min(cs, 16u) / cg + 1e-6 * cs;
         if (score > best) {
           best = score;
           bs = cs;
