@@ -20,6 +20,7 @@ ap.add_argument("--metric", type=int, default=0)
 ap.add_argument("--gen", default="sift_like")
 ap.add_argument("--rerank", type=int, default=4)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--debug", action="store_true")
 ap.add_argument("--out", default="gpurun_out/exact_probe.json")
 args = ap.parse_args()
 
@@ -55,6 +56,14 @@ for _ in range(args.reps):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / args.reps
+if args.debug:
+    idx.debug_counters(True)
+    run(); torch.cuda.synchronize()
+    c = idx.debug_counters(False).astype(np.float64)
+    tiles = max(c[5], 1)
+    print("dbg cycles per tile: producer wait a_empty %.0f  b_empty %.0f | mma wait a_full %.0f  t_empty %.0f  b_full %.0f | "
+          "epilogue wait t_full %.0f  work %.0f | tiles/CTA %.0f  kernel cycles/CTA(sum over passes) %.0f" %
+          (c[0] / tiles, c[1] / tiles, c[2] / tiles, c[3] / tiles, c[4] / tiles, c[6] / tiles, c[7] / tiles, tiles / 148, c[8] / 148), flush=True)
 flops = 2.0 * args.nq * n * args.dim
 # ground truth: FP32 (no TF32) matmul on a subset
 torch.backends.cuda.matmul.allow_tf32 = False

@@ -97,18 +97,22 @@ extern "C" int32_t turdb_cuda_bruteforce_topk_device(turdb_cuda_index* idx, cons
   uint32_t cap = 2048;
   while (cap < 8 * kprime) cap <<= 1;
 
-  // BF16 copy of the arena: built once per index
+  // BF16 copies of the arena, built once per index: raw rows (L2, IP) and rows scaled by 1/|x| (cosine)
+  const int copy = metric == kCosine ? 1 : 0;
   {
     std::lock_guard<std::mutex> lk(idx->mu);
-    if (!idx->d_arena_bf16) {
-      CUDA_TRY(cudaMalloc(&idx->d_arena_bf16, (size_t)n * kp * 2));
+    __nv_bfloat16*& dst = copy ? idx->d_arena_bf16n : idx->d_arena_bf16;
+    if (!dst) {
+      CUDA_TRY(cudaMalloc(&dst, (size_t)n * kp * 2));
       const uint64_t total = n * kp;
-      to_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(idx->d_arena, dim, ds, kp, n, idx->d_arena_bf16);
+      to_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(idx->d_arena, dim, ds, kp, n,
+                                                                            copy ? idx->d_norm2 : nullptr, dst);
       CUDA_TRY(cudaGetLastError());
       CUDA_TRY(cudaStreamSynchronize(stream));
       idx->device_bytes += (size_t)n * kp * 2;
     }
   }
+  const __nv_bfloat16* d_xb = copy ? idx->d_arena_bf16n : idx->d_arena_bf16;
 
   // scratch: Qb | col_ab | thresh | cand_cnt | overflow | cand_id | cand_key
   size_t off = 0;
@@ -117,13 +121,13 @@ extern "C" int32_t turdb_cuda_bruteforce_topk_device(turdb_cuda_index* idx, cons
     off = (off + bytes + 255) & ~(size_t)255;
     return o;
   };
-  const size_t o_qb = take((size_t)nq * kp * 2), o_ab = take((size_t)n * 8), o_th = take((size_t)nq * 4),
+  const size_t o_qb = take((size_t)nq * kp * 2), o_ab = take((size_t)n * 4), o_th = take((size_t)nq * 4),
                o_cnt = take((size_t)nq * 4), o_ovf = take(4), o_id = take((size_t)nq * cap * 4),
                o_key = take((size_t)nq * cap * 4);
   uint8_t* scr = nullptr;
   CUDA_TRY(cudaMallocFromPoolAsync(&scr, off, idx->pool, stream));
   __nv_bfloat16* d_qb = (__nv_bfloat16*)(scr + o_qb);
-  float2* d_ab = (float2*)(scr + o_ab);
+  float* d_bias = (float*)(scr + o_ab);
   float* d_th = (float*)(scr + o_th);
   uint32_t* d_cnt = (uint32_t*)(scr + o_cnt);
   uint32_t* d_ovf = (uint32_t*)(scr + o_ovf);
@@ -136,19 +140,21 @@ extern "C" int32_t turdb_cuda_bruteforce_topk_device(turdb_cuda_index* idx, cons
 
   {
     const uint64_t total = (uint64_t)nq * kp;
-    to_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_queries, dim, dim, kp, nq, d_qb);
-    col_ab_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(idx->d_norm2, n, metric, d_ab);
+    to_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_queries, dim, dim, kp, nq, nullptr, d_qb);
+    if (metric == kL2) col_bias_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(idx->d_norm2, n, d_bias);
     exact_init_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(d_th, d_cnt, nq, d_ovf);
   }
   CUtensorMap map_q, map_x;
-  if (!make_bf16_map(&map_q, d_qb, nq, kp) || !make_bf16_map(&map_x, idx->d_arena_bf16, n, kp))
+  if (!make_bf16_map(&map_q, d_qb, nq, kp) || !make_bf16_map(&map_x, d_xb, n, kp))
     return bail(fail(TURDB_ERR_CUDA, "cuTensorMapEncodeTiled failed"));
 
-  const size_t fixed_smem = (size_t)k_chunks * kChunkBytes + 2 * kTileN * 8 + 24 * 8 + 16;
+  const size_t fixed_smem = (size_t)k_chunks * kChunkBytes + 4 * kTileN * 4 + 2 * kRing * kTileM * 4 + 24 * 8 + 16;
   const uint32_t n_stages = (uint32_t)std::min<size_t>(kMaxStages, ((size_t)idx->max_smem_optin - fixed_smem) / kChunkBytes);
   if (n_stages < 2) return bail(fail(TURDB_ERR_UNSUPPORTED, "not enough shared memory for the exact path at dim %u", dim));
   const size_t gemm_smem = fixed_smem + (size_t)n_stages * kChunkBytes;
-  cudaError_t e = cudaFuncSetAttribute(exact_gemm_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
+  cudaError_t e = cudaFuncSetAttribute(exact_gemm_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(exact_gemm_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(exact_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cap * 8));
   if (e != cudaSuccess) return bail(fail(TURDB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)));
@@ -170,15 +176,17 @@ extern "C" int32_t turdb_cuda_bruteforce_topk_device(turdb_cuda_index* idx, cons
     a.tiles_per_item = tpi;
     a.n_qblocks = n_qblocks;
     a.n_items = n_qblocks * ((tiles + tpi - 1) / tpi);
-    a.col_ab = d_ab;
+    a.col_bias = d_bias;
     a.thresh = d_th;
     a.cand_cnt = d_cnt;
     a.cand_id = d_cid;
     a.cand_key = d_ckey;
     a.cap = cap;
     a.overflow_flag = d_ovf;
+    a.dbg = idx->d_dbg;
     const uint32_t grid = std::min<uint32_t>(a.n_items, (uint32_t)idx->num_sms);
-    exact_gemm_filter_kernel<<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
+    if (metric == kL2) exact_gemm_filter_kernel<true><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
+    else exact_gemm_filter_kernel<false><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
     exact_threshold_kernel<<<nq, 256, cap * 8, stream>>>(nq, kprime, cap, d_cnt, d_cid, d_ckey, d_th);
     e = cudaGetLastError();
     if (e != cudaSuccess) return bail(fail(TURDB_ERR_CUDA, "exact pass launch failed: %s", cudaGetErrorString(e)));

@@ -78,27 +78,27 @@ __global__ void merge_topk_kernel(const uint64_t* __restrict__ g_rows, const flo
 // ------------------------------------------------------------------------------------------------
 // operand preparation
 // ------------------------------------------------------------------------------------------------
-// FP32 rows [rows][ds] -> BF16 rows [rows][kp] (kp = dim rounded up to 64, zero padded).
+// FP32 rows [rows][ds] -> BF16 rows [rows][kp] (kp = dim rounded up to 64, zero padded).  With `norm2` the row is
+// scaled by 1/|x| first, so that the cosine pass's score q.x/|x| is already its ranking key.
 __global__ void to_bf16_kernel(const float* __restrict__ src, uint32_t dim, uint32_t ds, uint32_t kp,
-                               uint64_t rows, __nv_bfloat16* __restrict__ dst) {
+                               uint64_t rows, const float* __restrict__ norm2, __nv_bfloat16* __restrict__ dst) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * kp) return;
   const uint64_t r = i / kp;
   const uint32_t c = (uint32_t)(i % kp);
-  dst[i] = __float2bfloat16_rn(c < dim ? src[r * ds + c] : 0.f);
+  float v = c < dim ? src[r * ds + c] : 0.f;
+  if (norm2) {
+    const float n2 = norm2[r];
+    v = n2 > 0.f ? v * rsqrtf(n2) : 0.f;
+  }
+  dst[i] = __float2bfloat16_rn(v);
 }
 
-// Ranking key of a BF16 score s for column (vector) j: key = s * a + b, larger = closer.
-//   L2: 2 s - |x|^2      cosine: s / |x|      IP: s          (the query's own norm does not change ranks)
-__global__ void col_ab_kernel(const float* __restrict__ norm2, uint64_t n, int metric, float2* __restrict__ ab) {
+// Ranking key of a score s for column (vector) j, larger = closer (the query's own norm does not change ranks):
+//   L2: s - |x|^2 / 2  (bias array below)      cosine: s on rows pre-scaled by 1/|x|      IP: s
+__global__ void col_bias_kernel(const float* __restrict__ norm2, uint64_t n, float* __restrict__ bias) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float n2 = norm2[i];
-  float2 v;
-  if (metric == kL2) v = make_float2(2.f, -n2);
-  else if (metric == kCosine) v = make_float2(n2 > 0.f ? rsqrtf(n2) : 0.f, 0.f);
-  else v = make_float2(1.f, 0.f);
-  ab[i] = v;
+  if (i < n) bias[i] = -0.5f * norm2[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -160,6 +160,7 @@ constexpr uint32_t kTileN = 128;   // vectors per MMA tile (UMMA N)
 constexpr uint32_t kChunkK = 64;   // BF16 elements per 128 B swizzle row
 constexpr uint32_t kChunkBytes = kTileM * kChunkK * 2;  // 16 KB per operand chunk
 constexpr uint32_t kMaxStages = 8; // B pipeline depth is chosen at launch (as many 16 KB stages as fit)
+constexpr uint32_t kRing = 8;       // candidates a thread parks in shared memory before one atomic reserves their slots
 constexpr uint32_t kExactThreads = 192;  // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
 
 struct ExactArgs {
@@ -168,16 +169,18 @@ struct ExactArgs {
   uint32_t tile_lo, tile_hi;      // vector tiles of this pass
   uint32_t tiles_per_item;        // consecutive tiles one CTA handles for one query block
   uint32_t n_qblocks, n_items;
-  const float2* col_ab;           // [n_vec]
+  const float* col_bias;          // [n_vec] (L2 only)
   const float* thresh;            // [nq] keep keys >= thresh
   uint32_t* cand_cnt;             // [nq]
   uint32_t* cand_id;              // [nq][cap]
   float* cand_key;                // [nq][cap]
   uint32_t cap;
   uint32_t* overflow_flag;
+  unsigned long long* dbg;  // optional [16] cycle counters (diagnostics)
 };
 
-// smem: [A: k_chunks x 16 KB][B: n_stages x 16 KB][col_ab: 2 x 128 float2][barriers][tmem ptr]
+// smem: [A: k_chunks x 16 KB][B: n_stages x 16 KB][col bias: 2 x 128 float + pad][barriers][tmem ptr]
+template <bool BIAS>
 __global__ void __launch_bounds__(kExactThreads, 1)
 exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                          const ExactArgs a) {
@@ -186,8 +189,10 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
   uint8_t* sA = smem;
   uint8_t* sB = sA + (size_t)a.k_chunks * kChunkBytes;
   const uint32_t kStages = a.n_stages;
-  float2* s_ab = reinterpret_cast<float2*>(sB + (size_t)kStages * kChunkBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ab + 2 * kTileN);
+  float* s_bias = reinterpret_cast<float*>(sB + (size_t)kStages * kChunkBytes);  // [2][128] (+ pad to 2 KB)
+  float* ring_key = s_bias + 4 * kTileN;                                          // [kRing][128] pending candidates
+  uint32_t* ring_col = reinterpret_cast<uint32_t*>(ring_key + kRing * kTileM);    // [kRing][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_col + kRing * kTileM);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
   const uint32_t bar_a_full = smem_u32(bars + 0), bar_a_empty = smem_u32(bars + 1);
   const uint32_t bar_b_full = smem_u32(bars + 2), bar_b_empty = smem_u32(bars + 2 + kMaxStages);
@@ -215,6 +220,7 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const unsigned long long k_t0 = a.dbg ? (unsigned long long)clock64() : 0ull;
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -224,14 +230,18 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
         const uint32_t qb = item % a.n_qblocks;
         const uint32_t t0 = a.tile_lo + (item / a.n_qblocks) * a.tiles_per_item;
         const uint32_t t1 = min(a.tile_hi, t0 + a.tiles_per_item);
+        long long c0 = a.dbg ? clock64() : 0;
         mbar_wait(bar_a_empty, a_phase ^ 1);  // previous item's MMAs have drained A
+        if (a.dbg) atomicAdd(a.dbg + 0, (unsigned long long)(clock64() - c0));
         mbar_expect_tx(bar_a_full, a.k_chunks * kChunkBytes);
         for (uint32_t kc = 0; kc < a.k_chunks; ++kc)
           tma_load_2d(smem_u32(sA + (size_t)kc * kChunkBytes), &map_q, (int32_t)(kc * kChunkK), (int32_t)(qb * kTileM), bar_a_full);
         a_phase ^= 1;
         for (uint32_t t = t0; t < t1; ++t) {
           for (uint32_t kc = 0; kc < a.k_chunks; ++kc) {
+            long long c1 = a.dbg ? clock64() : 0;
             mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
+            if (a.dbg) atomicAdd(a.dbg + 1, (unsigned long long)(clock64() - c1));
             mbar_expect_tx(bar_b_full + 8 * stage, kChunkBytes);
             tma_load_2d(smem_u32(sB + (size_t)stage * kChunkBytes), &map_x, (int32_t)(kc * kChunkK), (int32_t)(t * kTileN),
                         bar_b_full + 8 * stage);
@@ -252,15 +262,21 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
       for (uint32_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
         const uint32_t t0 = a.tile_lo + (item / a.n_qblocks) * a.tiles_per_item;
         const uint32_t t1 = min(a.tile_hi, t0 + a.tiles_per_item);
+        long long c2 = a.dbg ? clock64() : 0;
         mbar_wait(bar_a_full, a_phase);
+        if (a.dbg) atomicAdd(a.dbg + 2, (unsigned long long)(clock64() - c2));
         a_phase ^= 1;
         tc_fence_after();
         for (uint32_t t = t0; t < t1; ++t) {
+          long long c3 = a.dbg ? clock64() : 0;
           mbar_wait(bar_t_empty + 8 * acc, acc_phase ^ 1);  // epilogue has drained this accumulator
+          if (a.dbg) atomicAdd(a.dbg + 3, (unsigned long long)(clock64() - c3));
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * kTileN;
           for (uint32_t kc = 0; kc < a.k_chunks; ++kc) {
+            long long c4 = a.dbg ? clock64() : 0;
             mbar_wait(bar_b_full + 8 * stage, phase);
+            if (a.dbg) atomicAdd(a.dbg + 4, (unsigned long long)(clock64() - c4));
             tc_fence_after();
             const uint64_t da = umma_desc_sw128(smem_u32(sA + (size_t)kc * kChunkBytes));
             const uint64_t db = umma_desc_sw128(smem_u32(sB + (size_t)stage * kChunkBytes));
@@ -274,6 +290,7 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
             }
           }
           tc_commit(bar_t_full + 8 * acc);
+          if (a.dbg) atomicAdd(a.dbg + 5, 1ull);  // tiles
           if (++acc == 2) {
             acc = 0;
             acc_phase ^= 1;
@@ -295,58 +312,86 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
       const uint32_t q = qb * kTileM + row;
       const bool q_ok = q < a.nq;
       const float tau = q_ok ? a.thresh[q] : INFINITY;
-      for (uint32_t t = t0; t < t1; ++t) {
-        {  // stage this tile's per-column (a, b); out-of-range columns never pass
-          const uint64_t col = (uint64_t)t * kTileN + et;
-          s_ab[acc * kTileN + et] = col < a.n_vec ? a.col_ab[col] : make_float2(0.f, __int_as_float(0x7fc00000));  // NaN key never passes
+      uint32_t n_pend = 0;
+      // passing keys are parked in a per-thread shared-memory ring; one atomicAdd per flush reserves their slots,
+      // so the L2 round trip of the counter is paid once per ~item instead of once per candidate
+      auto flush = [&]() {
+        const uint32_t pos = atomicAdd(a.cand_cnt + q, n_pend);
+        for (uint32_t i = 0; i < n_pend; ++i) {
+          if (pos + i < a.cap) {
+            a.cand_id[(size_t)q * a.cap + pos + i] = ring_col[i * kTileM + et];
+            a.cand_key[(size_t)q * a.cap + pos + i] = ring_key[i * kTileM + et];
+          } else {
+            *a.overflow_flag = 1u;
+          }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        n_pend = 0;
+      };
+      for (uint32_t t = t0; t < t1; ++t) {
+        if (BIAS) {  // stage this tile's per-column bias (L2: -|x|^2/2)
+          const uint64_t col = (uint64_t)t * kTileN + et;
+          s_bias[acc * kTileN + et] = col < a.n_vec ? a.col_bias[col] : 0.f;
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        long long c6 = (a.dbg && et == 0) ? clock64() : 0;
         mbar_wait(bar_t_full + 8 * acc, acc_phase);
+        long long c7 = (a.dbg && et == 0) ? clock64() : 0;
         tc_fence_after();
+        const uint32_t n_valid = min(kTileN, a.n_vec - t * kTileN);  // columns past the corpus are zero rows
 #pragma unroll 1
         for (uint32_t cb = 0; cb < kTileN / 32; ++cb) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(tmem_base + ((quarter * 32) << 16) + acc * kTileN + cb * 32, v);
-          // keys first (pure register/shared-memory work the scheduler can pipeline), appends after: a key
-          // that beats the running threshold is rare once the first slices have been seen
-          const float4* ab4 = reinterpret_cast<const float4*>(s_ab + acc * kTileN + cb * 32);
-          uint32_t pass = 0;
+          if (BIAS) {
+            const float4* b4 = reinterpret_cast<const float4*>(s_bias + acc * kTileN + cb * 32);
 #pragma unroll
-          for (uint32_t j = 0; j < 32; j += 2) {
-            const float4 ab = ab4[j >> 1];
-            const float k0 = fmaf(__uint_as_float(v[j]), ab.x, ab.y);
-            const float k1 = fmaf(__uint_as_float(v[j + 1]), ab.z, ab.w);
-            v[j] = __float_as_uint(k0);
-            v[j + 1] = __float_as_uint(k1);
-            pass |= (k0 >= tau ? 1u : 0u) << j;
-            pass |= (k1 >= tau ? 1u : 0u) << (j + 1);
+            for (uint32_t j = 0; j < 32; j += 4) {
+              const float4 b = b4[j >> 2];
+              v[j] = __float_as_uint(__uint_as_float(v[j]) + b.x);
+              v[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + b.y);
+              v[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) + b.z);
+              v[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + b.w);
+            }
           }
-          if (pass) {
+          // a key that reaches the running threshold is rare once the first slices have been seen: one
+          // max-tree over the 32 keys, then the per-key test only when something can pass
+          float mx[16];
+#pragma unroll
+          for (uint32_t j = 0; j < 16; ++j) mx[j] = fmaxf(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+#pragma unroll
+          for (uint32_t w = 8; w >= 1; w >>= 1)
+#pragma unroll
+            for (uint32_t j = 0; j < w; ++j) mx[j] = fmaxf(mx[j], mx[j + w]);
+          if (mx[0] >= tau) {
+            const uint32_t lim = n_valid > cb * 32 ? min(32u, n_valid - cb * 32) : 0u;
 #pragma unroll
             for (uint32_t j = 0; j < 32; ++j) {
-              if (pass & (1u << j)) {
-                const uint32_t pos = atomicAdd(a.cand_cnt + q, 1u);
-                if (pos < a.cap) {
-                  a.cand_id[(size_t)q * a.cap + pos] = t * kTileN + cb * 32 + j;
-                  a.cand_key[(size_t)q * a.cap + pos] = __uint_as_float(v[j]);
-                } else {
-                  *a.overflow_flag = 1u;
-                }
+              const float key = __uint_as_float(v[j]);
+              if (key >= tau && j < lim) {
+                ring_key[n_pend * kTileM + et] = key;
+                ring_col[n_pend * kTileM + et] = t * kTileN + cb * 32 + j;
+                if (++n_pend == kRing) flush();
               }
             }
           }
         }
         tc_fence_before();
         __syncwarp();
+        if (a.dbg && et == 0) {
+          atomicAdd(a.dbg + 6, (unsigned long long)(c7 - c6));
+          atomicAdd(a.dbg + 7, (unsigned long long)(clock64() - c7));
+        }
         if (lane == 0) mbar_arrive(bar_t_empty + 8 * acc);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
         }
       }
+      if (n_pend) flush();
     }
   }
 
+  if (a.dbg && threadIdx.x == 0) atomicAdd(a.dbg + 8, (unsigned long long)clock64() - k_t0);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {

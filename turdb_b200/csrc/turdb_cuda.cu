@@ -63,7 +63,8 @@ struct turdb_cuda_index {
   uint32_t* d_up_adj = nullptr;
   uint64_t* d_row_ids = nullptr;
   uint8_t* d_levels = nullptr;
-  __nv_bfloat16* d_arena_bf16 = nullptr;  // exact path operand, built lazily
+  __nv_bfloat16* d_arena_bf16 = nullptr;   // exact path operand (raw rows: L2, IP), built lazily
+  __nv_bfloat16* d_arena_bf16n = nullptr;  // exact path operand (rows scaled by 1/|x|: cosine), built lazily
   cudaMemPool_t pool = nullptr;            // per-index stream-ordered scratch pool (never trimmed)
   uint64_t device_bytes = 0;
   uint32_t tune_warps = 0, tune_slots = 0, tune_hash_bits = 0, tune_segs = 0;
@@ -151,6 +152,7 @@ int32_t turdb_cuda_index_destroy(turdb_cuda_index* idx) {
     cudaFree(idx->d_row_ids);
     cudaFree(idx->d_levels);
     cudaFree(idx->d_arena_bf16);
+    cudaFree(idx->d_arena_bf16n);
     for (cudaEvent_t ev : idx->prof_events) cudaEventDestroy(ev);
     cudaFree(idx->d_dbg);
     if (idx->pool) cudaMemPoolDestroy(idx->pool);
