@@ -141,6 +141,14 @@ int32_t turdb_cuda_index_profile_read(turdb_cuda_index* idx, float* main_ms, flo
  * clock reads per hop); out16 (nullable) receives the counters accumulated since they were armed. */
 int32_t turdb_cuda_index_debug_counters(turdb_cuda_index* idx, int32_t enable, uint64_t* out16);
 
+/* Diagnostics: ceiling of the traversal's access pattern.  Launches ctas_per_sm x SMs CTAs (capped by what
+ * cta_smem_bytes of shared memory per CTA lets an SM hold) that gather uniformly random whole arena rows
+ * with cp.async.bulk into staging_slots slots each, `rounds` copies per slot, no dependencies and no
+ * arithmetic.  out_bytes / out_ms is the random-row gather bandwidth the device sustains at that footprint. */
+int32_t turdb_cuda_index_gather_probe(turdb_cuda_index* idx, uint32_t ctas_per_sm, uint32_t staging_slots,
+                                      uint32_t cta_smem_bytes, uint32_t rounds, float* out_ms,
+                                      uint64_t* out_bytes);
+
 /*
  * ---- exact path: the SQL `ORDER BY vec <op> q LIMIT k` scan (TopKExec, ---------------------
  * src/sql/executor.rs:2239-2392 with the distance of :169-212) over the index's arena.
@@ -160,6 +168,29 @@ int32_t turdb_cuda_bruteforce_topk_device(turdb_cuda_index* idx, const float* d_
                                           float* d_out_dist, uint32_t* d_out_counts, void* stream);
 
 /*
+ * ---- the SQL vector-scan operator: ORDER BY vec <op> '[...]' LIMIT limit OFFSET offset, batched -------
+ * Replaces PhysicalOperator::TopKExec over a full scan (src/sql/planner/physical.rs:229, executor
+ * src/sql/executor.rs:2239-2392) when order_by[0] is Column <op> literal: one call = nq statements against
+ * the same table.  op 0 = `<->` (key sqrt(sum_f64((a-b)_f32^2))), 1 = `<=>` (key 1 - dot/(|a||b|) in f64, NULL
+ * when a norm is zero): executor.rs:169-212.  `<#>` is rejected with TURDB_ERR_UNSUPPORTED — the reference
+ * evaluates it to NULL for every row there (executor.rs:241).  Keys are the reference's f64 values, computed
+ * in its summation order for the candidate rows the FP32 exact path (or, use_index != 0, the HNSW traversal
+ * with ef) selects; rows ascend by (key, scan position == dense node id), NULL keys last, as a NaN key.
+ * out_* are [nq][limit]; out_counts[q] = rows returned.  The exact scan certifies that no row outside its
+ * candidate window can precede the (limit+offset)-th key; the host entry widens the window and retries, the
+ * _device entry reports an uncertified statement as out_counts[q] == 0xFFFFFFFD (margin 0 = default).
+ */
+int32_t turdb_cuda_sql_topk_batch(turdb_cuda_index* idx, const float* queries, uint32_t query_dim,
+                                  uint32_t nq, uint32_t limit, uint32_t offset, uint8_t op,
+                                  int32_t use_index, uint32_t ef, uint64_t* out_row_ids,
+                                  double* out_keys, uint32_t* out_counts);
+int32_t turdb_cuda_sql_topk_batch_device(turdb_cuda_index* idx, const float* d_queries,
+                                         uint32_t query_dim, uint32_t nq, uint32_t limit,
+                                         uint32_t offset, uint8_t op, uint32_t margin,
+                                         int32_t use_index, uint32_t ef, uint64_t* d_out_row_ids,
+                                         double* d_out_keys, uint32_t* d_out_counts, void* stream);
+
+/*
  * ---- multi-GPU: merge of per-shard top-k after the all-gather (one sub-index per GPU) --------
  * gathered_* are [n_shards][nq][k] device arrays (the NCCL all-gather output); ties order by
  * (distance, row_id).  Output [nq][k].
@@ -169,6 +200,64 @@ int32_t turdb_cuda_merge_topk_device(int32_t device, const uint64_t* d_gathered_
                                      uint32_t n_shards, uint32_t nq, uint32_t k,
                                      uint64_t* d_out_row_ids, float* d_out_dist,
                                      uint32_t* d_out_counts, void* stream);
+
+/*
+ * ---- the reference's on-disk index (`.hnsw`) -> device index -----------
+ * Replaces, for a GPU-served index, PersistentHnswIndex::open + rebuild_row_id_map + per-access read_node
+ * (src/hnsw/mod.rs:811-859, 906-911; file layout src/hnsw/storage.rs:98-119, 322-383, 485-546; node
+ * records src/hnsw/mod.rs:333-421).  Parsing is host-only (no GPU needed); `upload` calls
+ * turdb_cuda_index_create.  Vectors are NOT in the file (the table owns them, mod.rs:1097): the caller
+ * supplies them per dense id, or through a callback shaped like the reference's `get_vector` closure.
+ *
+ * Dense ids: readable active slots in (page, slot) order, then "tombstones" — NodeIds that are referenced
+ * but unreadable (deleted / missing / damaged); they keep the reference's behaviour for such nodes
+ * (distance +inf under L2, no neighbours, row_id 0; mod.rs:1111-1127, 1159-1171).  With cosine / inner
+ * product their distance is NaN (unspecified, like NaN elsewhere); the exact path must not be used on an
+ * index that holds tombstones or absent vectors.
+ */
+typedef struct turdb_cuda_hnsw_file turdb_cuda_hnsw_file; /* opaque, host memory only */
+
+enum turdb_hnsw_file_flags {
+  TURDB_HNSW_FILE_SUSPECT_PAGES = 1u,      /* overlapping records: the 13-bit slot offset of storage.rs:338-344 */
+  TURDB_HNSW_FILE_TOMBSTONES = 2u,          /* dangling NodeIds were mapped to tombstones */
+  TURDB_HNSW_FILE_NODE_COUNT_MISMATCH = 4u, /* header.node_count != readable active slots */
+  TURDB_HNSW_FILE_MAX_LEVEL_CLAMPED = 8u,   /* header.max_level > level of the entry node */
+  TURDB_HNSW_FILE_TRAILING_BYTES = 16u      /* file length is not a multiple of the 16 KiB page */
+};
+
+typedef struct {
+  uint64_t index_id, table_id;           /* storage.rs:100-101 */
+  uint32_t dimensions, m, m0, ef_construction, ef_search;
+  uint8_t distance_fn;                   /* 0 L2, 1 cosine, 2 inner product (storage.rs:227-233) */
+  uint8_t quantization;                  /* 0 none, 1 SQ8, 2 PQ — recorded only; records are never quantised */
+  uint8_t header_max_level, max_level;   /* as stored / as uploaded (clamped to the entry node's level) */
+  uint8_t has_entry, reserved[3];
+  uint32_t entry;                        /* dense id, TURDB_INVALID_NODE when the header has no entry point */
+  uint32_t flags;                        /* turdb_hnsw_file_flags */
+  uint32_t n_pages, n_foreign_pages, n_suspect_pages;
+  uint64_t header_node_count, header_vector_count;
+  uint64_t n_nodes, n_tombstones, n_up_slots;
+  uint64_t n_deleted_slots, n_unreadable_slots;
+} turdb_cuda_hnsw_file_info;
+
+/* get_vector(row_id) -> Option<Vec<f32>> (mod.rs:1097): write `dim` floats to out and return 1, or return 0. */
+typedef int32_t (*turdb_cuda_get_vector_fn)(void* user, uint64_t row_id, float* out);
+
+int32_t turdb_cuda_hnsw_file_open(const char* path, turdb_cuda_hnsw_file** out);
+int32_t turdb_cuda_hnsw_file_open_memory(const uint8_t* bytes, uint64_t len, turdb_cuda_hnsw_file** out);
+int32_t turdb_cuda_hnsw_file_close(turdb_cuda_hnsw_file* file);
+int32_t turdb_cuda_hnsw_file_get_info(const turdb_cuda_hnsw_file* file, turdb_cuda_hnsw_file_info* out);
+/* per dense id (n_nodes + n_tombstones entries, each pointer nullable): row id, NodeId page, NodeId slot */
+int32_t turdb_cuda_hnsw_file_nodes(const turdb_cuda_hnsw_file* file, uint64_t* out_row_ids,
+                                   uint32_t* out_pages, uint16_t* out_slots);
+/* a turdb_cuda_graph view over the file's arrays (valid until close); `vectors` is stored as given */
+int32_t turdb_cuda_hnsw_file_graph(const turdb_cuda_hnsw_file* file, const float* vectors,
+                                   turdb_cuda_graph* out);
+/* vectors [n_nodes][dim] in dense-id order and/or get_vector; present (nullable, [n_nodes]) marks rows
+ * the table still holds.  Absent vectors and tombstones are uploaded as +inf rows. */
+int32_t turdb_cuda_hnsw_file_upload(const turdb_cuda_hnsw_file* file, const float* vectors,
+                                    const uint8_t* present, turdb_cuda_get_vector_fn get_vector,
+                                    void* user, int32_t device, turdb_cuda_index** out);
 
 #ifdef __cplusplus
 }

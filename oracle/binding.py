@@ -249,6 +249,28 @@ def sql_projection_distance(op, a, b):
     return None if isnull.value else np.float32(v)
 
 
+def hnsw_file_write(graph: "OracleGraph", index_id=1, table_id=1, ef_search=32, distance_fn=L2, quantization=0,
+                    mode=1):
+    """The bytes PersistentHnswIndex would leave on disk for this graph (see tdo_hnsw_file_write).
+    mode 0 = the reference's page-fill rule verbatim (records overlap), 1 = no overlapping records.
+    Returns (file bytes, pages u32[n], slots u16[n])."""
+    L = lib()
+    L.tdo_hnsw_file_write.restype = C.c_int64
+    L.tdo_hnsw_file_write.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint16, C.c_int, C.c_int, C.c_int,
+                                      C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint16)]
+    n = graph.n
+    need = L.tdo_hnsw_file_write(graph._h, index_id, table_id, ef_search, distance_fn, quantization, mode, None, 0, None, None)
+    if need < 0:
+        raise RuntimeError(f"tdo_hnsw_file_write: {need}")
+    buf = np.zeros(need, np.uint8)
+    pages, slots = np.zeros(max(n, 1), np.uint32), np.zeros(max(n, 1), np.uint16)
+    got = L.tdo_hnsw_file_write(graph._h, index_id, table_id, ef_search, distance_fn, quantization, mode,
+                                _p(buf, C.c_uint8), need, _p(pages, C.c_uint32), _p(slots, C.c_uint16))
+    if got != need:
+        raise RuntimeError(f"tdo_hnsw_file_write: {got}")
+    return buf.tobytes(), pages[:n], slots[:n]
+
+
 def node_write(row_id, max_level, l0, upper) -> bytes:
     """l0: list[(page, slot)]; upper: list (len max_level) of list[(page, slot)]."""
     l0p = np.array([p for p, _ in l0] + [0], np.uint32)

@@ -976,3 +976,143 @@ int tdo_node_read(const uint8_t* buf, uint64_t len, uint64_t* row_id, uint8_t* m
 }
 
 }  // extern "C"
+
+// ----------------------------------------------------------------------------------------------
+// `.hnsw` file — the reference's WRITE path restated, so tests can hand the product reader a file laid
+// out the way a TurDB process would have left it:
+//   PersistentHnswIndex::create (mod.rs:776-809) -> HnswStorage::create (storage.rs:693-722, page 0 =
+//   HnswFileHeader::new, storage.rs:121-158), then per node allocate_node (mod.rs:883-904):
+//   page_has_space/can_fit (storage.rs:622-625) else allocate_page (storage.rs:746-757, HnswPage::init
+//   :545-565 with PageHeader::new, page.rs:130-141), allocate_slot (storage.rs:627-650), write_node_data
+//   (storage.rs:652-669, THROUGH the decoded 13-bit offset, :338-356), finally sync (mod.rs:877-881,
+//   sync_to_header :662-666).  All header fields are read back from the page bytes like the reference does.
+// The records hold each node's FINAL neighbour lists (the reference reaches the same bytes through
+// update_node, mod.rs:913-935, as long as records do not overlap).
+// mode 0 = verbatim can_fit rule (records overlap once a page holds more than ~39 of them: the 13-bit
+//          offset defect); mode 1 = additionally start a new page before a record's truncated offset would
+//          reach the slot directory (a file every record of which reads back intact).
+// ----------------------------------------------------------------------------------------------
+namespace {
+constexpr size_t kPage = 16384, kHnswHdr = 64;
+inline void w16(uint8_t* p, uint16_t v) { p[0] = v & 0xFF; p[1] = v >> 8; }
+inline void w32(uint8_t* p, uint32_t v) { for (int i = 0; i < 4; ++i) p[i] = (v >> (8 * i)) & 0xFF; }
+inline void w64(uint8_t* p, uint64_t v) { for (int i = 0; i < 8; ++i) p[i] = (v >> (8 * i)) & 0xFF; }
+inline uint16_t r16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+// HnswNode::max_serialized_size, mod.rs:252-257
+inline size_t max_serialized_size(uint8_t max_level) { return 10 + 32 * 6 + (size_t)max_level * (1 + 16 * 6); }
+}  // namespace
+
+extern "C" int64_t tdo_hnsw_file_write(const tdo_graph* g, uint64_t index_id, uint64_t table_id, uint16_t ef_search,
+                                       int distance_fn, int quantization, int mode, uint8_t* buf, uint64_t buf_len,
+                                       uint32_t* out_pages, uint16_t* out_slots) {
+  const size_t n = g->n();
+  std::vector<uint8_t> file(kPage, 0);
+  // HnswFileHeader::new + write_to
+  memcpy(file.data(), "TurDB HNSW\0\0\0\0\0\0", 16);
+  w64(&file[16], index_id);
+  w64(&file[24], table_id);
+  w16(&file[32], g->dim);
+  w16(&file[34], g->m);
+  w16(&file[36], (uint16_t)(g->m * 2));
+  w16(&file[38], g->efc);
+  w16(&file[40], ef_search);
+  file[42] = (uint8_t)distance_fn;
+  file[43] = (uint8_t)quantization;
+  w32(&file[44], 0xFFFFFFFFu);
+  w16(&file[48], 0xFFFF);
+  // pass 1: NodeIds.  The page state lives in the page bytes, as in the reference.
+  std::vector<uint32_t> pages(n);
+  std::vector<uint16_t> slots(n);
+  uint32_t current_page = 0;
+  auto page_ptr = [&](uint32_t p) { return file.data() + (size_t)p * kPage; };
+  std::vector<std::pair<size_t, size_t>> where(n);  // byte position + slot size of every record
+  for (size_t i = 0; i < n; ++i) {
+    const size_t max_size = max_serialized_size(g->levels[i]);
+    bool fits = false;
+    if (current_page != 0) {
+      uint8_t* pg = page_ptr(current_page);
+      if (pg[0] != 0x10) return -2;  // HnswPage::from_bytes: "not an HNSW node page" (header overwritten)
+      const uint16_t fs = r16(pg + 16 + 2), fe = r16(pg + 16 + 4);
+      const size_t space = fe > fs ? (size_t)(fe - fs) : 0;       // free_space(): saturating_sub
+      fits = space >= max_size + 4 + 64;                            // can_fit
+      if (fits && mode == 1) {
+        const size_t new_end = (size_t)fe - max_size, dir_end = (size_t)fs + 4;
+        if (new_end < 8192 + dir_end) fits = false;                 // truncated offset would meet the directory
+      }
+    }
+    if (!fits) {
+      current_page = (uint32_t)(file.size() / kPage);
+      file.resize(file.size() + kPage, 0);
+      uint8_t* pg = page_ptr(current_page);
+      pg[0] = 0x10;                    // PageHeader::new(PageType::HnswNode)
+      w16(pg + 4, 16);                 // free_start = PAGE_HEADER_SIZE
+      w16(pg + 6, (uint16_t)kPage);    // free_end = PAGE_SIZE
+      w16(pg + 16 + 0, 0);             // HnswPageHeader::new
+      w16(pg + 16 + 2, (uint16_t)kHnswHdr);
+      w16(pg + 16 + 4, (uint16_t)kPage);
+      w16(pg + 16 + 10, (uint16_t)(kPage - kHnswHdr));
+    }
+    uint8_t* pg = page_ptr(current_page);
+    // allocate_slot
+    const uint16_t slot_index = r16(pg + 16 + 0);
+    const uint16_t new_fs = (uint16_t)(r16(pg + 16 + 2) + 4);
+    const uint16_t new_fe = (uint16_t)(r16(pg + 16 + 4) - (uint16_t)max_size);
+    w16(pg + 16 + 0, (uint16_t)(slot_index + 1));
+    w16(pg + 16 + 2, new_fs);
+    w16(pg + 16 + 4, new_fe);
+    w16(pg + 16 + 6, (uint16_t)(r16(pg + 16 + 6) + 1));
+    w16(pg + 16 + 10, (uint16_t)(r16(pg + 16 + 10) - (uint16_t)max_size - 4));
+    uint8_t* se = pg + kHnswHdr + (size_t)slot_index * 4;
+    w16(se, (uint16_t)((new_fe & 0x1FFF) | (1u << 13)));  // SlotEntry::encode, status Active
+    w16(se + 2, (uint16_t)max_size);
+    pages[i] = current_page;
+    slots[i] = slot_index;
+    where[i] = {(size_t)current_page * kPage + (new_fe & 0x1FFF), max_size};  // write_node_data: decoded offset
+    // a placeholder record of the node's own size is written now so later allocations see the same bytes the
+    // reference's insert would have left (row id / level / empty lists); the final record replaces it below
+    uint8_t* rec = file.data() + where[i].first;
+    if (where[i].first + 10 + g->levels[i] <= file.size()) {
+      w64(rec, g->row_ids[i]);
+      rec[8] = g->levels[i];
+      rec[9] = 0;
+      for (uint8_t l = 0; l < g->levels[i]; ++l) rec[10 + l] = 0;
+    }
+  }
+  // pass 2: final records
+  for (size_t i = 0; i < n; ++i) {
+    uint8_t rec[10 + 32 * 6 + 255 * 97];
+    size_t off = 0;
+    w64(rec, g->row_ids[i]);
+    rec[8] = g->levels[i];
+    rec[9] = g->l0_cnt[i];
+    off = 10;
+    for (uint8_t j = 0; j < g->l0_cnt[i]; ++j, off += 6) {
+      const uint32_t nb = g->l0_adj[i * TDO_MAX_L0_NEIGHBORS + j];
+      put_node_id(rec + off, pages[nb], slots[nb]);
+    }
+    for (uint8_t l = 1; l <= g->levels[i]; ++l) {
+      const size_t slot = (size_t)g->up_base[i] + (l - 1);
+      rec[off++] = g->up_cnt[slot];
+      for (uint8_t j = 0; j < g->up_cnt[slot]; ++j, off += 6) {
+        const uint32_t nb = g->up_adj[slot * TDO_MAX_LEVEL_NEIGHBORS + j];
+        put_node_id(rec + off, pages[nb], slots[nb]);
+      }
+    }
+    if (off > where[i].second) return -3;  // write_node_data: "data size exceeds slot size"
+    memcpy(file.data() + where[i].first, rec, off);
+  }
+  // sync_to_header
+  if (g->entry != TDO_INVALID) {
+    w32(&file[44], pages[g->entry]);
+    w16(&file[48], slots[g->entry]);
+  }
+  file[50] = g->max_level;
+  w64(&file[52], n);
+  if (out_pages && n) memcpy(out_pages, pages.data(), n * 4);
+  if (out_slots && n) memcpy(out_slots, slots.data(), n * 2);
+  if (buf) {
+    if (buf_len < file.size()) return -1;
+    memcpy(buf, file.data(), file.size());
+  }
+  return (int64_t)file.size();
+}

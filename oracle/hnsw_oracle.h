@@ -92,6 +92,15 @@ int tdo_node_read(const uint8_t* buf, uint64_t len, uint64_t* row_id, uint8_t* m
                   uint32_t* l0_pages, uint16_t* l0_slots, uint8_t* l0_count, uint32_t* up_pages,
                   uint16_t* up_slots, uint8_t* up_counts /* [max_level] , up arrays [max_level][16] */);
 
+/* ---- .hnsw file: the reference's write path (storage.rs:121-158, 545-669, 693-757; mod.rs:776-904) ----
+ * mode 0 = verbatim page-fill rule (records overlap: 13-bit slot offsets); mode 1 = new page before overlap.
+ * buf may be NULL (size query).  out_pages/out_slots: NodeId of every dense node.  Returns the file length,
+ * -1 buffer too small, -2 a page header was overwritten (the reference's insert would fail there), -3 record
+ * larger than its slot. */
+int64_t tdo_hnsw_file_write(const tdo_graph* g, uint64_t index_id, uint64_t table_id, uint16_t ef_search,
+                            int distance_fn, int quantization, int mode, uint8_t* buf, uint64_t buf_len,
+                            uint32_t* out_pages, uint16_t* out_slots);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,15 +23,58 @@ ap.add_argument("--latent", type=int, default=16)
 ap.add_argument("--tunings", default="0,0,0;1,8,0;1,16,0;1,24,0;1,32,0;2,16,0;1,16,12;1,24,12")
 ap.add_argument("--out", default="gpurun_out/sweep.json")
 ap.add_argument("--debug", action="store_true")
+ap.add_argument("--gen", default="gaussian_latent", choices=["gaussian_latent", "sift_like", "clustered"])
+ap.add_argument("--libs", default="", help="A/B: comma-separated library files; the graph is built once and each "
+                "library is measured in a child process (TURDB_CUDA_LIB)")
+ap.add_argument("--graph", default="", help="(internal) npz with a prebuilt graph")
+ap.add_argument("--probe", default="", help="gather-ceiling probe settings: ctas_per_sm,slots,cta_smem_bytes;...")
 args = ap.parse_args()
 
 norm = args.metric == 1
-x = ds.gaussian_latent(args.n, args.dim, seed=1, latent=args.latent, normalise=norm)
-q = ds.gaussian_latent(args.nq, args.dim, seed=2, latent=args.latent, normalise=norm)
+if args.gen == "gaussian_latent":
+    x = ds.gaussian_latent(args.n, args.dim, seed=1, latent=args.latent, normalise=norm)
+    q = ds.gaussian_latent(args.nq, args.dim, seed=2, latent=args.latent, normalise=norm)
+else:
+    x = ds.make(args.gen, args.n, args.dim, seed=1)
+    q = ds.make(args.gen, args.nq, args.dim, seed=2)
 t = time.time()
-arrays = build_graph(x, seed=42)
-torch.cuda.synchronize()
-print(f"graph build {time.time() - t:.1f}s", flush=True)
+if args.graph:
+    z = np.load(args.graph)
+    arrays = {k: (z[k] if z[k].ndim else z[k].item()) for k in z.files}
+    arrays["vectors"] = x
+else:
+    arrays = build_graph(x, seed=42)
+    torch.cuda.synchronize()
+print(f"graph build/load {time.time() - t:.1f}s", flush=True)
+if args.libs:
+    import os, subprocess
+    gpath = "/tmp/sweep_graph.npz"
+    np.savez(gpath, **{k: v for k, v in arrays.items() if k != "vectors"})
+    del arrays
+    torch.cuda.empty_cache()
+    allres = {}
+    for lib in args.libs.split(","):
+        print(f"=== {lib}", flush=True)
+        out = args.out + "." + os.path.basename(lib) + ".json"
+        cmd = [sys.executable, __file__, "--graph", gpath, "--out", out] + [a for a in sys.argv[1:] if not a.startswith("--libs")]
+        # drop the value that followed --libs / --out in the parent's argv
+        clean, skip = [], False
+        for a in sys.argv[1:]:
+            if skip:
+                skip = False
+                continue
+            if a in ("--libs", "--out"):
+                skip = True
+                continue
+            clean.append(a)
+        cmd = [sys.executable, __file__, "--graph", gpath, "--out", out] + clean
+        subprocess.run(cmd, env=dict(os.environ, TURDB_CUDA_LIB=os.path.abspath(lib)))
+        try:
+            allres[lib] = json.load(open(out))["runs"]
+        except Exception as ex:  # noqa
+            allres[lib] = str(ex)
+    json.dump(dict(args=vars(args), libs=allres), open(args.out, "w"), indent=1)
+    sys.exit(0)
 idx = CudaHnswIndex.from_graph(arrays)
 dev = torch.device("cuda:0")
 dq = torch.from_numpy(q).to(dev)
@@ -46,6 +89,12 @@ gt = torch.topk(dq[:1000] @ xd.T, args.k, dim=1).indices.cpu().numpy() if norm e
 del xd
 res = []
 ref_nodes = None
+probes = []
+for pr in [p for p in args.probe.split(";") if p]:
+    c, sl, sm = [int(v) for v in pr.split(",")]
+    gbs, ms = idx.gather_probe(c, sl, sm, 64)
+    probes.append(dict(ctas_per_sm=c, slots=sl, cta_smem_bytes=sm, gbs=gbs, ms=ms))
+    print("gather probe", probes[-1], flush=True)
 for tun in args.tunings.split(";"):
     warps, slots, hb, segs = ([int(v) for v in tun.split(",")] + [0])[:4]
     try:
@@ -67,6 +116,7 @@ for tun in args.tunings.split(";"):
             run(); torch.cuda.synchronize()
             c = idx.debug_counters(False).astype(np.float64)
             h = max(c[0], 1.0)
+            print("  dbg per-hop cycles: visited-insert %.0f" % (c[12]/h))
             print("  dbg per-hop cycles: select %.0f adj+hash %.0f request %.0f (w0: issue %.0f wait %.0f comp %.0f) merge %.0f | "
                   "spec-hit %.2f | per-query: total %.0f upper %.0f hops %.1f" % (c[1]/h, c[2]/h, c[3]/h, c[6]/h, c[5]/h, c[7]/h, c[4]/h,
                    c[8]/h, c[9]/max(c[11],1), c[10]/max(c[11],1), c[0]/max(c[11],1)), flush=True)
@@ -86,4 +136,4 @@ for tun in args.tunings.split(";"):
         res.append(r)
     except Exception as ex:  # noqa
         print("tuning", tun, "failed:", ex, flush=True)
-json.dump(dict(args=vars(args), runs=res), open(args.out, "w"), indent=1)
+json.dump(dict(args=vars(args), runs=res, gather_probe=probes), open(args.out, "w"), indent=1)

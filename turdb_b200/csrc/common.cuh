@@ -69,6 +69,23 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
       : "memory");
 }
 
+// ---- per-thread 16 B async copies (cp.async; SASS: LDGSTS) ---------------------------------------
+// 32 lanes x 16 B = 512 contiguous bytes per warp instruction, no uniform-register operands (a bulk copy
+// costs ~10 instructions per issuing lane because its operands must be moved to uniform registers).
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most `n` of this thread's committed groups are pending (n in 0..3)
+__device__ __forceinline__ void cp_async_wait_pending(uint32_t n) {
+  switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+  }
+}
+
 // ---- the reference's AVX2 reduction order, one QUAD (4 lanes) per vector ---------------------
 // Lane p of a quad owns AVX lanes 2p and 2p+1 (distance.rs:105-129): it walks elements 8t+2p,
 // 8t+2p+1 with one fused multiply-add each, then the quad reproduces horizontal_sum_avx2

@@ -24,7 +24,15 @@
 // 0: double-buffered list merge (2 x 8 B x ef of shared memory); 1: in-place merge (half the list memory,
 // one more warp sync per 32 entries).  Measured on 1M x 384: see DESIGN.md.
 #ifndef TURDB_MERGE_MODE
-#define TURDB_MERGE_MODE 0
+#define TURDB_MERGE_MODE 1
+#endif
+
+// 0: whole vectors arrive by TMA bulk copies (one per vector, mbarrier completion) — the default;
+// 1: by per-thread 16 B cp.async (LDGSTS), 512 B per warp instruction, commit/wait groups.  Measured on B200
+//    (1M x 384 and 1M x 128): the LDGSTS issue stalls for ~2.6k cycles per 8-vector chunk against ~0.9k for
+//    eight bulk copies, 25-33 % slower end to end — kept only as the measured alternative.
+#ifndef TURDB_GATHER_MODE
+#define TURDB_GATHER_MODE 0
 #endif
 
 namespace turdb {
@@ -72,6 +80,24 @@ struct SearchArgs {
 
 // Per-team shared state handed to every warp.
 struct Team {
+  // chunk c of a request is gathered and reduced by owner(c): with helpers, warp 0 (the leader) keeps out of
+  // the data path and spends the gather time preparing the next hop (speculative visited filtering)
+  // A request has at most 4 chunks (32 candidates); their staging group (c % n_groups) and whether this warp
+  // owns them are tabulated once per kernel (grp_pack: 2 bits per chunk, own_mask: 1 bit per chunk) so that
+  // the per-hop loops hold no integer division.
+  __device__ __forceinline__ bool owns(uint32_t c) const { return (own_mask >> c) & 1u; }
+  __device__ __forceinline__ uint32_t group_of(uint32_t c) const { return (grp_pack >> (2 * c)) & 3u; }
+  __device__ __forceinline__ void tabulate() {
+    grp_pack = 0;
+    own_mask = 0;
+    for (uint32_t c = 0; c < 4; ++c) {
+      const uint32_t g = c % n_groups;
+      const uint32_t o = n_warps == 1 ? 0u : 1u + g % (n_warps - 1);
+      grp_pack |= g << (2 * c);
+      own_mask |= (o == warp ? 1u : 0u) << c;
+    }
+  }
+  uint32_t grp_pack, own_mask;
   uint32_t lane, warp, n_warps;
   uint32_t bar0;             // shared address of mbarrier 0 (8 B apart)
   volatile uint32_t* ctl;    // [0] = m of the current request or kDone, [1] = work item
@@ -94,12 +120,12 @@ struct Team {
 // chunk mapped to that group).
 template <int METRIC>
 __device__ __forceinline__ void team_distances_pieces(const DeviceIndex& ix, Team& t, uint32_t m) {
-  const uint32_t lane = t.lane, p = lane & 3, G = t.n_groups, W = t.n_warps, S = t.n_segs;
+  const uint32_t lane = t.lane, p = lane & 3, G = t.n_groups, S = t.n_segs;
   const uint32_t nchunks = (m + 7) >> 3;
   const uint32_t steps = ix.dim >> 3;
   auto seg_lo = [&](uint32_t sgm) { return min(steps, sgm * t.seg_steps); };
   auto issue = [&](uint32_t c, uint32_t sgm) {
-    const uint32_t g = c % G;
+    const uint32_t g = t.group_of(c);
     const uint32_t bar = t.bar0 + 8 * g;
     const uint32_t cnt = min(8u, m - 8 * c);
     const uint32_t b0 = seg_lo(sgm) * 32;
@@ -114,11 +140,11 @@ __device__ __forceinline__ void team_distances_pieces(const DeviceIndex& ix, Tea
   };
   long long t0 = t.dbg ? clock64() : 0;
   for (uint32_t c = 0; c < min(G, nchunks); ++c)
-    if ((c % G) % W == t.warp) issue(c, 0);
+    if (t.owns(c)) issue(c, 0);
   if (t.dbg) t.c_issue += (uint32_t)(clock64() - t0);
   for (uint32_t c = 0; c < nchunks; ++c) {
-    const uint32_t g = c % G;
-    if (g % W != t.warp) continue;
+    const uint32_t g = t.group_of(c);
+    if (!t.owns(c)) continue;
     const uint32_t slot = 8 * c + (lane >> 2);
     float nb = 0.f;
     if (METRIC == kCosine && slot < m) nb = __ldg(ix.norm2 + t.cand_ids[slot]);
@@ -157,10 +183,10 @@ __device__ __forceinline__ void team_distances_pieces(const DeviceIndex& ix, Tea
 // Whole-vector form (n_segs == 1): same dealing of chunks to groups and warps, one bulk copy per vector.
 template <int METRIC>
 __device__ __forceinline__ void team_distances_whole(const DeviceIndex& ix, Team& t, uint32_t m) {
-  const uint32_t lane = t.lane, p = lane & 3, G = t.n_groups, W = t.n_warps;
+  const uint32_t lane = t.lane, p = lane & 3, G = t.n_groups;
   const uint32_t nchunks = (m + 7) >> 3;
   auto issue = [&](uint32_t c) {
-    const uint32_t g = c % G;
+    const uint32_t g = t.group_of(c);
     const uint32_t bar = t.bar0 + 8 * g;
     const uint32_t cnt = min(8u, m - 8 * c);
     if (lane == 0) mbar_expect_tx(bar, cnt * t.vec_bytes);
@@ -171,12 +197,24 @@ __device__ __forceinline__ void team_distances_whole(const DeviceIndex& ix, Team
     }
   };
   long long t0 = t.dbg ? clock64() : 0;
-  for (uint32_t c = 0; c < min(G, nchunks); ++c)
-    if ((c % G) % W == t.warp) issue(c);
+  // Round 1 (the first min(m, 8G) vectors): a bulk copy is issued lane by lane (ELECT / R2UR / UBLKCP, ~100
+  // cycles each), so the copies are dealt to ALL warps of the team, the leader included (vector v to warp
+  // v % W, one lane each), which divides that latency by W.  The owner of a chunk arms the chunk's barrier
+  // with the byte count; completions that land before the arming only run the transaction count negative.
+  {
+    const uint32_t m1 = min(m, 8 * G);
+    for (uint32_t c = 0; c < min(G, nchunks); ++c)
+      if (t.owns(c) && lane == 0) mbar_expect_tx(t.bar0 + 8 * c, min(8u, m - 8 * c) * t.vec_bytes);
+    const uint32_t v = t.warp + t.n_warps * lane;
+    if (v < m1) {
+      const uint32_t id = t.cand_ids[v];  // chunk v >> 3 < G uses group v >> 3, slot v & 7: staging slot v
+      bulk_g2s(t.stage_u32 + v * t.stride, ix.arena + (size_t)id * ix.ds, t.vec_bytes, t.bar0 + 8 * (v >> 3));
+    }
+  }
   if (t.dbg) t.c_issue += (uint32_t)(clock64() - t0);
   for (uint32_t c = 0; c < nchunks; ++c) {
-    const uint32_t g = c % G;
-    if (g % W != t.warp) continue;
+    const uint32_t g = t.group_of(c);
+    if (!t.owns(c)) continue;
     const uint32_t slot = 8 * c + (lane >> 2);
     float nb = 0.f;
     if (METRIC == kCosine && slot < m) nb = __ldg(ix.norm2 + t.cand_ids[slot]);
@@ -199,20 +237,86 @@ __device__ __forceinline__ void team_distances_whole(const DeviceIndex& ix, Team
   }
 }
 
+// Whole-vector form with per-thread async copies: chunk c is copied AND reduced by warp (c % G) % W, so a
+// warp only ever waits on its own commit groups; a warp that owns several staging groups keeps one chunk
+// in flight in each.
+template <int METRIC>
+__device__ __forceinline__ void team_distances_ldgsts(const DeviceIndex& ix, Team& t, uint32_t m) {
+  const uint32_t lane = t.lane, p = lane & 3, G = t.n_groups;
+  const uint32_t nchunks = (m + 7) >> 3;
+  const uint32_t pieces = t.vec_bytes >> 4;
+  auto issue = [&](uint32_t c) {
+    const uint32_t g = t.group_of(c);
+    const uint32_t cnt = min(8u, m - 8 * c);
+    for (uint32_t v = 0; v < cnt; ++v) {
+      const uint32_t id = t.cand_ids[8 * c + v];
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(ix.arena + (size_t)id * ix.ds);
+      const uint32_t dst = t.stage_u32 + (g * 8 + v) * t.stride;
+      for (uint32_t i = lane; i < pieces; i += 32) cp_async16(dst + 16 * i, src + 16 * i);
+    }
+    cp_async_commit();
+  };
+  long long t0 = t.dbg ? clock64() : 0;
+  uint32_t pend = 0;
+  for (uint32_t c = 0; c < min(G, nchunks); ++c)
+    if (t.owns(c)) {
+      issue(c);
+      ++pend;
+    }
+  if (t.dbg) t.c_issue += (uint32_t)(clock64() - t0);
+  for (uint32_t c = 0; c < nchunks; ++c) {
+    const uint32_t g = t.group_of(c);
+    if (!t.owns(c)) continue;
+    const uint32_t slot = 8 * c + (lane >> 2);
+    float nb = 0.f;
+    if (METRIC == kCosine && slot < m) nb = __ldg(ix.norm2 + t.cand_ids[slot]);
+    long long w0 = t.dbg ? clock64() : 0;
+    cp_async_wait_pending(pend - 1);  // the oldest pending group is this chunk
+    --pend;
+    __syncwarp();                     // every lane's pieces of the chunk are visible to the warp
+    long long w1 = t.dbg ? clock64() : 0;
+    t.c_wait += (uint32_t)(w1 - w0);
+    const float* b = reinterpret_cast<const float*>(t.stage + (g * 8 + (lane >> 2)) * t.stride);
+    const float raw = (METRIC == kL2) ? quad_l2sq(t.q, b, ix.dim, p) : quad_dot(t.q, b, ix.dim, p);
+    if (p == 0 && slot < m) {
+      float d = raw;
+      if (METRIC == kIP) d = -raw;  // inner_product_avx2, distance.rs:240-242
+      if (METRIC == kCosine) d = cosine_finish(raw, t.qnorm, nb);
+      t.cand_d[slot] = d;
+    }
+    __syncwarp();                     // the group's slots are free again
+    if (t.dbg) t.c_comp += (uint32_t)(clock64() - w1);
+    if (c + G < nchunks) {
+      issue(c + G);
+      ++pend;
+    }
+  }
+}
+
 template <int METRIC>
 __device__ __forceinline__ void team_distances(const DeviceIndex& ix, Team& t, uint32_t m) {
+#if TURDB_GATHER_MODE == 1
+  if (t.n_segs == 1) team_distances_ldgsts<METRIC>(ix, t, m);
+#else
   if (t.n_segs == 1) team_distances_whole<METRIC>(ix, t, m);
+#endif
   else team_distances_pieces<METRIC>(ix, t, m);
 }
 
 // Leader side of a request: publish m, run the team's distance pass, return this lane's distance.
-template <int METRIC>
-__device__ __forceinline__ float leader_request(const DeviceIndex& ix, Team& t, uint32_t m) {
+// `overlap` runs on the leader between the two barriers, i.e. while the helper warps gather and reduce.
+template <int METRIC, typename F>
+__device__ __forceinline__ float leader_request(const DeviceIndex& ix, Team& t, uint32_t m, F&& overlap) {
   if (t.lane == 0) t.ctl[0] = m;
   __syncthreads();
-  team_distances<METRIC>(ix, t, m);
+  team_distances<METRIC>(ix, t, m);  // no-op for the leader unless it is the only warp
+  overlap();
   __syncthreads();
   return t.lane < m ? t.cand_d[t.lane] : INFINITY;
+}
+template <int METRIC>
+__device__ __forceinline__ float leader_request(const DeviceIndex& ix, Team& t, uint32_t m) {
+  return leader_request<METRIC>(ix, t, m, [] {});
 }
 
 // Exact visited set, called by all 32 lanes of the leader with one (distinct) id per active lane.
@@ -226,11 +330,14 @@ __device__ __forceinline__ float leader_request(const DeviceIndex& ix, Team& t, 
 //     32-bit entries hold the id.  16-bit entries: h = id * odd (mod 2^key_bits) is a bijection; home = top
 //     hash_bits of h; the entry stores the low rem_bits of h plus (displacement + 1), which together name h
 //     and therefore the id — an exact set in half the bytes.
+// *where (optional) receives the table position a newly inserted key went to, for visited_undo.
 template <bool GLOBAL>
-__device__ __forceinline__ uint32_t visited_insert(uint32_t* tab, uint32_t id, bool active, const TeamLayout& L) {
+__device__ __forceinline__ uint32_t visited_insert(uint32_t* tab, uint32_t id, bool active, const TeamLayout& L,
+                                                   uint32_t* where = nullptr) {
   if (GLOBAL) {
     if (!active) return 0u;
     const uint32_t bit = 1u << (id & 31);
+    if (where) *where = id;
     return (atomicOr(tab + (id >> 5), bit) & bit) == 0 ? 1u : 0u;
   }
   const uint32_t mask = (1u << L.hash_bits) - 1;
@@ -264,8 +371,12 @@ __device__ __forceinline__ uint32_t visited_insert(uint32_t* tab, uint32_t id, b
       }
       __syncwarp();
       if (wrote) {
-        if (t16[slot] == want) res = 1u;
-        else ++disp;
+        if (t16[slot] == want) {
+          res = 1u;
+          if (where) *where = slot;
+        } else {
+          ++disp;
+        }
       }
       __syncwarp();
     }
@@ -287,12 +398,29 @@ __device__ __forceinline__ uint32_t visited_insert(uint32_t* tab, uint32_t id, b
     }
     __syncwarp();
     if (wrote) {
-      if (t32[slot] == id) res = 1u;
-      else slot = (slot + 1) & mask;
+      if (t32[slot] == id) {
+        res = 1u;
+        if (where) *where = slot;
+      } else {
+        slot = (slot + 1) & mask;
+      }
     }
     __syncwarp();
   }
   return res;
+}
+
+// Takes back the keys one visited_insert call inserted (`inserted` = that call returned 1 for this lane,
+// `where` = its position).  Exact as long as nothing was inserted since: keys only ever go to EMPTY slots, so
+// emptying the newest ones cannot cut the probe sequence of any older key.
+template <bool GLOBAL>
+__device__ __forceinline__ void visited_undo(uint32_t* tab, bool inserted, uint32_t where, const TeamLayout& L) {
+  if (inserted) {
+    if (GLOBAL) atomicAnd(tab + (where >> 5), ~(1u << (where & 31)));
+    else if (L.hash16) reinterpret_cast<volatile unsigned short*>(tab)[where] = 0;
+    else reinterpret_cast<volatile uint32_t*>(tab)[where] = kInvalid;
+  }
+  __syncwarp();
 }
 
 // Merge up to 32 new (d, id) pairs (one per `elig` lane) into the ascending list src[head, len) -> dst[0, ..),
@@ -385,6 +513,7 @@ __global__ void __launch_bounds__(128, 5) hnsw_search_kernel(const SearchArgs a)
   uint32_t* cand_ids = reinterpret_cast<uint32_t*>(smem + a.lay.off_cand);
   float* cand_d = reinterpret_cast<float*>(cand_ids + 32);
   uint32_t* tmp_ub = cand_ids + 64;
+  uint32_t* cand_next = cand_ids + 96;  // ids of the speculatively prepared next request
   uint32_t* vis = GLOBAL_VISITED ? a.global_visited + (size_t)blockIdx.x * a.vis_words
                                  : reinterpret_cast<uint32_t*>(smem + a.lay.off_hash);
   const uint32_t hash_slots = 1u << a.lay.hash_bits;
@@ -410,6 +539,7 @@ __global__ void __launch_bounds__(128, 5) hnsw_search_kernel(const SearchArgs a)
   t.qnorm = 0.f;
   t.c_issue = t.c_wait = t.c_comp = 0;
   t.dbg = a.dbg != nullptr;
+  t.tabulate();
 
   if (tid == 0) {
     for (uint32_t g = 0; g < a.lay.n_groups; ++g) mbar_init(t.bar0 + 8 * g, 1);
@@ -454,7 +584,7 @@ __global__ void __launch_bounds__(128, 5) hnsw_search_kernel(const SearchArgs a)
     // ---- leader warp ----
     const long long q_t0 = t.dbg ? clock64() : 0;
     long long l0_t0 = 0;
-    uint32_t c_sel = 0, c_adj = 0, c_req = 0, c_mrg = 0, n_hops = 0, n_spec = 0;
+    uint32_t c_sel = 0, c_adj = 0, c_req = 0, c_mrg = 0, c_vis = 0, n_hops = 0, n_spec = 0;
     t.c_issue = t.c_wait = t.c_comp = 0;
     uint32_t n_dist = 0, n_dist_upper = 0, n_expanded = 0, n_upper_hops = 0;
     uint32_t len = 0;
@@ -633,7 +763,13 @@ __global__ void __launch_bounds__(128, 5) hnsw_search_kernel(const SearchArgs a)
       (void)visited_insert<GLOBAL_VISITED>(vis, cur, lane == 0, a.lay);
       len = 1;
       uint32_t n_visited = 1;
-      uint32_t spec_node = kInvalid, spec_nid = kInvalid;  // speculatively fetched adjacency row
+      uint32_t row_node = kInvalid, row_nid = kInvalid;  // prefetched adjacency row of the runner-up
+      // Speculation: while the helper warps gather hop h, the leader filters the runner-up's neighbours
+      // through the visited set as if it were hop h+1.  If the merge confirms the runner-up (it does ~80 % of
+      // the time) hop h+1 starts with its request ready; otherwise the keys are taken back (visited_undo),
+      // which restores the table exactly, and the hop proceeds as usual.  Results and counters are unchanged.
+      bool sp_valid = false, sp_inserted = false;
+      uint32_t sp_node = kInvalid, sp_where = 0, sp_m = 0;
       uint32_t scan_from = 0;                               // list entries below this index are expanded
       __syncwarp();
       if (t.dbg) l0_t0 = clock64();
@@ -641,7 +777,7 @@ __global__ void __launch_bounds__(128, 5) hnsw_search_kernel(const SearchArgs a)
       for (;;) {
         const long long h0 = t.dbg ? clock64() : 0;
         // closest unexpanded entry == the reference's candidates.pop() that passes `d <= worst`;
-        // the runner-up is the likely next hop: its adjacency row is fetched while this hop gathers.
+        // the runner-up is the likely next hop.
         // Everything below `scan_from` is known to be expanded, so one 32-wide probe usually suffices.
         uint32_t idx = 0xFFFFFFFFu, idx2 = 0xFFFFFFFFu;
         for (uint32_t base = scan_from; base < len; base += 32) {
@@ -661,35 +797,71 @@ __global__ void __launch_bounds__(128, 5) hnsw_search_kernel(const SearchArgs a)
         if (lane == 0) A_id[idx] = c | kExpandedBit;
         __syncwarp();
         n_expanded += 1;
-        const long long h1 = t.dbg ? clock64() : 0;
-        if (t.dbg && c == spec_node) n_spec += 1;
-
-        if (!GLOBAL_VISITED && n_visited + kL0 > hash_limit) {
-          overflow = true;
-          break;
-        }
-        const uint32_t nid = (c == spec_node) ? spec_nid : __ldg(ix.l0_adj + (size_t)c * kL0 + lane);
-        if (c2 != kInvalid) {
-          spec_node = c2;
-          spec_nid = __ldg(ix.l0_adj + (size_t)c2 * kL0 + lane);
-        } else {
-          spec_node = kInvalid;
-        }
         scan_from = idx + 1;
-        const uint32_t ins = visited_insert<GLOBAL_VISITED>(vis, nid, nid != kInvalid, a.lay);
-        if (__any_sync(kFullMask, ins == 2u)) {
-          overflow = true;
-          break;
+        const long long h1 = t.dbg ? clock64() : 0;
+
+        const bool hit = sp_valid && sp_node == c;
+        if (sp_valid && !hit) visited_undo<GLOBAL_VISITED>(vis, sp_inserted, sp_where, a.lay);
+        sp_valid = false;
+        uint32_t m;
+        if (hit) {
+          // c's unvisited neighbours are already in the table; their ids wait in cand_next (stored order)
+          if (t.dbg) n_spec += 1;
+          m = sp_m;
+          if (lane < m) cand_ids[lane] = cand_next[lane];
+          if (c2 != kInvalid) {
+            row_node = c2;
+            row_nid = __ldg(ix.l0_adj + (size_t)c2 * kL0 + lane);
+          } else {
+            row_node = kInvalid;
+          }
+          if (m == 0) continue;
+        } else {
+          if (!GLOBAL_VISITED && n_visited + kL0 > hash_limit) {
+            overflow = true;
+            break;
+          }
+          const uint32_t nid = (c == row_node) ? row_nid : __ldg(ix.l0_adj + (size_t)c * kL0 + lane);
+          if (c2 != kInvalid) {
+            row_node = c2;
+            row_nid = __ldg(ix.l0_adj + (size_t)c2 * kL0 + lane);
+          } else {
+            row_node = kInvalid;
+          }
+          const long long v0 = t.dbg ? clock64() : 0;
+          const uint32_t ins = visited_insert<GLOBAL_VISITED>(vis, nid, nid != kInvalid, a.lay);
+          if (t.dbg) c_vis += (uint32_t)(clock64() - v0);
+          if (__any_sync(kFullMask, ins == 2u)) {
+            overflow = true;
+            break;
+          }
+          const bool isnew = ins == 1u;
+          const uint32_t newmask = __ballot_sync(kFullMask, isnew);
+          m = __popc(newmask);
+          if (m == 0) continue;
+          // compact to slots 0..m-1 in stored order
+          if (isnew) cand_ids[__popc(newmask & ((1u << lane) - 1))] = nid;
         }
-        const bool isnew = ins == 1u;
-        const uint32_t newmask = __ballot_sync(kFullMask, isnew);
-        const uint32_t m = __popc(newmask);
-        if (m == 0) continue;
         n_visited += m;
-        // compact to slots 0..m-1 in stored order
-        if (isnew) cand_ids[__popc(newmask & ((1u << lane) - 1))] = nid;
         const long long h2 = t.dbg ? clock64() : 0;
-        const float d = leader_request<METRIC>(ix, t, m);
+        const float d = leader_request<METRIC>(ix, t, m, [&] {
+          // hop h+1 prepared under hop h's gather (leader only; cand_ids belongs to the helpers meanwhile)
+          if (row_node == kInvalid) return;
+          if (!GLOBAL_VISITED && n_visited + kL0 > hash_limit) return;  // the real hop reports the overflow
+          uint32_t w = 0;
+          const uint32_t ins2 = visited_insert<GLOBAL_VISITED>(vis, row_nid, row_nid != kInvalid, a.lay, &w);
+          sp_inserted = ins2 == 1u;
+          sp_where = w;
+          if (__any_sync(kFullMask, ins2 == 2u)) {
+            visited_undo<GLOBAL_VISITED>(vis, sp_inserted, sp_where, a.lay);
+            return;
+          }
+          const uint32_t nm = __ballot_sync(kFullMask, sp_inserted);
+          sp_m = __popc(nm);
+          if (sp_inserted) cand_next[__popc(nm & ((1u << lane) - 1))] = row_nid;
+          sp_node = row_node;
+          sp_valid = true;
+        });
         const long long h3 = t.dbg ? clock64() : 0;
         if (t.dbg) {
           c_sel += (uint32_t)(h1 - h0);
@@ -802,6 +974,7 @@ __global__ void __launch_bounds__(128, 5) hnsw_search_kernel(const SearchArgs a)
       atomicAdd(a.dbg + 9, (unsigned long long)(q_t1 - q_t0));
       atomicAdd(a.dbg + 10, (unsigned long long)(l0_t0 - q_t0));
       atomicAdd(a.dbg + 11, 1ull);
+      atomicAdd(a.dbg + 12, (unsigned long long)c_vis);
     }
 
     // release the helper warps

@@ -14,6 +14,7 @@
 
 #include "common.cuh"
 #include "exact_search.cuh"
+#include "gather_probe.cuh"
 #include "hnsw_search.cuh"
 
 using namespace turdb;
@@ -400,7 +401,7 @@ static TeamLayout make_layout(uint32_t dim, uint32_t ds, uint32_t ef, uint32_t h
   L.off_q = off;     off += (ds * 4 + 15) & ~15u;
   L.off_list = off;  off += (filtered || TURDB_MERGE_MODE == 0) ? ef * 16 : ef * 8;  // result list (x2 when double-buffered)
   L.off_clist = off; off += filtered ? ef * 16 : 0;       // search_filtered: candidate window (double-buffered)
-  L.off_cand = off;  off += 384;  // cand_ids[32], cand_d[32], tmp_ub[32]
+  L.off_cand = off;  off += 512;  // cand_ids[32], cand_d[32], tmp_ub[32], cand_next[32]
   L.off_hash = off;  off += global_visited ? 0 : ((L.hash16 ? 2u : 4u) << hash_bits);
   off = (off + 127) & ~127u;
   L.off_stage = off; off += n_slots * L.stride;
@@ -441,6 +442,29 @@ static cudaError_t launch_metric(int metric, const SearchArgs& a, uint32_t warps
                                  cudaStream_t stream, uint32_t* rw) {
   return a.visible ? launch_metric2<GV, true>(metric, a, warps, num_sms, max_ctas, stream, rw)
                    : launch_metric2<GV, false>(metric, a, warps, num_sms, max_ctas, stream, rw);
+}
+
+template <int METRIC, bool FILT>
+static cudaError_t search_occupancy_t(uint32_t warps, size_t smem, int* occ) {
+  auto kern = hnsw_search_kernel<METRIC, false, FILT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, 32 * warps, smem);
+}
+// resident CTAs per SM of the traversal kernel for a team of `warps` warps
+static cudaError_t search_occupancy(int metric, bool filt, uint32_t warps, size_t smem, int* occ) {
+  if (filt) {
+    switch (metric) {
+      case kCosine: return search_occupancy_t<kCosine, true>(warps, smem, occ);
+      case kIP: return search_occupancy_t<kIP, true>(warps, smem, occ);
+      default: return search_occupancy_t<kL2, true>(warps, smem, occ);
+    }
+  }
+  switch (metric) {
+    case kCosine: return search_occupancy_t<kCosine, false>(warps, smem, occ);
+    case kIP: return search_occupancy_t<kIP, false>(warps, smem, occ);
+    default: return search_occupancy_t<kL2, false>(warps, smem, occ);
+  }
 }
 
 __global__ void fill_empty_results_kernel(uint64_t* rows, uint32_t* nodes, float* dist, uint32_t* counts,
@@ -492,7 +516,7 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
   }
   const uint32_t ds = idx->ix.ds, dim = idx->ix.dim;
   uint32_t hash_bits = th ? th : std::min(15u, std::max(9u, ceil_log2(ef * 64)));
-  const uint32_t warps = tw ? std::min(tw, 4u) : 4u;  // team size: warps cooperating on one query
+  uint32_t warps = tw ? std::min(tw, 4u) : 0u;  // team size (0: leader + one helper per staging group, below)
   const uint32_t budget = (uint32_t)idx->max_smem_optin;
   const uint64_t nn = idx->ix.n;
   const bool filt = d_visible != nullptr;
@@ -526,6 +550,15 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
     segs = bg;
   }
   TeamLayout lay = make_layout(dim, ds, ef, hash_bits, slots, segs, false, nn, filt);
+  // Team size: warp 0 leads (control flow + speculative preparation of the next hop), the others gather and
+  // reduce; every warp takes a share of a hop's bulk-copy issue.  Resident queries per SM come first (the
+  // kernel is latency-bound: 1M x 128, 8 queries of 2 warps beat 7 of 3 and 5 of 4, measured); among equal
+  // residency the larger team wins (shorter issue phase).
+  bool auto_warps = false;
+  if (!warps) {
+    auto_warps = true;
+    warps = 4;
+  }
   while (lay.team_bytes > budget && lay.n_segs < 16 && lay.seg_steps > 8)
     lay = make_layout(dim, ds, ef, hash_bits, lay.n_groups * 8, lay.n_segs + 1, false, nn, filt);
   while (lay.team_bytes > budget && lay.n_groups > 1)
@@ -576,6 +609,17 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
   {
     std::lock_guard<std::mutex> lk(idx->mu);
     if (idx->prof_used < idx->prof_capacity) pev = &idx->prof_events[3 * idx->prof_used++];
+  }
+  if (auto_warps) {
+    int best_occ = 0;
+    for (uint32_t w = 4; w >= 2; --w) {
+      int occ = 0;
+      if (search_occupancy(metric, filt, w, lay.team_bytes, &occ) != cudaSuccess) break;
+      if (occ > best_occ) {
+        best_occ = occ;
+        warps = w;
+      }
+    }
   }
   if (pev) cudaEventRecord(pev[0], stream);
   cudaError_t e = launch_metric<false>(metric, a, warps, idx->num_sms, filt ? std::min<uint32_t>(nq, idx->num_sms * 8) : nq, stream, nullptr);
@@ -684,5 +728,58 @@ extern "C" int32_t turdb_cuda_search_batch(turdb_cuda_index* idx, const float* q
   return TURDB_OK;
 }
 
+// Diagnostics: random-row gather ceiling (gather_probe.cuh).  Same copies as the traversal, no dependencies.
+extern "C" int32_t turdb_cuda_index_gather_probe(turdb_cuda_index* idx, uint32_t ctas_per_sm, uint32_t staging_slots,
+                                                 uint32_t cta_smem_bytes, uint32_t rounds, float* out_ms,
+                                                 uint64_t* out_bytes) {
+  if (!idx || !out_ms || !out_bytes) return fail(TURDB_ERR_INVALID_ARGUMENT, "null argument");
+  if (idx->ix.n == 0) return fail(TURDB_ERR_INVALID_ARGUMENT, "empty index");
+  if (staging_slots == 0 || staging_slots > 64 * 8 || (staging_slots & 7)) return fail(TURDB_ERR_INVALID_ARGUMENT, "staging_slots must be a multiple of 8");
+  if (ctas_per_sm == 0 || ctas_per_sm > 16 || rounds == 0) return fail(TURDB_ERR_INVALID_ARGUMENT, "ctas_per_sm 1..16, rounds >= 1");
+  DeviceGuard guard(idx->device);
+  if (!guard.ok) return fail(TURDB_ERR_CUDA, "cudaSetDevice(%d) failed", idx->device);
+  TeamLayout lay = make_layout(idx->ix.dim, idx->ix.ds, 8, 8, staging_slots, 1, true, idx->ix.n, false);
+  GatherProbeArgs a{};
+  a.arena = idx->ix.arena;
+  a.n = idx->ix.n;
+  a.ds = idx->ix.ds;
+  a.vec_bytes = lay.vec_bytes;
+  a.stride = lay.stride;
+  a.n_groups = staging_slots / 8;
+  a.rounds = rounds;
+  a.off_stage = 1024;
+  const uint32_t need = a.off_stage + staging_slots * a.stride;
+  const uint32_t smem = std::max(need, cta_smem_bytes);
+  if (smem > (uint32_t)idx->max_smem_optin) return fail(TURDB_ERR_UNSUPPORTED, "%u B of shared memory per CTA", smem);
+  CUDA_TRY(cudaFuncSetAttribute(gather_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gather_probe_kernel, 128, smem));
+  if (occ < 1) return fail(TURDB_ERR_UNSUPPORTED, "probe does not fit an SM");
+  const uint32_t per_sm = std::min<uint32_t>(ctas_per_sm, (uint32_t)occ);
+  const uint32_t grid = per_sm * (uint32_t)idx->num_sms;
+  uint32_t* d_sink = nullptr;
+  CUDA_TRY(cudaMalloc(&d_sink, 4));
+  a.sink = d_sink;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  gather_probe_kernel<<<grid, 128, smem>>>(a);  // warm-up
+  cudaEventRecord(e0);
+  gather_probe_kernel<<<grid, 128, smem>>>(a);
+  cudaEventRecord(e1);
+  cudaError_t e = cudaEventSynchronize(e1);
+  float ms = 0.f;
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_sink);
+  if (e != cudaSuccess) return fail(TURDB_ERR_CUDA, "gather probe failed: %s", cudaGetErrorString(e));
+  *out_ms = ms;
+  *out_bytes = (uint64_t)grid * rounds * staging_slots * a.vec_bytes;
+  return TURDB_OK;
+}
+
 // exact path + merge entry points live in exact_search.cuh / below
 #include "exact_abi.inl"
+#include "sql_topk.inl"
+#include "hnsw_file.inl"

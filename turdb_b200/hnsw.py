@@ -157,6 +157,13 @@ class CudaHnswIndex:
         _check(_lib.load().turdb_cuda_index_debug_counters(self._h, 1 if enable else 0, _ptr(out, C.c_uint64)))
         return out
 
+    def gather_probe(self, ctas_per_sm: int = 5, staging_slots: int = 16, cta_smem_bytes: int = 0, rounds: int = 64):
+        """Diagnostics: random whole-row gather bandwidth (GB/s) at the given residency; see gather_probe.cuh."""
+        ms, nbytes = C.c_float(0), C.c_uint64(0)
+        _check(_lib.load().turdb_cuda_index_gather_probe(self._h, ctas_per_sm, staging_slots, cta_smem_bytes, rounds,
+                                                          C.byref(ms), C.byref(nbytes)))
+        return nbytes.value / ms.value / 1e6, ms.value
+
     def profile_begin(self, capacity: int):
         _check(_lib.load().turdb_cuda_index_profile_begin(self._h, capacity))
 
