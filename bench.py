@@ -297,6 +297,17 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    # DRAM bytes of one traversal launch from the committed `ncu --set full` capture of this kernel on this
+    # workload (profiles/): read + write, per launch like `achieved`'s numerator
+    traffic, traffic_src = None, None
+    try:
+        import glob
+        cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic_hnsw_search_1m384.json")))
+        if cands and args.n == 1_000_000 and args.dim == 384 and args.ef == 128 and args.nq == 10_000:
+            tj = json.load(open(cands[-1]))
+            traffic, traffic_src = float(tj["dram_bytes_per_launch"]), os.path.relpath(cands[-1], ROOT)
+    except Exception:
+        pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
 
@@ -413,7 +424,8 @@ def main():
             "recall_at_10": recall,
             "exact_path": exact_info,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_kind": peak_kind, "kernel": "hnsw_search_kernel<cosine>",
+                         "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "traffic_source": traffic_src, "peak_kind": peak_kind, "kernel": "hnsw_search_kernel<cosine>",
                          "kernel_ms_avg": float(np.mean(kern_ms)), "overflow_pass_ms_avg": float(np.mean(over_ms)),
                          "algorithmic_bytes_per_launch": float(np.mean(step_bytes))},
             "cpu_baseline": cpu_baseline,

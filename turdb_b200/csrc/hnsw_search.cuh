@@ -38,6 +38,10 @@
 namespace turdb {
 
 constexpr uint32_t kDone = 0xFFFFFFFFu;
+#ifndef TURDB_MERGE_BATCH
+#define TURDB_MERGE_BATCH 4
+#endif
+constexpr int kMergeBatch = TURDB_MERGE_BATCH;
 
 struct TeamLayout {
   uint32_t off_bar, off_ctl, off_q, off_list, off_clist, off_cand, off_hash, off_stage;
@@ -924,23 +928,37 @@ __global__ void __launch_bounds__(128, 5) hnsw_search_kernel(const SearchArgs a)
           uint32_t* ti = A_id; A_id = B_id; B_id = ti;
         }
 #else
-        // in place: 32-entry blocks move from the top down (read block, sync, write block)
-        for (int32_t blk = (int32_t)((len - 1) >> 5); blk >= 0; --blk) {
-          const uint32_t i = (uint32_t)blk * 32 + lane;
-          float od = 0.f;
-          uint32_t oi = 0, np = 0xFFFFFFFFu;
-          if (i < len) {
-            od = A_d[i];
-            oi = A_id[i];
-            uint32_t sft = 0;
-            for (uint32_t j = 0; j < mp; ++j) sft += (tmp_ub[j] <= i) ? 1u : 0u;
-            np = i + sft;
+        // in place, from the top down in batches of kMergeBatch 32-entry blocks: a batch is read into registers, the
+        // warp synchronises, the batch is written at its shifted positions (always >= the old ones, and the
+        // batches above have already moved), the warp synchronises
+        for (int32_t top = (int32_t)((len - 1) >> 5); top >= 0; top -= kMergeBatch) {
+          float od[kMergeBatch];
+          uint32_t oi[kMergeBatch], np[kMergeBatch];
+#pragma unroll
+          for (int u = 0; u < kMergeBatch; ++u) {
+            const int32_t blk = top - u;
+            const uint32_t i = (uint32_t)blk * 32 + lane;
+            np[u] = 0xFFFFFFFFu;
+            od[u] = 0.f;
+            oi[u] = 0;
+            if (blk >= 0 && i < len) {
+              od[u] = A_d[i];
+              oi[u] = A_id[i];
+              np[u] = i;
+            }
+          }
+          for (uint32_t j = 0; j < mp; ++j) {
+            const uint32_t tv = tmp_ub[j];
+#pragma unroll
+            for (int u = 0; u < kMergeBatch; ++u) np[u] += (np[u] != 0xFFFFFFFFu && tv <= (uint32_t)(top - u) * 32 + lane) ? 1u : 0u;
           }
           __syncwarp();
-          if (np < ef) {
-            A_d[np] = od;
-            A_id[np] = oi;
-          }
+#pragma unroll
+          for (int u = 0; u < kMergeBatch; ++u)
+            if (np[u] < ef) {
+              A_d[np[u]] = od[u];
+              A_id[np[u]] = oi[u];
+            }
           __syncwarp();
         }
         uint32_t my_np = 0xFFFFFFFFu;
