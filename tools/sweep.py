@@ -116,7 +116,8 @@ for tun in args.tunings.split(";"):
             run(); torch.cuda.synchronize()
             c = idx.debug_counters(False).astype(np.float64)
             h = max(c[0], 1.0)
-            print("  dbg per-hop cycles: visited-insert %.0f" % (c[12]/h))
+            print("  dbg per-hop cycles: visited-insert (non-speculative) %.0f | helper warp 1: issue %.0f wait %.0f comp(+round-2 issue) %.0f"
+                  % (c[12]/h, c[13]/h, c[14]/h, c[15]/h))
             print("  dbg per-hop cycles: select %.0f adj+hash %.0f request %.0f (w0: issue %.0f wait %.0f comp %.0f) merge %.0f | "
                   "spec-hit %.2f | per-query: total %.0f upper %.0f hops %.1f" % (c[1]/h, c[2]/h, c[3]/h, c[6]/h, c[5]/h, c[7]/h, c[4]/h,
                    c[8]/h, c[9]/max(c[11],1), c[10]/max(c[11],1), c[0]/max(c[11],1)), flush=True)

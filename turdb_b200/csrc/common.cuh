@@ -120,43 +120,16 @@ __device__ __forceinline__ float2 unpack2(uint64_t v) {
 // float2 of the first step (base + 8*step0 + 2p floats); consecutive steps are 4 uint64 apart.
 template <bool L2>
 __device__ __forceinline__ uint64_t quad_accum(uint64_t acc, const uint64_t* av, const uint64_t* bv, uint32_t nsteps) {
-  // Blocks of 4 steps, software-pipelined: the loads of block i+1 are issued before the dependent
-  // multiply-add chain of block i, so the chain (one FFMA2 per step, in step order) never waits on shared
-  // memory after the first block.  The order of operations on `acc` is unchanged.
   uint32_t t = 0;
-#ifndef TURDB_ACCUM_PIPE
-#define TURDB_ACCUM_PIPE 1
-#endif
-  if (TURDB_ACCUM_PIPE && nsteps >= 4) {
-    uint64_t x[4], y[4];
+  for (; t + 8 <= nsteps; t += 8, av += 32, bv += 32) {
+    uint64_t x[8], y[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       x[u] = av[4 * u];
       y[u] = bv[4 * u];
     }
-    for (t = 4; t + 4 <= nsteps; t += 4) {
-      av += 16;
-      bv += 16;
-      uint64_t xn[4], yn[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        xn[u] = av[4 * u];
-        yn[u] = bv[4 * u];
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (L2) {
-          const uint64_t d = sub2(x[u], y[u]);
-          acc = fma2(d, d, acc);
-        } else {
-          acc = fma2(x[u], y[u], acc);
-        }
-        x[u] = xn[u];
-        y[u] = yn[u];
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       if (L2) {
         const uint64_t d = sub2(x[u], y[u]);
         acc = fma2(d, d, acc);
@@ -164,8 +137,6 @@ __device__ __forceinline__ uint64_t quad_accum(uint64_t acc, const uint64_t* av,
         acc = fma2(x[u], y[u], acc);
       }
     }
-    av += 16;
-    bv += 16;
   }
   for (; t < nsteps; ++t, av += 4, bv += 4) {
     if (L2) {

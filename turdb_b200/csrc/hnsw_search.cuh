@@ -582,6 +582,12 @@ __global__ void __launch_bounds__(128, 5) hnsw_search_kernel(const SearchArgs a)
         team_distances<METRIC>(ix, t, m);
         __syncthreads();
       }
+      if (t.dbg && warp == 1 && lane == 0) {  // diagnostics: the first helper's share of the data path
+        atomicAdd(a.dbg + 13, (unsigned long long)t.c_issue);
+        atomicAdd(a.dbg + 14, (unsigned long long)t.c_wait);
+        atomicAdd(a.dbg + 15, (unsigned long long)t.c_comp);
+        t.c_issue = t.c_wait = t.c_comp = 0;
+      }
       continue;
     }
 

@@ -58,6 +58,14 @@ class VectorScanBatch:
         return rows[:, :self.limit], keys[:, :self.limit], counts
 
 
+    def execute_device(self, d_literals: int, nq: int, d_rows: int, d_keys: int, d_counts: int, stream: int = 0, margin: int = 0):
+        """Device-resident form: raw device addresses, enqueued on `stream` (no host synchronisation).
+        A statement the exact scan cannot certify at this margin has count 0xFFFFFFFD."""
+        _check(_lib.load().turdb_cuda_sql_topk_batch_device(self.index._h, d_literals, self.index.dim, nq, self.limit, self.offset,
+                                                            int(self.op), margin, 1 if self.use_index else 0, self.ef_search,
+                                                            d_rows, d_keys, d_counts, stream or None))
+
+
 class VectorTopKExec:
     """One statement with the executor protocol of the reference: open() / next() -> (row_id, key) | None / close()."""
 
