@@ -104,9 +104,6 @@ __global__ void col_bias_kernel(const float* __restrict__ norm2, uint64_t n, flo
 // ------------------------------------------------------------------------------------------------
 // tcgen05 helpers
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),

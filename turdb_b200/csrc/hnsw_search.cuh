@@ -31,6 +31,19 @@
 // 1: by per-thread 16 B cp.async (LDGSTS), 512 B per warp instruction, commit/wait groups.  Measured on B200
 //    (1M x 384 and 1M x 128): the LDGSTS issue stalls for ~2.6k cycles per 8-vector chunk against ~0.9k for
 //    eight bulk copies, 25-33 % slower end to end — kept only as the measured alternative.
+// 1: vectors of a hop that do not fit the first gather round are prefetched into L2 during that round
+#ifndef TURDB_R2_PREFETCH
+#define TURDB_R2_PREFETCH 1
+#endif
+
+// Measured and dropped: splitting the bulk-copy issue of a second-round chunk between its owner and an idle
+// helper (through a "slots free" mbarrier) — 3 % slower at 1M x 384 than the owner issuing alone.
+
+// resident CTAs per SM the register allocation is bounded for (8 -> 64 registers per thread at 128 threads)
+#ifndef TURDB_MIN_CTAS
+#define TURDB_MIN_CTAS 5
+#endif
+
 #ifndef TURDB_GATHER_MODE
 #define TURDB_GATHER_MODE 0
 #endif
@@ -214,6 +227,13 @@ __device__ __forceinline__ void team_distances_whole(const DeviceIndex& ix, Team
       const uint32_t id = t.cand_ids[v];  // chunk v >> 3 < G uses group v >> 3, slot v & 7: staging slot v
       bulk_g2s(t.stage_u32 + v * t.stride, ix.arena + (size_t)id * ix.ds, t.vec_bytes, t.bar0 + 8 * (v >> 3));
     }
+#if TURDB_R2_PREFETCH
+    // The vectors that have to wait for a second round (no free staging slot yet) are pulled into L2 now, by
+    // the leader (it has slack): their bulk copies will then pay an L2 hit instead of a second DRAM round
+    // trip.  Same DRAM bytes — every one of them is read exactly once, for certain, a little later.
+    if (t.warp == 0 && t.n_warps >= 3 && m1 + lane < m)  // a 2-warp team has no slack on the leader (measured)
+      bulk_prefetch_l2(ix.arena + (size_t)t.cand_ids[m1 + lane] * ix.ds, t.vec_bytes);
+#endif
   }
   if (t.dbg) t.c_issue += (uint32_t)(clock64() - t0);
   for (uint32_t c = 0; c < nchunks; ++c) {
@@ -500,7 +520,7 @@ __device__ __forceinline__ uint32_t rank_merge(const float* src_d, const uint32_
 }
 
 template <int METRIC, bool GLOBAL_VISITED, bool FILTERED>
-__global__ void __launch_bounds__(128, 5) hnsw_search_kernel(const SearchArgs a) {
+__global__ void __launch_bounds__(128, TURDB_MIN_CTAS) hnsw_search_kernel(const SearchArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const DeviceIndex& ix = a.ix;
   const uint32_t tid = threadIdx.x, nthreads = blockDim.x;
