@@ -140,3 +140,20 @@ def test_sharded_search_world2_gloo(tmp_path):
     gt, _, _ = ob.sql_topk(x, q, k)
     rec = np.mean([len(set(r0["rows"][i].tolist()) & set(gt[i].astype(np.int64).tolist())) / k for i in range(nq)])
     assert rec >= 0.9
+
+
+def test_partitioned_builder_keeps_structure():
+    """graph_build's IVF candidate pass (large corpora): same structural contract as the all-pairs pass."""
+    import torch
+    from turdb_b200 import datasets as ds
+    from turdb_b200.graph_build import build_graph
+    torch.set_num_threads(4)
+    x = ds.gaussian_latent(6000, 32, seed=3)
+    a = build_graph(x, seed=5, device="cpu", ivf_cells=32, ivf_probe=6, ivf_exact_prefix=512)
+    assert a["provenance"].endswith("(ivf 32x6)")
+    n = 6000
+    assert a["l0_adj"].shape == (n, 32) and a["l0_cnt"].max() <= 32 and a["l0_cnt"].min() >= 1
+    valid = np.arange(32)[None, :] < a["l0_cnt"][:, None]
+    assert (a["l0_adj"][valid] < n).all() and (a["l0_adj"][~valid] == 0xFFFFFFFF).all()
+    assert not (a["l0_adj"] == np.arange(n, dtype=np.uint32)[:, None]).any()  # no self loops
+    assert a["levels"][a["entry"]] == a["max_level"]

@@ -18,6 +18,7 @@ from turdb_b200.hnsw import CudaHnswIndex, DistanceFunction
 ap = argparse.ArgumentParser()
 ap.add_argument("--out", default="gpurun_out/configs.json")
 ap.add_argument("--only", default="")
+ap.add_argument("--heavy", action="store_true", help="also run the configs marked heavy (minutes of build time)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 stream = torch.cuda.current_stream().cuda_stream
@@ -35,6 +36,9 @@ CONFIGS = [
     dict(name="config5_128_L2_clustered_latent_centres (2M rows per GPU of the 12.5M named)", n=2_000_000, dim=128, metric=0,
          gen="clustered", kw=dict(centre_latent=16, corpus_n=2_000_000), m=16, ef=64, k=10, nq=10_000, builder="knn-heuristic",
          sql=True),
+    dict(name="config5_full_shard_12.5Mx128_L2_clustered_latent_centres (one of the 8 sub-indexes of 100M)", n=12_500_000, dim=128,
+         metric=0, gen="clustered", kw=dict(centre_latent=16, corpus_n=12_500_000), m=16, ef=64, k=10, nq=10_000,
+         builder="knn-heuristic", sql=True, heavy=True),
     dict(name="config5_128_L2_clustered_iid_centres (2M rows per GPU; i.i.d. centres, recall ceiling documented)", n=2_000_000,
          dim=128, metric=0, gen="clustered", kw=dict(corpus_n=2_000_000), m=16, ef=64, k=10, nq=10_000, builder="knn-heuristic"),
 ]
@@ -42,6 +46,8 @@ CONFIGS = [
 out = []
 for cfg in CONFIGS:
     if args.only and args.only not in cfg["name"]:
+        continue
+    if cfg.get("heavy") and not (args.heavy or args.only):
         continue
     t0 = time.time()
     x = ds.make(cfg["gen"], cfg["n"], cfg["dim"], seed=1, **cfg["kw"])

@@ -74,6 +74,67 @@ def _knn_level(xf: torch.Tensor, norms: torch.Tensor, ids: torch.Tensor, k: int,
 
 
 @torch.no_grad()
+def _knn_level0_ivf(xf: torch.Tensor, norms: torch.Tensor, k: int, margin: int, n_cells: int, n_probe: int,
+                    exact_prefix: int, chunk: int, seed: int):
+    """Predecessor k-NN for corpora too large for the all-pairs pass (O(n^2) scores; 12.5M rows = 8e13 of them).
+    Coarse partition: `n_cells` corpus points as centroids, every node in its nearest cell; a node's candidates are
+    its predecessors inside the `n_probe` cells nearest to ITS CELL's centroid (one dense score block per cell).
+    The first `exact_prefix` nodes still take the exact pass: they are the ones whose few predecessors are far away
+    and give the graph its long-range links.  Same outputs as _knn_level (positions == node ids at level 0)."""
+    n, dev = xf.shape[0], xf.device
+    out_pos = torch.full((n, k), -1, dtype=torch.int64, device=dev)
+    out_d = torch.full((n, k), float("inf"), dtype=torch.float32, device=dev)
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    cent_ids = torch.randperm(n, generator=gen)[:n_cells].to(dev)
+    cent = xf[cent_ids]
+    cn = norms[cent_ids]
+    cell = torch.empty(n, dtype=torch.int64, device=dev)
+    for s in range(0, n, 1 << 18):
+        e = min(n, s + (1 << 18))
+        cell[s:e] = torch.argmin(cn[None, :] - 2.0 * (xf[s:e] @ cent.T), dim=1)
+    cc = cn[:, None] + cn[None, :] - 2.0 * (cent @ cent.T)
+    probe = torch.topk(cc, min(n_probe, n_cells), dim=1, largest=False).indices  # [n_cells, n_probe], own cell first
+    order = torch.argsort(cell, stable=True)  # ids ascending inside a cell
+    counts = torch.bincount(cell, minlength=n_cells)
+    starts = torch.cumsum(counts, 0) - counts
+    starts_h, counts_h, probe_h = starts.cpu().tolist(), counts.cpu().tolist(), probe.cpu().tolist()
+    for c in range(n_cells):
+        if counts_h[c] == 0:
+            continue
+        col_ids = torch.cat([order[starts_h[p]:starts_h[p] + counts_h[p]] for p in probe_h[c]])
+        cols, coln = xf[col_ids], norms[col_ids]
+        for rs in range(0, counts_h[c], chunk):
+            re = min(counts_h[c], rs + chunk)
+            row_ids = order[starts_h[c] + rs:starts_h[c] + re]
+            rows = xf[row_ids]
+            score = rows @ cols.T
+            score.mul_(-2.0).add_(coln[None, :])
+            score.masked_fill_(col_ids[None, :] >= row_ids[:, None], float("inf"))  # predecessors only
+            kc = min(k + margin, col_ids.numel())
+            cs, cand = torch.topk(score, kc, dim=1, largest=False, sorted=False)
+            del score
+            valid = torch.isfinite(cs)
+            cid = col_ids[cand]
+            de = ((xf[cid] - rows[:, None, :]) ** 2).sum(-1)
+            de = torch.where(valid, de, torch.full_like(de, float("inf")))
+            de, o = torch.sort(de, dim=1)
+            cid = torch.gather(cid, 1, o)
+            cid = torch.where(torch.isfinite(de), cid, torch.full_like(cid, -1))
+            kk = min(k, kc)
+            out_pos[row_ids, :kk] = cid[:, :kk]
+            out_d[row_ids, :kk] = de[:, :kk]
+    p = min(exact_prefix, n)
+    if p > 1:
+        ids = torch.arange(p, device=dev)
+        pp, pd = _knn_level(xf[:p], norms[:p], ids, min(k, p - 1), margin, chunk)
+        out_pos[:p] = -1
+        out_d[:p] = float("inf")
+        out_pos[:p, :pp.shape[1]] = pp
+        out_d[:p, :pd.shape[1]] = pd
+    return out_pos, out_d
+
+
+@torch.no_grad()
 def _heuristic(cols: torch.Tensor, cand: torch.Tensor, cand_d: torch.Tensor, cap: int, chunk: int):
     """select_neighbors_heuristic over rows of ascending candidates (local positions, -1 / inf padded).
     Returns ids [B,cap] (-1 padded), d [B,cap], counts [B]; kept candidates first, then the back-fill."""
@@ -115,8 +176,9 @@ def _heuristic(cols: torch.Tensor, cand: torch.Tensor, cand_d: torch.Tensor, cap
 
 
 @torch.no_grad()
-def _level_lists(xf, norms, ids, cap, knn_k, rev_cap, chunk_rows, chunk_h):
-    """Neighbour lists (local positions, -1 padded) for one level."""
+def _level_lists(xf, norms, ids, cap, knn_k, rev_cap, chunk_rows, chunk_h, ivf=None):
+    """Neighbour lists (local positions, -1 padded) for one level.  ivf = (n_cells, n_probe, exact_prefix, seed)
+    switches the candidate pass of a whole-corpus level to the partitioned form."""
     dev = xf.device
     n_l = ids.numel()
     if n_l <= 1:
@@ -124,7 +186,10 @@ def _level_lists(xf, norms, ids, cap, knn_k, rev_cap, chunk_rows, chunk_h):
     whole = n_l == xf.shape[0]
     cols = xf if whole else xf[ids]
     k = min(knn_k, n_l - 1)
-    pos, d = _knn_level(xf, norms, ids, k, margin=16, chunk=chunk_rows)  # forward candidates: predecessors only
+    if ivf is not None and whole:
+        pos, d = _knn_level0_ivf(xf, norms, k, 16, ivf[0], ivf[1], ivf[2], chunk_rows, ivf[3])
+    else:
+        pos, d = _knn_level(xf, norms, ids, k, margin=16, chunk=chunk_rows)  # forward candidates: predecessors only
     f_ids, f_d, f_cnt = _heuristic(cols, pos, d, cap, chunk_h)
     del pos, d
     # ---- back-links: dst <- src for every forward edge src -> dst that dst does not already hold ----
@@ -174,8 +239,11 @@ def _level_lists(xf, norms, ids, cap, knn_k, rev_cap, chunk_rows, chunk_h):
 @torch.no_grad()
 def build_graph(vectors: np.ndarray, m: int = 16, seed: int = 1234, device: str | torch.device = "cuda:0",
                 knn_k: int = 64, row_ids: np.ndarray | None = None, chunk_rows: int = 4096,
-                l0_rev: int = MAX_L0, up_rev: int = 64) -> dict:
-    """vectors [n, dim] f32 -> the flattened graph dict `CudaHnswIndex.from_graph` / the oracle take."""
+                l0_rev: int = MAX_L0, up_rev: int = 64, ivf_cells: int | None = None, ivf_probe: int = 10,
+                ivf_exact_prefix: int = 131072) -> dict:
+    """vectors [n, dim] f32 -> the flattened graph dict `CudaHnswIndex.from_graph` / the oracle take.
+    ivf_cells: None = all-pairs candidate pass up to 3M rows, partitioned pass (~sqrt(n) cells) above; 0 = always
+    all-pairs; > 0 = that many cells."""
     vectors = np.ascontiguousarray(vectors, dtype=np.float32)
     n, dim = vectors.shape
     dev = torch.device(device)
@@ -189,7 +257,10 @@ def build_graph(vectors: np.ndarray, m: int = 16, seed: int = 1234, device: str 
         norms = (xf * xf).sum(1)
         lv = torch.from_numpy(levels.astype(np.int64)).to(dev)
         chunk_h = max(256, min(8192, (1 << 28) // max(1, (knn_k + max(l0_rev, up_rev)) * dim)))
-        l0, l0_cnt = _level_lists(xf, norms, torch.arange(n, device=dev), MAX_L0, knn_k, l0_rev, chunk_rows, chunk_h)
+        if ivf_cells is None:
+            ivf_cells = 0 if n <= 3_000_000 else 1 << max(6, int(round(math.log2(math.sqrt(n)))))
+        ivf = (min(ivf_cells, n), ivf_probe, ivf_exact_prefix, seed) if ivf_cells else None
+        l0, l0_cnt = _level_lists(xf, norms, torch.arange(n, device=dev), MAX_L0, knn_k, l0_rev, chunk_rows, chunk_h, ivf)
         l0_adj = torch.where(l0 >= 0, l0, torch.full_like(l0, INVALID)).to(torch.int64).cpu().numpy().astype(np.uint32)
         n_slots = int(levels.astype(np.int64).sum())
         up_base = np.full(n, INVALID, np.uint32)
@@ -211,6 +282,7 @@ def build_graph(vectors: np.ndarray, m: int = 16, seed: int = 1234, device: str 
             vectors=vectors,
             row_ids=np.arange(n, dtype=np.uint64) if row_ids is None else np.ascontiguousarray(row_ids, np.uint64),
             levels=levels, l0_adj=l0_adj, l0_cnt=l0_cnt.cpu().numpy().astype(np.uint8), up_base=up_base,
-            up_adj=up_adj, up_cnt=up_cnt, entry=entry, max_level=max_level, provenance="predecessor-knn-heuristic")
+            up_adj=up_adj, up_cnt=up_cnt, entry=entry, max_level=max_level,
+            provenance="predecessor-knn-heuristic" if not ivf else f"predecessor-knn-heuristic(ivf {ivf[0]}x{ivf[1]})")
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev_tf32
