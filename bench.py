@@ -201,7 +201,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a mismatched collective must fail in minutes, not hold the box for NCCL's default 10
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
 
     t0 = time.time()
     x, qb = make_data(args, rank)
@@ -270,10 +272,11 @@ def main():
     elapsed_ms = e0.elapsed_time(e1)
     kern_ms, over_ms = idx.profile_read(args.steps)
     if rank == 0 and elapsed_ms < 400:  # keep the GPU under the same load until the sampler has a few readings
+        # rank-local kernel launches only: a collective here would not be matched by the other ranks
         t_end = time.time() + 0.45
         i = 0
         while time.time() < t_end:
-            step(i)
+            local_search(dq[i % nb])
             i += 1
         torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
