@@ -120,6 +120,26 @@ int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const float* d_que
                                        float* d_out_dist, uint32_t* d_out_counts,
                                        turdb_cuda_search_stats* d_out_stats, void* stream);
 
+/*
+ * ---- SQ8 arena (QuantizationType::SQ8, header byte 43 = 1) ---------------------
+ * enable_sq8 encodes every arena row as SQ8Vector::from_f32 does (src/hnsw/quantization.rs:68-95: per-row
+ * min, scale = (max - min) / 255, code = round((v - min) / scale)) into rows of `dim` codes | pad to 4 | min f32 |
+ * scale f32, row_bytes apart (a multiple of 16), on the device; out_rows (nullable, out_capacity bytes) receives
+ * a copy.  search_batch_sq8_device is search_batch_device over that arena: every element is decoded as
+ * SQ8Vector::decode does (min + q * scale, :108-113) and fed to the same distance chains, so its results equal
+ * the FP32 search over the decoded vectors bit for bit while it gathers dim + 8 instead of 4 dim bytes per
+ * distance.  The reference declares SQ8 but never wires it into the index, so that equality is
+ * the parity contract.  Distances returned are distances to the DECODED vectors.  No filtered variant.
+ */
+int32_t turdb_cuda_index_enable_sq8(turdb_cuda_index* idx, uint8_t* out_rows, uint64_t out_capacity,
+                                    uint32_t* out_row_bytes);
+int32_t turdb_cuda_search_batch_sq8_device(turdb_cuda_index* idx, const float* d_queries,
+                                           uint32_t query_dim, uint32_t nq, uint32_t k, uint32_t ef,
+                                           uint8_t metric, uint64_t* d_out_row_ids,
+                                           uint32_t* d_out_node_ids, float* d_out_dist,
+                                           uint32_t* d_out_counts,
+                                           turdb_cuda_search_stats* d_out_stats, void* stream);
+
 /* Tunables of the traversal kernel (0 = automatic).  warps_per_cta (1..4) warps cooperate on one
  * query, staging_slots (8..32) neighbour vectors are in flight per query, hash_bits sizes the
  * shared-memory visited table, segments = pieces a vector is streamed in through its staging slot. */

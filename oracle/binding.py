@@ -249,6 +249,35 @@ def sql_projection_distance(op, a, b):
     return None if isnull.value else np.float32(v)
 
 
+def sq8_encode(vectors):
+    """SQ8Vector::from_f32 per row -> (codes u8 [n, dim], min f32 [n], scale f32 [n])."""
+    v = np.ascontiguousarray(vectors, dtype=np.float32)
+    n, dim = v.shape
+    L = lib()
+    L.tdo_sq8_encode.restype = None
+    L.tdo_sq8_encode.argtypes = [C.POINTER(C.c_float), C.c_uint32, C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    codes = np.zeros((n, dim), np.uint8)
+    mn, sc = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    for i in range(n):
+        a, b = C.c_float(0), C.c_float(0)
+        L.tdo_sq8_encode(_p(v[i], C.c_float), dim, _p(codes[i], C.c_uint8), C.byref(a), C.byref(b))
+        mn[i], sc[i] = a.value, b.value
+    return codes, mn, sc
+
+
+def sq8_decode(codes, mn, sc):
+    """SQ8Vector::decode per row."""
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    n, dim = codes.shape
+    L = lib()
+    L.tdo_sq8_decode.restype = None
+    L.tdo_sq8_decode.argtypes = [C.POINTER(C.c_uint8), C.c_uint32, C.c_float, C.c_float, C.POINTER(C.c_float)]
+    out = np.zeros((n, dim), np.float32)
+    for i in range(n):
+        L.tdo_sq8_decode(_p(codes[i], C.c_uint8), dim, float(mn[i]), float(sc[i]), _p(out[i], C.c_float))
+    return out
+
+
 def hnsw_file_write(graph: "OracleGraph", index_id=1, table_id=1, ef_search=32, distance_fn=L2, quantization=0,
                     mode=1):
     """The bytes PersistentHnswIndex would leave on disk for this graph (see tdo_hnsw_file_write).

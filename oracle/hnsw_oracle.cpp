@@ -1116,3 +1116,40 @@ extern "C" int64_t tdo_hnsw_file_write(const tdo_graph* g, uint64_t index_id, ui
   }
   return (int64_t)file.size();
 }
+
+// ----------------------------------------------------------------------------------------------
+// SQ8 — SQ8Vector::from_f32 / decode, src/hnsw/quantization.rs:68-95, 108-113.  (The reference never wires
+// SQ8 into the index; an SQ8 traversal is DEFINED here as the FP32 search over the decoded vectors.)
+// ----------------------------------------------------------------------------------------------
+extern "C" void tdo_sq8_encode(const float* values, uint32_t dim, uint8_t* codes, float* out_min, float* out_scale) {
+  if (dim == 0) {
+    *out_min = 0.f;
+    *out_scale = 0.f;
+    return;
+  }
+  float mn = INFINITY, mx = -INFINITY;
+  for (uint32_t i = 0; i < dim; ++i) {  // fold(f32::INFINITY, f32::min) / fold(NEG_INFINITY, f32::max)
+    mn = std::fmin(mn, values[i]);
+    mx = std::fmax(mx, values[i]);
+  }
+  const float range = mx - mn;
+  const float scale = range > 0.0f ? range / 255.0f : 1.0f;
+  for (uint32_t i = 0; i < dim; ++i) {
+    if (scale == 0.0f || range == 0.0f) {
+      codes[i] = 0;
+    } else {
+      float q = std::round((values[i] - mn) / scale);  // f32::round: half away from zero
+      q = q < 0.0f ? 0.0f : (q > 255.0f ? 255.0f : q);
+      codes[i] = (uint8_t)q;
+    }
+  }
+  *out_min = mn;
+  *out_scale = scale;
+}
+
+extern "C" void tdo_sq8_decode(const uint8_t* codes, uint32_t dim, float mn, float scale, float* out) {
+  for (uint32_t i = 0; i < dim; ++i) {
+    volatile float prod = (float)codes[i] * scale;  // two roundings: rustc does not contract `min + q * scale`
+    out[i] = mn + prod;
+  }
+}

@@ -92,6 +92,10 @@ int tdo_node_read(const uint8_t* buf, uint64_t len, uint64_t* row_id, uint8_t* m
                   uint32_t* l0_pages, uint16_t* l0_slots, uint8_t* l0_count, uint32_t* up_pages,
                   uint16_t* up_slots, uint8_t* up_counts /* [max_level] , up arrays [max_level][16] */);
 
+/* ---- SQ8 (src/hnsw/quantization.rs:68-95, 108-113) ---- */
+void tdo_sq8_encode(const float* values, uint32_t dim, uint8_t* codes, float* out_min, float* out_scale);
+void tdo_sq8_decode(const uint8_t* codes, uint32_t dim, float mn, float scale, float* out);
+
 /* ---- .hnsw file: the reference's write path (storage.rs:121-158, 545-669, 693-757; mod.rs:776-904) ----
  * mode 0 = verbatim page-fill rule (records overlap: 13-bit slot offsets); mode 1 = new page before overlap.
  * buf may be NULL (size query).  out_pages/out_slots: NodeId of every dense node.  Returns the file length,

@@ -27,6 +27,7 @@ ap.add_argument("--gen", default="gaussian_latent", choices=["gaussian_latent", 
 ap.add_argument("--libs", default="", help="A/B: comma-separated library files; the graph is built once and each "
                 "library is measured in a child process (TURDB_CUDA_LIB)")
 ap.add_argument("--graph", default="", help="(internal) npz with a prebuilt graph")
+ap.add_argument("--sq8", action="store_true", help="traverse the SQ8 arena (enable_sq8 + search_batch_sq8_device)")
 ap.add_argument("--probe", default="", help="gather-ceiling probe settings: ctas_per_sm,slots,cta_smem_bytes;...")
 args = ap.parse_args()
 
@@ -99,7 +100,13 @@ for tun in args.tunings.split(";"):
     warps, slots, hb, segs = ([int(v) for v in tun.split(",")] + [0])[:4]
     try:
         idx.set_tuning(warps, slots, hb, segs)
+        if args.sq8:
+            idx.enable_sq8()
         def run():
+            if args.sq8:
+                idx.search_batch_sq8_device(dq.data_ptr(), args.nq, args.k, args.ef, args.metric, rows.data_ptr(), dist.data_ptr(),
+                                            cnt.data_ptr(), nodes.data_ptr(), stats.data_ptr(), stream)
+                return
             idx.search_batch_device(dq.data_ptr(), args.nq, args.k, args.ef, args.metric, rows.data_ptr(), dist.data_ptr(),
                                     cnt.data_ptr(), nodes.data_ptr(), stats.data_ptr(), 0, stream)
         for _ in range(2):
@@ -123,7 +130,8 @@ for tun in args.tunings.split(";"):
                    c[8]/h, c[9]/max(c[11],1), c[10]/max(c[11],1), c[0]/max(c[11],1)), flush=True)
         ms = float(km.mean())
         st = stats.cpu().numpy().astype(np.int64)
-        nbytes = (st[:, 0] * args.dim * 4 + st[:, 2] * 129 + st[:, 3] * 65 + args.dim * 4 + args.k * 12).sum()
+        row_b = (args.dim + 8) if args.sq8 else args.dim * 4
+        nbytes = (st[:, 0] * row_b + st[:, 2] * 129 + st[:, 3] * 65 + args.dim * 4 + args.k * 12).sum()
         nd = nodes.cpu().numpy()
         if ref_nodes is None:
             ref_nodes = nd.copy()

@@ -187,6 +187,53 @@ __device__ __forceinline__ float quad_dot(const float* a, const float* b, uint32
   return quad_finish<false>(acc, a + (steps << 3), b + (steps << 3), dim & 7);
 }
 
+// ---- SQ8 rows (SQ8Vector, src/hnsw/quantization.rs:60-116): dim u8 codes | pad to 4 | min f32 | scale f32 ----
+// A quad walks the codes in the same AVX2 lane order as the FP32 rows; every element is decoded exactly as
+// SQ8Vector::decode does (min + (q as f32) * scale, two roundings, quantization.rs:108-113) before it enters the
+// chain, so the value equals the FP32 functions applied to the decoded vector bit for bit.
+__device__ __forceinline__ uint64_t sq8_pair(const uint8_t* row, uint32_t step, uint32_t p, float mn, float sc) {
+  const uint2 w = *reinterpret_cast<const uint2*>(row + 8 * step);  // the 8 codes of this AVX step (quad broadcast)
+  const uint32_t word = (p & 2) ? w.y : w.x, sh = (p & 1) * 16;
+  const float b0 = __fadd_rn(mn, __fmul_rn((float)((word >> sh) & 0xFFu), sc));
+  const float b1 = __fadd_rn(mn, __fmul_rn((float)((word >> (sh + 8)) & 0xFFu), sc));
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(b0), "f"(b1));
+  return r;
+}
+// MODE 0: squared L2 of (a, decode(row)); 1: dot(a, decode(row)); 2: dot(decode(row), decode(row)) (a unused)
+template <int MODE>
+__device__ __forceinline__ float quad_sq8(const float* a, const uint8_t* row, uint32_t dim, uint32_t p) {
+  const uint32_t steps = dim >> 3, tail0 = steps << 3;
+  const float* ms = reinterpret_cast<const float*>(row + ((dim + 3) & ~3u));
+  const float mn = ms[0], sc = ms[1];
+  const uint64_t* av = reinterpret_cast<const uint64_t*>(a) + p;
+  uint64_t acc = 0ull;
+  for (uint32_t t = 0; t < steps; ++t) {
+    const uint64_t b = sq8_pair(row, t, p, mn, sc);
+    if (MODE == 0) {
+      const uint64_t d = sub2(av[4 * t], b);
+      acc = fma2(d, d, acc);
+    } else if (MODE == 1) {
+      acc = fma2(av[4 * t], b, acc);
+    } else {
+      acc = fma2(b, b, acc);
+    }
+  }
+  float r = quad_hsum(unpack2(acc));
+  for (uint32_t i = tail0; i < dim; ++i) {  // the unfused scalar tail (distance.rs:120-126 / 225-229)
+    const float b = __fadd_rn(mn, __fmul_rn((float)row[i], sc));
+    if (MODE == 0) {
+      const float d = __fsub_rn(a[i], b);
+      r = __fadd_rn(r, __fmul_rn(d, d));
+    } else if (MODE == 1) {
+      r = __fadd_rn(r, __fmul_rn(a[i], b));
+    } else {
+      r = __fadd_rn(r, __fmul_rn(b, b));
+    }
+  }
+  return r;
+}
+
 // cosine_avx2's epilogue, distance.rs:279-284
 __device__ __forceinline__ float cosine_finish(float dot, float na, float nb) {
   float np = __fsqrt_rn(__fmul_rn(na, nb));

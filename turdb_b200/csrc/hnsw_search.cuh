@@ -89,6 +89,9 @@ struct SearchArgs {
   uint32_t* global_visited;  // fallback pass: [CTAs][vis_words] bitsets
   uint32_t vis_words;
   unsigned long long* dbg;   // optional [16] cycle counters (diagnostics), null in production
+  // rows the traversal gathers: the FP32 arena (row_bytes == ds * 4) or, for the SQ8 kernels, the code arena
+  const uint8_t* rows;
+  uint32_t row_bytes;        // bytes between rows == bytes copied per row (multiple of 16)
   // search_filtered (search.rs:352-398): one bit per node; candidates that do not fit the shared window
   const uint64_t* visible;   // null => unfiltered search
   uint2* f_ovf;              // [CTAs][f_ocap] (distance bits, id) overflow of the candidate window
@@ -124,6 +127,7 @@ struct Team {
   const uint8_t* stage;
   uint32_t stage_u32;
   uint32_t stride, vec_bytes, n_groups, n_segs, seg_steps;
+  const uint8_t* rows;       // gather source, vec_bytes apart
   uint32_t phases;           // per-warp parity bits of the groups this warp owns
   float qnorm;
   uint32_t c_issue, c_wait, c_comp;  // diagnostics: cycles spent by this warp per phase
@@ -198,7 +202,7 @@ __device__ __forceinline__ void team_distances_pieces(const DeviceIndex& ix, Tea
 }
 
 // Whole-vector form (n_segs == 1): same dealing of chunks to groups and warps, one bulk copy per vector.
-template <int METRIC>
+template <int METRIC, bool SQ8>
 __device__ __forceinline__ void team_distances_whole(const DeviceIndex& ix, Team& t, uint32_t m) {
   const uint32_t lane = t.lane, p = lane & 3, G = t.n_groups;
   const uint32_t nchunks = (m + 7) >> 3;
@@ -210,7 +214,7 @@ __device__ __forceinline__ void team_distances_whole(const DeviceIndex& ix, Team
     __syncwarp();
     if (lane < cnt) {
       const uint32_t id = t.cand_ids[8 * c + lane];
-      bulk_g2s(t.stage_u32 + (g * 8 + lane) * t.stride, ix.arena + (size_t)id * ix.ds, t.vec_bytes, bar);
+      bulk_g2s(t.stage_u32 + (g * 8 + lane) * t.stride, t.rows + (size_t)id * t.vec_bytes, t.vec_bytes, bar);
     }
   };
   long long t0 = t.dbg ? clock64() : 0;
@@ -225,14 +229,14 @@ __device__ __forceinline__ void team_distances_whole(const DeviceIndex& ix, Team
     const uint32_t v = t.warp + t.n_warps * lane;
     if (v < m1) {
       const uint32_t id = t.cand_ids[v];  // chunk v >> 3 < G uses group v >> 3, slot v & 7: staging slot v
-      bulk_g2s(t.stage_u32 + v * t.stride, ix.arena + (size_t)id * ix.ds, t.vec_bytes, t.bar0 + 8 * (v >> 3));
+      bulk_g2s(t.stage_u32 + v * t.stride, t.rows + (size_t)id * t.vec_bytes, t.vec_bytes, t.bar0 + 8 * (v >> 3));
     }
 #if TURDB_R2_PREFETCH
     // The vectors that have to wait for a second round (no free staging slot yet) are pulled into L2 now, by
     // the leader (it has slack): their bulk copies will then pay an L2 hit instead of a second DRAM round
     // trip.  Same DRAM bytes — every one of them is read exactly once, for certain, a little later.
     if (t.warp == 0 && t.n_warps >= 3 && m1 + lane < m)  // a 2-warp team has no slack on the leader (measured)
-      bulk_prefetch_l2(ix.arena + (size_t)t.cand_ids[m1 + lane] * ix.ds, t.vec_bytes);
+      bulk_prefetch_l2(t.rows + (size_t)t.cand_ids[m1 + lane] * t.vec_bytes, t.vec_bytes);
 #endif
   }
   if (t.dbg) t.c_issue += (uint32_t)(clock64() - t0);
@@ -247,8 +251,11 @@ __device__ __forceinline__ void team_distances_whole(const DeviceIndex& ix, Team
     long long w1 = t.dbg ? clock64() : 0;
     t.c_wait += (uint32_t)(w1 - w0);
     t.phases ^= (1u << g);
-    const float* b = reinterpret_cast<const float*>(t.stage + (g * 8 + (lane >> 2)) * t.stride);
-    const float raw = (METRIC == kL2) ? quad_l2sq(t.q, b, ix.dim, p) : quad_dot(t.q, b, ix.dim, p);
+    const uint8_t* bs = t.stage + (g * 8 + (lane >> 2)) * t.stride;
+    const float* b = reinterpret_cast<const float*>(bs);
+    float raw;
+    if (SQ8) raw = (METRIC == kL2) ? quad_sq8<0>(t.q, bs, ix.dim, p) : quad_sq8<1>(t.q, bs, ix.dim, p);
+    else raw = (METRIC == kL2) ? quad_l2sq(t.q, b, ix.dim, p) : quad_dot(t.q, b, ix.dim, p);
     if (p == 0 && slot < m) {
       float d = raw;
       if (METRIC == kIP) d = -raw;  // inner_product_avx2, distance.rs:240-242
@@ -317,30 +324,34 @@ __device__ __forceinline__ void team_distances_ldgsts(const DeviceIndex& ix, Tea
   }
 }
 
-template <int METRIC>
+template <int METRIC, bool SQ8>
 __device__ __forceinline__ void team_distances(const DeviceIndex& ix, Team& t, uint32_t m) {
+  if (SQ8) {  // code rows are short: always the whole-row form (the host never splits them)
+    team_distances_whole<METRIC, true>(ix, t, m);
+    return;
+  }
 #if TURDB_GATHER_MODE == 1
   if (t.n_segs == 1) team_distances_ldgsts<METRIC>(ix, t, m);
 #else
-  if (t.n_segs == 1) team_distances_whole<METRIC>(ix, t, m);
+  if (t.n_segs == 1) team_distances_whole<METRIC, false>(ix, t, m);
 #endif
   else team_distances_pieces<METRIC>(ix, t, m);
 }
 
 // Leader side of a request: publish m, run the team's distance pass, return this lane's distance.
 // `overlap` runs on the leader between the two barriers, i.e. while the helper warps gather and reduce.
-template <int METRIC, typename F>
+template <int METRIC, bool SQ8, typename F>
 __device__ __forceinline__ float leader_request(const DeviceIndex& ix, Team& t, uint32_t m, F&& overlap) {
   if (t.lane == 0) t.ctl[0] = m;
   __syncthreads();
-  team_distances<METRIC>(ix, t, m);  // no-op for the leader unless it is the only warp
+  team_distances<METRIC, SQ8>(ix, t, m);  // the leader only takes its share of the first round's copies
   overlap();
   __syncthreads();
   return t.lane < m ? t.cand_d[t.lane] : INFINITY;
 }
-template <int METRIC>
+template <int METRIC, bool SQ8>
 __device__ __forceinline__ float leader_request(const DeviceIndex& ix, Team& t, uint32_t m) {
-  return leader_request<METRIC>(ix, t, m, [] {});
+  return leader_request<METRIC, SQ8>(ix, t, m, [] {});
 }
 
 // Exact visited set, called by all 32 lanes of the leader with one (distinct) id per active lane.
@@ -519,7 +530,7 @@ __device__ __forceinline__ uint32_t rank_merge(const float* src_d, const uint32_
   return min(n_old + mp, cap);
 }
 
-template <int METRIC, bool GLOBAL_VISITED, bool FILTERED>
+template <int METRIC, bool GLOBAL_VISITED, bool FILTERED, bool SQ8 = false>
 __global__ void __launch_bounds__(128, TURDB_MIN_CTAS) hnsw_search_kernel(const SearchArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const DeviceIndex& ix = a.ix;
@@ -556,6 +567,7 @@ __global__ void __launch_bounds__(128, TURDB_MIN_CTAS) hnsw_search_kernel(const 
   t.stage_u32 = smem_u32(t.stage);
   t.stride = a.lay.stride;
   t.vec_bytes = a.lay.vec_bytes;
+  t.rows = a.rows;
   t.n_groups = a.lay.n_groups;
   t.n_segs = a.lay.n_segs;
   t.seg_steps = a.lay.seg_steps;
@@ -599,7 +611,7 @@ __global__ void __launch_bounds__(128, TURDB_MIN_CTAS) hnsw_search_kernel(const 
         __syncthreads();
         const uint32_t m = t.ctl[0];
         if (m == kDone) break;
-        team_distances<METRIC>(ix, t, m);
+        team_distances<METRIC, SQ8>(ix, t, m);
         __syncthreads();
       }
       if (t.dbg && warp == 1 && lane == 0) {  // diagnostics: the first helper's share of the data path
@@ -624,7 +636,7 @@ __global__ void __launch_bounds__(128, TURDB_MIN_CTAS) hnsw_search_kernel(const 
       // entry distance (mod.rs:1129)
       uint32_t cur = ix.entry;
       if (lane == 0) cand_ids[0] = cur;
-      float cur_d = __shfl_sync(kFullMask, leader_request<METRIC>(ix, t, 1), 0);
+      float cur_d = __shfl_sync(kFullMask, leader_request<METRIC, SQ8>(ix, t, 1), 0);
       n_dist = 1;
       n_dist_upper = 1;
 
@@ -640,7 +652,7 @@ __global__ void __launch_bounds__(128, TURDB_MIN_CTAS) hnsw_search_kernel(const 
           const uint32_t m = __popc(__ballot_sync(kFullMask, nid != kInvalid));
           if (m == 0) break;
           if (lane < m) cand_ids[lane] = nid;
-          const float d = leader_request<METRIC>(ix, t, m);
+          const float d = leader_request<METRIC, SQ8>(ix, t, m);
           n_dist += m;
           n_dist_upper += m;
           // arg-min, strict `<`, first stored neighbour wins ties (search.rs:272-277)
@@ -740,7 +752,7 @@ __global__ void __launch_bounds__(128, TURDB_MIN_CTAS) hnsw_search_kernel(const 
           if (m == 0) continue;
           n_visited += m;
           if (isnew) cand_ids[__popc(newmask & ((1u << lane) - 1))] = nid;
-          const float d = leader_request<METRIC>(ix, t, m);
+          const float d = leader_request<METRIC, SQ8>(ix, t, m);
           const uint32_t cid = lane < m ? cand_ids[lane] : kInvalid;
           n_dist += m;
           // results: visible && (d < worst || |R| < ef), search.rs:391-395 (batch form)
@@ -874,7 +886,7 @@ __global__ void __launch_bounds__(128, TURDB_MIN_CTAS) hnsw_search_kernel(const 
         }
         n_visited += m;
         const long long h2 = t.dbg ? clock64() : 0;
-        const float d = leader_request<METRIC>(ix, t, m, [&] {
+        const float d = leader_request<METRIC, SQ8>(ix, t, m, [&] {
           // hop h+1 prepared under hop h's gather (leader only; cand_ids belongs to the helpers meanwhile)
           if (row_node == kInvalid) return;
           if (!GLOBAL_VISITED && n_visited + kL0 > hash_limit) return;  // the real hop reports the overflow

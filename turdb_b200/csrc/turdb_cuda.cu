@@ -64,6 +64,9 @@ struct turdb_cuda_index {
   uint32_t* d_up_adj = nullptr;
   uint64_t* d_row_ids = nullptr;
   uint8_t* d_levels = nullptr;
+  uint8_t* d_arena_sq8 = nullptr;          // SQ8 rows: dim codes | pad | min | scale, sq8_row_bytes apart (enable_sq8)
+  float* d_norm2_sq8 = nullptr;            // dot(decode(x), decode(x)) per row, AVX2 lane order
+  uint32_t sq8_row_bytes = 0;
   __nv_bfloat16* d_arena_bf16 = nullptr;   // exact path operand (raw rows: L2, IP), built lazily
   __nv_bfloat16* d_arena_bf16n = nullptr;  // exact path operand (rows scaled by 1/|x|: cosine), built lazily
   cudaMemPool_t pool = nullptr;            // per-index stream-ordered scratch pool (never trimmed)
@@ -123,6 +126,48 @@ __global__ void norm2_kernel(const float* arena, uint32_t dim, uint32_t ds, uint
   if (quad < n && (threadIdx.x & 3) == 0) out[quad] = r;
 }
 
+// SQ8Vector::from_f32 (src/hnsw/quantization.rs:68-95), one warp per row: min / max over the row, scale =
+// range / 255 (1.0 when the row is constant), code = round((v - min) / scale) clamped to 0..255 (`round` = half
+// away from zero, like f32::round).  Row layout: dim codes | pad to 4 | min f32 | scale f32, row_bytes apart.
+__global__ void sq8_encode_kernel(const float* arena, uint32_t dim, uint32_t ds, uint64_t n, uint8_t* out, uint32_t row_bytes) {
+  const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (r >= n) return;
+  const float* v = arena + r * ds;
+  float mn = INFINITY, mx = -INFINITY;
+  for (uint32_t i = lane; i < dim; i += 32) {
+    mn = fminf(mn, v[i]);
+    mx = fmaxf(mx, v[i]);
+  }
+  for (uint32_t off = 16; off >= 1; off >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(kFullMask, mn, off));
+    mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, off));
+  }
+  const float range = __fsub_rn(mx, mn);
+  const float scale = range > 0.f ? __fdiv_rn(range, 255.0f) : 1.0f;
+  uint8_t* row = out + r * row_bytes;
+  for (uint32_t i = lane; i < dim; i += 32) {
+    float c = 0.f;
+    if (range != 0.f) c = fminf(fmaxf(roundf(__fdiv_rn(__fsub_rn(v[i], mn), scale)), 0.f), 255.f);
+    row[i] = (uint8_t)c;
+  }
+  const uint32_t tail = (dim + 3) & ~3u;
+  for (uint32_t i = dim + lane; i < tail; i += 32) row[i] = 0;
+  if (lane == 0) {
+    float* ms = reinterpret_cast<float*>(row + tail);
+    ms[0] = mn;
+    ms[1] = scale;
+  }
+  for (uint32_t i = tail + 8 + lane; i < row_bytes; i += 32) row[i] = 0;
+}
+
+__global__ void sq8_norm2_kernel(const uint8_t* rows, uint32_t dim, uint32_t row_bytes, uint64_t n, float* out) {
+  uint64_t quad = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  uint64_t row = quad < n ? quad : n - 1;  // keep the quad shuffles converged
+  float r = quad_sq8<2>(nullptr, rows + row * row_bytes, dim, threadIdx.x & 3);
+  if (quad < n && (threadIdx.x & 3) == 0) out[quad] = r;
+}
+
 extern "C" {
 
 uint32_t turdb_cuda_abi_version(void) { return TURDB_CUDA_ABI_VERSION; }
@@ -152,6 +197,8 @@ int32_t turdb_cuda_index_destroy(turdb_cuda_index* idx) {
     cudaFree(idx->d_up_adj);
     cudaFree(idx->d_row_ids);
     cudaFree(idx->d_levels);
+    cudaFree(idx->d_arena_sq8);
+    cudaFree(idx->d_norm2_sq8);
     cudaFree(idx->d_arena_bf16);
     cudaFree(idx->d_arena_bf16n);
     for (cudaEvent_t ev : idx->prof_events) cudaEventDestroy(ev);
@@ -295,6 +342,32 @@ int32_t turdb_cuda_index_create(const turdb_cuda_graph* g, int32_t device, turdb
   return TURDB_OK;
 }
 
+int32_t turdb_cuda_index_enable_sq8(turdb_cuda_index* idx, uint8_t* out_rows, uint64_t out_capacity, uint32_t* out_row_bytes) {
+  if (!idx) return fail(TURDB_ERR_INVALID_ARGUMENT, "idx is null");
+  DeviceGuard guard(idx->device);
+  if (!guard.ok) return fail(TURDB_ERR_CUDA, "cudaSetDevice(%d) failed", idx->device);
+  std::lock_guard<std::mutex> lk(idx->mu);
+  const uint64_t n = idx->ix.n;
+  const uint32_t dim = idx->ix.dim;
+  const uint32_t row_bytes = (((dim + 3) & ~3u) + 8 + 15) & ~15u;
+  if (!idx->d_arena_sq8 && n) {
+    CUDA_TRY(cudaMalloc(&idx->d_arena_sq8, n * row_bytes));
+    CUDA_TRY(cudaMalloc(&idx->d_norm2_sq8, n * 4));
+    sq8_encode_kernel<<<(unsigned)((n * 32 + 255) / 256), 256>>>(idx->d_arena, dim, idx->ix.ds, n, idx->d_arena_sq8, row_bytes);
+    sq8_norm2_kernel<<<(unsigned)((n * 4 + 255) / 256), 256>>>(idx->d_arena_sq8, dim, row_bytes, n, idx->d_norm2_sq8);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    idx->device_bytes += n * row_bytes + n * 4;
+  }
+  idx->sq8_row_bytes = row_bytes;
+  if (out_row_bytes) *out_row_bytes = row_bytes;
+  if (out_rows) {
+    if (out_capacity < n * row_bytes) return fail(TURDB_ERR_INVALID_ARGUMENT, "out_rows holds %llu bytes, need %llu", (unsigned long long)out_capacity, (unsigned long long)(n * row_bytes));
+    if (n) CUDA_TRY(cudaMemcpy(out_rows, idx->d_arena_sq8, n * row_bytes, cudaMemcpyDeviceToHost));
+  }
+  return TURDB_OK;
+}
+
 int32_t turdb_cuda_index_info(const turdb_cuda_index* idx, uint64_t* n, uint32_t* dim, uint32_t* max_level,
                               uint32_t* entry, uint64_t* device_bytes) {
   if (!idx) return fail(TURDB_ERR_INVALID_ARGUMENT, "idx is null");
@@ -380,14 +453,15 @@ int32_t turdb_cuda_index_profile_read(turdb_cuda_index* idx, float* main_ms, flo
 // traversal launch
 // ------------------------------------------------------------------------------------------
 static TeamLayout make_layout(uint32_t dim, uint32_t ds, uint32_t ef, uint32_t hash_bits, uint32_t n_slots, uint32_t n_segs,
-                              bool global_visited, uint64_t n_nodes, bool filtered = false) {
+                              bool global_visited, uint64_t n_nodes, bool filtered = false, uint32_t sq8_row_bytes = 0) {
   TeamLayout L{};
-  L.vec_bytes = ds * 4;
+  L.vec_bytes = sq8_row_bytes ? sq8_row_bytes : ds * 4;
   const uint32_t steps = dim >> 3;
+  if (sq8_row_bytes) n_segs = 1;  // code rows are never split
   n_segs = std::max(1u, std::min(n_segs, std::max(1u, steps)));
   L.seg_steps = steps ? (steps + n_segs - 1) / n_segs : 0;
   L.n_segs = L.seg_steps ? (steps + L.seg_steps - 1) / L.seg_steps : 1;
-  const uint32_t slot_words = L.seg_steps * 8 + (ds - steps * 8);  // one piece + the < 8-element tail
+  const uint32_t slot_words = sq8_row_bytes ? sq8_row_bytes / 4 : L.seg_steps * 8 + (ds - steps * 8);  // one piece + the < 8-element tail
   const uint32_t pad_words = (8 + 32 - (slot_words & 31)) & 31;
   L.stride = (slot_words + pad_words) * 4;
   L.hash_bits = hash_bits;
@@ -409,10 +483,10 @@ static TeamLayout make_layout(uint32_t dim, uint32_t ds, uint32_t ef, uint32_t h
   return L;
 }
 
-template <int METRIC, bool GV, bool FILT>
+template <int METRIC, bool GV, bool FILT, bool SQ8 = false>
 static cudaError_t launch_search(const SearchArgs& a, uint32_t warps, int num_sms, uint32_t max_ctas,
                                  cudaStream_t stream, uint32_t* resident_warps) {
-  auto kern = hnsw_search_kernel<METRIC, GV, FILT>;
+  auto kern = hnsw_search_kernel<METRIC, GV, FILT, SQ8>;
   const size_t smem = (size_t)a.lay.team_bytes;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -439,7 +513,14 @@ static cudaError_t launch_metric2(int metric, const SearchArgs& a, uint32_t warp
 }
 template <bool GV>
 static cudaError_t launch_metric(int metric, const SearchArgs& a, uint32_t warps, int num_sms, uint32_t max_ctas,
-                                 cudaStream_t stream, uint32_t* rw) {
+                                 cudaStream_t stream, uint32_t* rw, bool sq8 = false) {
+  if (sq8) {  // code-arena kernels: unfiltered search only
+    switch (metric) {
+      case kCosine: return launch_search<kCosine, GV, false, true>(a, warps, num_sms, max_ctas, stream, rw);
+      case kIP: return launch_search<kIP, GV, false, true>(a, warps, num_sms, max_ctas, stream, rw);
+      default: return launch_search<kL2, GV, false, true>(a, warps, num_sms, max_ctas, stream, rw);
+    }
+  }
   return a.visible ? launch_metric2<GV, true>(metric, a, warps, num_sms, max_ctas, stream, rw)
                    : launch_metric2<GV, false>(metric, a, warps, num_sms, max_ctas, stream, rw);
 }
@@ -479,13 +560,14 @@ __global__ void fill_empty_results_kernel(uint64_t* rows, uint32_t* nodes, float
   if (stats && i < (uint64_t)nq * 4) stats[i] = 0;
 }
 
-extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const float* d_queries, uint32_t query_dim,
-                                                  uint32_t nq, uint32_t k, uint32_t ef, uint8_t metric,
-                                                  const uint64_t* d_visible, uint64_t* d_out_row_ids,
-                                                  uint32_t* d_out_node_ids, float* d_out_dist,
-                                                  uint32_t* d_out_counts, turdb_cuda_search_stats* d_out_stats,
-                                                  void* stream_) {
+static int32_t search_batch_device_impl(turdb_cuda_index* idx, const float* d_queries, uint32_t query_dim, uint32_t nq,
+                                        uint32_t k, uint32_t ef, uint8_t metric, const uint64_t* d_visible,
+                                        uint64_t* d_out_row_ids, uint32_t* d_out_node_ids, float* d_out_dist,
+                                        uint32_t* d_out_counts, turdb_cuda_search_stats* d_out_stats, void* stream_,
+                                        bool sq8) {
   if (!idx) return fail(TURDB_ERR_INVALID_ARGUMENT, "idx is null");
+  if (sq8 && d_visible) return fail(TURDB_ERR_UNSUPPORTED, "search_filtered over the SQ8 arena is not built");
+  if (sq8 && idx->ix.n && !idx->d_arena_sq8) return fail(TURDB_ERR_INVALID_ARGUMENT, "call turdb_cuda_index_enable_sq8 first");
   if (query_dim != idx->ix.dim)
     return fail(TURDB_ERR_DIMENSION_MISMATCH, "query dimension %u does not match index dimension %u", query_dim, idx->ix.dim);
   if (metric > 2) return fail(TURDB_ERR_INVALID_ARGUMENT, "metric %u unknown", metric);
@@ -532,7 +614,7 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
     for (uint32_t cg = tg ? tg : 1; cg <= (tg ? tg : 8); ++cg) {
       uint32_t best_occ = 0;
       for (uint32_t cs = ts ? ts : 8; cs <= (ts ? ts : 32); cs += 8) {
-        TeamLayout L = make_layout(dim, ds, ef, hash_bits, cs, cg, false, nn, filt);
+        TeamLayout L = make_layout(dim, ds, ef, hash_bits, cs, cg, false, nn, filt, sq8 ? idx->sq8_row_bytes : 0);
         if (L.n_segs != cg || L.team_bytes > budget) continue;
         if (cg > 1 && L.seg_steps * 32 < 512) continue;
         const uint32_t occ = std::min(8u, sm_bytes / (L.team_bytes + 1024));
@@ -549,7 +631,8 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
     slots = bs;
     segs = bg;
   }
-  TeamLayout lay = make_layout(dim, ds, ef, hash_bits, slots, segs, false, nn, filt);
+  const uint32_t rb8 = sq8 ? idx->sq8_row_bytes : 0;
+  TeamLayout lay = make_layout(dim, ds, ef, hash_bits, slots, segs, false, nn, filt, rb8);
   // Team size: warp 0 leads (control flow + speculative preparation of the next hop), the others gather and
   // reduce; every warp takes a share of a hop's bulk-copy issue.  Resident queries per SM come first (the
   // kernel is latency-bound: 1M x 128, 8 queries of 2 warps beat 7 of 3 and 5 of 4, measured); among equal
@@ -560,11 +643,11 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
     warps = 4;
   }
   while (lay.team_bytes > budget && lay.n_segs < 16 && lay.seg_steps > 8)
-    lay = make_layout(dim, ds, ef, hash_bits, lay.n_groups * 8, lay.n_segs + 1, false, nn, filt);
+    lay = make_layout(dim, ds, ef, hash_bits, lay.n_groups * 8, lay.n_segs + 1, false, nn, filt, rb8);
   while (lay.team_bytes > budget && lay.n_groups > 1)
-    lay = make_layout(dim, ds, ef, hash_bits, lay.n_groups * 8 - 8, lay.n_segs, false, nn, filt);
+    lay = make_layout(dim, ds, ef, hash_bits, lay.n_groups * 8 - 8, lay.n_segs, false, nn, filt, rb8);
   while (lay.team_bytes > budget && hash_bits > 8)
-    lay = make_layout(dim, ds, ef, --hash_bits, lay.n_groups * 8, lay.n_segs, false, nn, filt);
+    lay = make_layout(dim, ds, ef, --hash_bits, lay.n_groups * 8, lay.n_segs, false, nn, filt, rb8);
   if (lay.team_bytes > budget)
     return fail(TURDB_ERR_UNSUPPORTED, "dim %u / ef %u need %u B of shared memory per query (> %u)", idx->ix.dim, ef, lay.team_bytes, budget);
 
@@ -591,6 +674,9 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
   a.vis_words = 0;
   a.dbg = idx->d_dbg;
   a.visible = d_visible;
+  a.rows = sq8 ? idx->d_arena_sq8 : reinterpret_cast<const uint8_t*>(idx->d_arena);
+  a.row_bytes = lay.vec_bytes;
+  if (sq8) a.ix.norm2 = idx->d_norm2_sq8;  // cosine's norm_b chain runs over the decoded row
   a.f_ovf = nullptr;
   a.f_ocap = 0;
   uint2* d_fovf = nullptr;
@@ -622,7 +708,7 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
     }
   }
   if (pev) cudaEventRecord(pev[0], stream);
-  cudaError_t e = launch_metric<false>(metric, a, warps, idx->num_sms, filt ? std::min<uint32_t>(nq, idx->num_sms * 8) : nq, stream, nullptr);
+  cudaError_t e = launch_metric<false>(metric, a, warps, idx->num_sms, filt ? std::min<uint32_t>(nq, idx->num_sms * 8) : nq, stream, nullptr, sq8);
   if (pev) cudaEventRecord(pev[1], stream);
   if (e != cudaSuccess) {
     cudaFreeAsync(d_scratch, stream);
@@ -632,7 +718,7 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
   // exact fallback for queries whose shared visited table filled: same kernel, one bit per node in
   // global memory.  Always enqueued (no host sync); exits immediately when the list is empty.
   {
-    TeamLayout glay = make_layout(dim, ds, ef, 8, lay.n_groups * 8, lay.n_segs, true, nn, filt);
+    TeamLayout glay = make_layout(dim, ds, ef, 8, lay.n_groups * 8, lay.n_segs, true, nn, filt, rb8);
     SearchArgs b = a;
     b.lay = glay;
     b.work_counter = d_scratch + 2;
@@ -642,7 +728,7 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
     e = cudaMallocFromPoolAsync(&d_gv, (size_t)fb_ctas * b.vis_words * 4, idx->pool, stream);
     if (e == cudaSuccess) {
       b.global_visited = d_gv;
-      e = launch_metric<true>(metric, b, warps, idx->num_sms, fb_ctas, stream, nullptr);
+      e = launch_metric<true>(metric, b, warps, idx->num_sms, fb_ctas, stream, nullptr, sq8);
       if (pev) cudaEventRecord(pev[2], stream);
       cudaFreeAsync(d_gv, stream);
     }
@@ -654,6 +740,25 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
   if (d_fovf) cudaFreeAsync(d_fovf, stream);
   CUDA_TRY(cudaFreeAsync(d_scratch, stream));
   return TURDB_OK;
+}
+
+extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const float* d_queries, uint32_t query_dim,
+                                                  uint32_t nq, uint32_t k, uint32_t ef, uint8_t metric,
+                                                  const uint64_t* d_visible, uint64_t* d_out_row_ids,
+                                                  uint32_t* d_out_node_ids, float* d_out_dist,
+                                                  uint32_t* d_out_counts, turdb_cuda_search_stats* d_out_stats,
+                                                  void* stream_) {
+  return search_batch_device_impl(idx, d_queries, query_dim, nq, k, ef, metric, d_visible, d_out_row_ids, d_out_node_ids,
+                                  d_out_dist, d_out_counts, d_out_stats, stream_, false);
+}
+
+extern "C" int32_t turdb_cuda_search_batch_sq8_device(turdb_cuda_index* idx, const float* d_queries, uint32_t query_dim,
+                                                      uint32_t nq, uint32_t k, uint32_t ef, uint8_t metric,
+                                                      uint64_t* d_out_row_ids, uint32_t* d_out_node_ids, float* d_out_dist,
+                                                      uint32_t* d_out_counts, turdb_cuda_search_stats* d_out_stats,
+                                                      void* stream_) {
+  return search_batch_device_impl(idx, d_queries, query_dim, nq, k, ef, metric, nullptr, d_out_row_ids, d_out_node_ids,
+                                  d_out_dist, d_out_counts, d_out_stats, stream_, true);
 }
 
 extern "C" int32_t turdb_cuda_search_batch(turdb_cuda_index* idx, const float* queries, uint32_t query_dim, uint32_t nq,

@@ -226,6 +226,27 @@ class CudaHnswIndex:
                                                           d_rows, d_nodes or None, d_dist, d_counts, d_stats or None,
                                                           stream or None))
 
+    # ---- SQ8 arena (src/hnsw/quantization.rs) ----
+    def enable_sq8(self, return_rows: bool = False):
+        """Encode the arena as SQ8 on the device.  return_rows -> (codes u8 [n, dim], min f32 [n], scale f32 [n])."""
+        L = _lib.load()
+        rb = C.c_uint32(0)
+        _check(L.turdb_cuda_index_enable_sq8(self._h, None, 0, C.byref(rb)))
+        if not return_rows:
+            return rb.value
+        raw = np.zeros((self.n, rb.value), np.uint8)
+        _check(L.turdb_cuda_index_enable_sq8(self._h, _ptr(raw, C.c_uint8), raw.size, C.byref(rb)))
+        tail = (self.dim + 3) & ~3
+        ms = raw[:, tail:tail + 8].copy().view(np.float32)
+        return raw[:, :self.dim].copy(), ms[:, 0].copy(), ms[:, 1].copy()
+
+    def search_batch_sq8_device(self, d_queries, nq: int, k: int, ef: int, metric, d_rows, d_dist, d_counts, d_nodes=0,
+                                d_stats=0, stream=0):
+        m = int(self._metric if metric is None else metric)
+        _check(_lib.load().turdb_cuda_search_batch_sq8_device(self._h, d_queries, self.dim, nq, k, ef, m, d_rows,
+                                                              d_nodes or None, d_dist, d_counts, d_stats or None,
+                                                              stream or None))
+
     def bruteforce_topk(self, queries, k: int, metric: DistanceFunction | None = None, rerank_factor: int = 4):
         """Exact path: ORDER BY <distance> LIMIT k over the whole arena (src/sql/executor.rs:2239-2392)."""
         q = np.ascontiguousarray(queries, dtype=np.float32)
