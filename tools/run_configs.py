@@ -39,6 +39,9 @@ CONFIGS = [
     dict(name="config5_full_shard_12.5Mx128_L2_clustered_latent_centres (one of the 8 sub-indexes of 100M)", n=12_500_000, dim=128,
          metric=0, gen="clustered", kw=dict(centre_latent=16, corpus_n=12_500_000), m=16, ef=64, k=10, nq=10_000,
          builder="knn-heuristic", sql=True, heavy=True, ef_sweep=[64, 128, 256, 512]),
+    dict(name="config5_full_shard_12.5Mx128_L2_clustered_sigma0.3 (one of the 8 sub-indexes of 100M; clusters as wide as their spacing)",
+         n=12_500_000, dim=128, metric=0, gen="clustered", kw=dict(centre_latent=16, corpus_n=12_500_000, sigma=0.3), m=16, ef=128,
+         k=10, nq=10_000, builder="knn-heuristic", sql=True, heavy=True, ef_sweep=[64, 128, 256, 512]),
     dict(name="config5_128_L2_clustered_iid_centres (2M rows per GPU; i.i.d. centres, recall ceiling documented)", n=2_000_000,
          dim=128, metric=0, gen="clustered", kw=dict(corpus_n=2_000_000), m=16, ef=64, k=10, nq=10_000, builder="knn-heuristic"),
 ]

@@ -191,14 +191,35 @@ __device__ __forceinline__ float quad_dot(const float* a, const float* b, uint32
 // A quad walks the codes in the same AVX2 lane order as the FP32 rows; every element is decoded exactly as
 // SQ8Vector::decode does (min + (q as f32) * scale, two roundings, quantization.rs:108-113) before it enters the
 // chain, so the value equals the FP32 functions applied to the decoded vector bit for bit.
-__device__ __forceinline__ uint64_t sq8_pair(const uint8_t* row, uint32_t step, uint32_t p, float mn, float sc) {
-  const uint2 w = *reinterpret_cast<const uint2*>(row + 8 * step);  // the 8 codes of this AVX step (quad broadcast)
-  const uint32_t word = (p & 2) ? w.y : w.x, sh = (p & 1) * 16;
-  const float b0 = __fadd_rn(mn, __fmul_rn((float)((word >> sh) & 0xFFu), sc));
-  const float b1 = __fadd_rn(mn, __fmul_rn((float)((word >> (sh + 8)) & 0xFFu), sc));
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t pack2(float x, float y) {
   uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(b0), "f"(b1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
   return r;
+}
+// Two codes -> two decoded floats.  `q as f32` without the conversion pipe: 0x4B000000 | q is the float 2^23 + q,
+// and subtracting 2^23 is exact; then the reference's two roundings, q * scale and min + (.), as packed FP32x2.
+__device__ __forceinline__ uint64_t sq8_pair(const uint8_t* row, uint32_t step, uint32_t p, uint64_t mn2, uint64_t sc2) {
+  const uint2 w = *reinterpret_cast<const uint2*>(row + 8 * step);  // the 8 codes of this AVX step (quad broadcast)
+  const uint32_t word = (p & 2) ? w.y : w.x;
+  // byte_perm over {word (bytes 0-3), 0x4B000000 (bytes 4-7)}: result = 4B 00 00 cc
+  const uint32_t sel0 = 0x7440u | (2 * (p & 1)), sel1 = sel0 | 1u;
+  const float f0 = __uint_as_float(__byte_perm(word, 0x4B000000u, sel0));
+  const float f1 = __uint_as_float(__byte_perm(word, 0x4B000000u, sel1));
+  // ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (seen in SASS; one rounding instead of the
+  // reference's two), so the products are formed by scalar FMULs, which it leaves alone
+  const float2 q = unpack2(add2(pack2(f0, f1), pack2(-8388608.0f, -8388608.0f)));
+  const float2 sc = unpack2(sc2);
+  return add2(mn2, pack2(__fmul_rn(q.x, sc.x), __fmul_rn(q.y, sc.y)));
 }
 // MODE 0: squared L2 of (a, decode(row)); 1: dot(a, decode(row)); 2: dot(decode(row), decode(row)) (a unused)
 template <int MODE>
@@ -206,10 +227,12 @@ __device__ __forceinline__ float quad_sq8(const float* a, const uint8_t* row, ui
   const uint32_t steps = dim >> 3, tail0 = steps << 3;
   const float* ms = reinterpret_cast<const float*>(row + ((dim + 3) & ~3u));
   const float mn = ms[0], sc = ms[1];
+  const uint64_t mn2 = pack2(mn, mn), sc2 = pack2(sc, sc);
   const uint64_t* av = reinterpret_cast<const uint64_t*>(a) + p;
   uint64_t acc = 0ull;
+#pragma unroll 4
   for (uint32_t t = 0; t < steps; ++t) {
-    const uint64_t b = sq8_pair(row, t, p, mn, sc);
+    const uint64_t b = sq8_pair(row, t, p, mn2, sc2);
     if (MODE == 0) {
       const uint64_t d = sub2(av[4 * t], b);
       acc = fma2(d, d, acc);

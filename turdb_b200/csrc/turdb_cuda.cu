@@ -603,6 +603,14 @@ static int32_t search_batch_device_impl(turdb_cuda_index* idx, const float* d_qu
   const uint64_t nn = idx->ix.n;
   const bool filt = d_visible != nullptr;
   uint32_t slots = ts, segs = tg;
+  if (sq8) {
+    // code rows are short (dim + 8 B) but cost ~10 instructions per element pair to decode with the reference's
+    // roundings: the reduce phase, not the gather, bounds a hop -> one gather round (32 slots) and the full team
+    // (measured at 1M x 384: 4 warps x 32 slots 7.97 ms, 2 x 16 8.92 ms)
+    if (!slots) slots = 32;
+    segs = 1;
+    if (!warps) warps = 4;
+  }
   if (!slots || !segs) {
     // Measured at 1M x 384 (tools/sweep.py): whole vectors (1 piece) through 16 slots with 5 resident queries
     // per SM beat every split; pieces only pay when a whole vector leaves fewer than 4 queries resident
