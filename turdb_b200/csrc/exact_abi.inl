@@ -148,7 +148,7 @@ extern "C" int32_t turdb_cuda_bruteforce_topk_device(turdb_cuda_index* idx, cons
   if (!make_bf16_map(&map_q, d_qb, nq, kp) || !make_bf16_map(&map_x, d_xb, n, kp))
     return bail(fail(TURDB_ERR_CUDA, "cuTensorMapEncodeTiled failed"));
 
-  const size_t fixed_smem = (size_t)k_chunks * kChunkBytes + 4 * kTileN * 4 + 2 * kRing * kTileM * 4 + 24 * 8 + 16;
+  const size_t fixed_smem = (size_t)k_chunks * kChunkBytes + 4 * kTileN * 4 + 4 * kRing * kTileM * 4 + 24 * 8 + 16;
   const uint32_t n_stages = (uint32_t)std::min<size_t>(kMaxStages, ((size_t)idx->max_smem_optin - fixed_smem) / kChunkBytes);
   if (n_stages < 2) return bail(fail(TURDB_ERR_UNSUPPORTED, "not enough shared memory for the exact path at dim %u", dim));
   const size_t gemm_smem = fixed_smem + (size_t)n_stages * kChunkBytes;

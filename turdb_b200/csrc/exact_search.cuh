@@ -149,6 +149,19 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32x32b_x32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // pass (1): GEMM + threshold filter
 // ------------------------------------------------------------------------------------------------
@@ -187,9 +200,9 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
   uint8_t* sB = sA + (size_t)a.k_chunks * kChunkBytes;
   const uint32_t kStages = a.n_stages;
   float* s_bias = reinterpret_cast<float*>(sB + (size_t)kStages * kChunkBytes);  // [2][128] (+ pad to 2 KB)
-  float* ring_key = s_bias + 4 * kTileN;                                          // [kRing][128] pending candidates
-  uint32_t* ring_col = reinterpret_cast<uint32_t*>(ring_key + kRing * kTileM);    // [kRing][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_col + kRing * kTileM);
+  float* ring_key = s_bias + 4 * kTileN;                                              // [2][kRing][128] pending candidates
+  uint32_t* ring_col = reinterpret_cast<uint32_t*>(ring_key + 2 * kRing * kTileM);    // [2][kRing][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_col + 2 * kRing * kTileM);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
   const uint32_t bar_a_full = smem_u32(bars + 0), bar_a_empty = smem_u32(bars + 1);
   const uint32_t bar_b_full = smem_u32(bars + 2), bar_b_empty = smem_u32(bars + 2 + kMaxStages);
@@ -298,10 +311,30 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
     }
   } else {
     // ===== epilogue: 4 warps, thread = one query row, 128 scores per tile =====
+    // ncu (round 1, source counters): a third of all samples sat in the MMA issuer's wait for a drained accumulator
+    // and 17 % in the candidate flush (an atomicAdd round trip with the accumulator still held).  Hence:
+    //  * the whole 128-column row is read into registers at once (4 x tcgen05.ld, one wait) and the accumulator is
+    //    handed back to the tensor pipe BEFORE any key is looked at;
+    //  * a flush is split: the atomicAdd that reserves the slots is issued when a ring half fills or the item ends,
+    //    its result is consumed one flush later (double-buffered ring), so nobody waits for the round trip.
     const uint32_t quarter = warp & 3;               // TMEM lane quarter this warp may read
     const uint32_t row = quarter * 32 + lane;
     const uint32_t et = threadIdx.x - 64;            // 0..127 among epilogue threads
     uint32_t acc = 0, acc_phase = 0;
+    uint32_t half = 0, n_pend = 0;                   // ring half being filled, entries in it
+    uint32_t p_pos = 0, p_n = 0, p_q = 0;            // reserved-but-unwritten flush of the other half
+    auto flush_end = [&]() {                         // write the other half out (its reservation has long arrived)
+      const uint32_t base = (half ^ 1) * kRing;
+      for (uint32_t i = 0; i < p_n; ++i) {
+        if (p_pos + i < a.cap) {
+          a.cand_id[(size_t)p_q * a.cap + p_pos + i] = ring_col[(base + i) * kTileM + et];
+          a.cand_key[(size_t)p_q * a.cap + p_pos + i] = ring_key[(base + i) * kTileM + et];
+        } else {
+          *a.overflow_flag = 1u;
+        }
+      }
+      p_n = 0;
+    };
     for (uint32_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
       const uint32_t qb = item % a.n_qblocks;
       const uint32_t t0 = a.tile_lo + (item / a.n_qblocks) * a.tiles_per_item;
@@ -309,19 +342,12 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
       const uint32_t q = qb * kTileM + row;
       const bool q_ok = q < a.nq;
       const float tau = q_ok ? a.thresh[q] : INFINITY;
-      uint32_t n_pend = 0;
-      // passing keys are parked in a per-thread shared-memory ring; one atomicAdd per flush reserves their slots,
-      // so the L2 round trip of the counter is paid once per ~item instead of once per candidate
-      auto flush = [&]() {
-        const uint32_t pos = atomicAdd(a.cand_cnt + q, n_pend);
-        for (uint32_t i = 0; i < n_pend; ++i) {
-          if (pos + i < a.cap) {
-            a.cand_id[(size_t)q * a.cap + pos + i] = ring_col[i * kTileM + et];
-            a.cand_key[(size_t)q * a.cap + pos + i] = ring_key[i * kTileM + et];
-          } else {
-            *a.overflow_flag = 1u;
-          }
-        }
+      auto flush_begin = [&]() {                     // reserve slots for the half just filled, switch halves
+        flush_end();
+        p_n = n_pend;
+        p_q = q;
+        p_pos = atomicAdd(a.cand_cnt + q, n_pend);
+        half ^= 1;
         n_pend = 0;
       };
       for (uint32_t t = t0; t < t1; ++t) {
@@ -335,57 +361,88 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
         long long c7 = (a.dbg && et == 0) ? clock64() : 0;
         tc_fence_after();
         const uint32_t n_valid = min(kTileN, a.n_vec - t * kTileN);  // columns past the corpus are zero rows
-#pragma unroll 1
-        for (uint32_t cb = 0; cb < kTileN / 32; ++cb) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + ((quarter * 32) << 16) + acc * kTileN + cb * 32, v);
+        uint32_t v[4][32];
+        const uint32_t tcol = tmem_base + ((quarter * 32) << 16) + acc * kTileN;
+#pragma unroll
+        for (uint32_t cb = 0; cb < 4; ++cb) tmem_ld_32x32b_x32_nowait(tcol + cb * 32, v[cb]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_t_empty + 8 * acc);  // the tensor pipe may refill this accumulator now
+        const uint32_t bias_buf = acc * kTileN;
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+#pragma unroll
+        for (uint32_t cb = 0; cb < 4; ++cb) {
           if (BIAS) {
-            const float4* b4 = reinterpret_cast<const float4*>(s_bias + acc * kTileN + cb * 32);
+            const float4* b4 = reinterpret_cast<const float4*>(s_bias + bias_buf + cb * 32);
 #pragma unroll
             for (uint32_t j = 0; j < 32; j += 4) {
               const float4 b = b4[j >> 2];
-              v[j] = __float_as_uint(__uint_as_float(v[j]) + b.x);
-              v[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + b.y);
-              v[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) + b.z);
-              v[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + b.w);
+              v[cb][j] = __float_as_uint(__uint_as_float(v[cb][j]) + b.x);
+              v[cb][j + 1] = __float_as_uint(__uint_as_float(v[cb][j + 1]) + b.y);
+              v[cb][j + 2] = __float_as_uint(__uint_as_float(v[cb][j + 2]) + b.z);
+              v[cb][j + 3] = __float_as_uint(__uint_as_float(v[cb][j + 3]) + b.w);
             }
           }
           // a key that reaches the running threshold is rare once the first slices have been seen: one
           // max-tree over the 32 keys, then the per-key test only when something can pass
           float mx[16];
 #pragma unroll
-          for (uint32_t j = 0; j < 16; ++j) mx[j] = fmaxf(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+          for (uint32_t j = 0; j < 16; ++j) mx[j] = fmaxf(__uint_as_float(v[cb][2 * j]), __uint_as_float(v[cb][2 * j + 1]));
 #pragma unroll
           for (uint32_t w = 8; w >= 1; w >>= 1)
 #pragma unroll
             for (uint32_t j = 0; j < w; ++j) mx[j] = fmaxf(mx[j], mx[j + w]);
           if (mx[0] >= tau) {
+            // rare: count first, make room once, then predicated pushes — no call inside the unrolled loop, so
+            // the hot path (above) stays a few hundred instructions
             const uint32_t lim = n_valid > cb * 32 ? min(32u, n_valid - cb * 32) : 0u;
+            uint32_t cnt = 0;
 #pragma unroll
-            for (uint32_t j = 0; j < 32; ++j) {
-              const float key = __uint_as_float(v[j]);
-              if (key >= tau && j < lim) {
-                ring_key[n_pend * kTileM + et] = key;
-                ring_col[n_pend * kTileM + et] = t * kTileN + cb * 32 + j;
-                if (++n_pend == kRing) flush();
+            for (uint32_t j = 0; j < 32; ++j) cnt += (__uint_as_float(v[cb][j]) >= tau && j < lim) ? 1u : 0u;
+            if (cnt > kRing) {
+              // more keys than a ring half holds (the first slices, where everything passes): reserve directly
+              if (n_pend) flush_begin();
+              const uint32_t pos = atomicAdd(a.cand_cnt + q, cnt);
+              uint32_t o = pos;
+#pragma unroll
+              for (uint32_t j = 0; j < 32; ++j) {
+                const float key = __uint_as_float(v[cb][j]);
+                if (key >= tau && j < lim) {
+                  if (o < a.cap) {
+                    a.cand_id[(size_t)q * a.cap + o] = t * kTileN + cb * 32 + j;
+                    a.cand_key[(size_t)q * a.cap + o] = key;
+                  } else {
+                    *a.overflow_flag = 1u;
+                  }
+                  ++o;
+                }
+              }
+            } else if (cnt) {
+              if (n_pend + cnt > kRing) flush_begin();
+#pragma unroll
+              for (uint32_t j = 0; j < 32; ++j) {
+                const float key = __uint_as_float(v[cb][j]);
+                if (key >= tau && j < lim) {
+                  ring_key[(half * kRing + n_pend) * kTileM + et] = key;
+                  ring_col[(half * kRing + n_pend) * kTileM + et] = t * kTileN + cb * 32 + j;
+                  ++n_pend;
+                }
               }
             }
           }
         }
-        tc_fence_before();
-        __syncwarp();
         if (a.dbg && et == 0) {
           atomicAdd(a.dbg + 6, (unsigned long long)(c7 - c6));
           atomicAdd(a.dbg + 7, (unsigned long long)(clock64() - c7));
         }
-        if (lane == 0) mbar_arrive(bar_t_empty + 8 * acc);
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
-        }
       }
-      if (n_pend) flush();
+      if (n_pend) flush_begin();  // the ring belongs to query q: reserve now, write during the next item
     }
+    flush_end();
   }
 
   if (a.dbg && threadIdx.x == 0) atomicAdd(a.dbg + 8, (unsigned long long)clock64() - k_t0);
