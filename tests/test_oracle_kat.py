@@ -237,3 +237,22 @@ def test_filtered_search_semantics():
     a = g.search(q, 5, 32, visible=allvis)
     b = g.search(q, 5, 32)
     assert np.array_equal(a[1], b[1])     # every node visible: same results as search()
+
+
+def test_sq8_from_f32_hand_computed():
+    """SQ8Vector::from_f32 / decode (src/hnsw/quantization.rs:68-95, 108-113), values worked out by hand."""
+    v = np.array([[0.0, 0.5, 1.0, 0.25]], np.float32)
+    codes, mn, sc = ob.sq8_encode(v)
+    assert mn[0] == 0.0 and sc[0] == np.float32(1.0) / np.float32(255.0)
+    # in f32, fl(1/255) is a hair above 1/255, so 0.5 / scale = 127.49999 -> 127 (not the 127.5 -> 128 of exact
+    # arithmetic); 0.25 / scale = 63.749996 -> 64; 1.0 / scale = 255 exactly
+    assert codes[0].tolist() == [0, 127, 255, 64]
+    dec = ob.sq8_decode(codes, mn, sc)
+    assert dec[0, 0] == 0.0 and dec[0, 2] == np.float32(255.0) * sc[0] and abs(dec[0, 1] - 0.5) < 1.0 / 255
+    # constant vector: range 0 -> scale 1.0 and all codes 0 (quantization.rs:80-86)
+    codes, mn, sc = ob.sq8_encode(np.full((1, 5), 3.5, np.float32))
+    assert codes[0].tolist() == [0] * 5 and mn[0] == 3.5 and sc[0] == 1.0
+    # negative range and clamping stay inside 0..255
+    v = np.array([[-2.0, -1.0, 0.0, 2.0]], np.float32)
+    codes, mn, sc = ob.sq8_encode(v)
+    assert mn[0] == -2.0 and codes[0, 0] == 0 and codes[0, 3] == 255 and codes[0, 1] == 64 and codes[0, 2] == 127
