@@ -13,6 +13,7 @@ ap.add_argument("--sigmas", default="0.1,0.2,0.3")
 ap.add_argument("--knn", default="64")
 ap.add_argument("--efs", default="64,128,256")
 ap.add_argument("--ivf", type=int, default=1024)
+ap.add_argument("--variants", default="10:131072", help="ivf_probe:exact_prefix;... builder variants")
 ap.add_argument("--out", default="gpurun_out/cluster_probe.json")
 a = ap.parse_args()
 dev = torch.device("cuda:0"); stream = torch.cuda.current_stream().cuda_stream
@@ -21,9 +22,10 @@ res = []
 for sg in [float(v) for v in a.sigmas.split(",")]:
     x = ds.clustered(a.n, a.dim, seed=1, centre_latent=16, corpus_n=a.n, sigma=sg)
     q = ds.clustered(nq, a.dim, seed=2, centre_latent=16, corpus_n=a.n, sigma=sg)
-    for kk in [int(v) for v in a.knn.split(",")]:
+    for kk, var in [(int(v), w) for v in a.knn.split(",") for w in a.variants.split(";")]:
+        pr, px = [int(z) for z in var.split(":")]
         t = time.time()
-        arrays = build_graph(x, seed=42, knn_k=kk, ivf_cells=a.ivf)
+        arrays = build_graph(x, seed=42, knn_k=kk, ivf_cells=a.ivf, ivf_probe=pr, ivf_exact_prefix=px)
         torch.cuda.synchronize(); tb = time.time() - t
         idx = CudaHnswIndex.from_graph(arrays)
         dq = torch.from_numpy(q).to(dev)
@@ -45,7 +47,7 @@ for sg in [float(v) for v in a.sigmas.split(",")]:
             km, _ = idx.profile_read(3)
             nd = nodes.cpu().numpy()
             rec = float(np.mean([len(set(nd[i].tolist()) & set(gt[i].tolist())) / k for i in range(2000)]))
-            r = dict(sigma=sg, knn_k=kk, ef=ef, recall=rec, ms=float(km.mean()), n_dist=float(stats[:, 0].float().mean()), build_s=round(tb, 1))
+            r = dict(sigma=sg, knn_k=kk, ivf_probe=pr, exact_prefix=px, ef=ef, recall=rec, ms=float(km.mean()), n_dist=float(stats[:, 0].float().mean()), build_s=round(tb, 1))
             print(json.dumps(r), flush=True); res.append(r)
         idx.close(); del arrays
 json.dump(res, open(a.out, "w"), indent=1)

@@ -239,11 +239,13 @@ def _level_lists(xf, norms, ids, cap, knn_k, rev_cap, chunk_rows, chunk_h, ivf=N
 @torch.no_grad()
 def build_graph(vectors: np.ndarray, m: int = 16, seed: int = 1234, device: str | torch.device = "cuda:0",
                 knn_k: int = 64, row_ids: np.ndarray | None = None, chunk_rows: int = 4096,
-                l0_rev: int = MAX_L0, up_rev: int = 64, ivf_cells: int | None = None, ivf_probe: int = 10,
-                ivf_exact_prefix: int = 131072) -> dict:
+                l0_rev: int = MAX_L0, up_rev: int = 64, ivf_cells: int | None = None, ivf_probe: int = 16,
+                ivf_exact_prefix: int = 1 << 20) -> dict:
     """vectors [n, dim] f32 -> the flattened graph dict `CudaHnswIndex.from_graph` / the oracle take.
     ivf_cells: None = all-pairs candidate pass up to 3M rows, partitioned pass (~sqrt(n) cells) above; 0 = always
-    all-pairs; > 0 = that many cells."""
+    all-pairs; > 0 = that many cells.  ivf_exact_prefix: the first that many nodes take the exact predecessor pass —
+    they carry the long-range links; measured on 12.5M x 128 clustered (sigma 0.3): recall@10 at ef 128 is 0.78 with
+    a 131k prefix and 0.96 with a 1M prefix (tools/cluster_probe.py)."""
     vectors = np.ascontiguousarray(vectors, dtype=np.float32)
     n, dim = vectors.shape
     dev = torch.device(device)
@@ -286,3 +288,7 @@ def build_graph(vectors: np.ndarray, m: int = 16, seed: int = 1234, device: str 
             provenance="predecessor-knn-heuristic" if not ivf else f"predecessor-knn-heuristic(ivf {ivf[0]}x{ivf[1]})")
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+        if dev.type == "cuda":
+            # hand the builder's cached blocks back: the index is uploaded by libturdb_cuda's own cudaMalloc next
+            xf = norms = lv = None  # noqa: F841
+            torch.cuda.empty_cache()
