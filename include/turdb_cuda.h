@@ -215,6 +215,14 @@ int32_t turdb_cuda_sql_topk_batch_device(turdb_cuda_index* idx, const float* d_q
  * gathered_* are [n_shards][nq][k] device arrays (the NCCL all-gather output); ties order by
  * (distance, row_id).  Output [nq][k].
  */
+/* Single-process form of the same path: `shards` are sub-indexes (usually one per GPU; several on one device
+ * are allowed), `queries` one host batch replicated to all of them; per-shard lists are copied device to device
+ * into shard 0's gather buffer and merged there.  Results equal the multi-process (NCCL) path's. */
+int32_t turdb_cuda_shards_search_batch(turdb_cuda_index* const* shards, uint32_t n_shards,
+                                       const float* queries, uint32_t query_dim, uint32_t nq, uint32_t k,
+                                       uint32_t ef, uint8_t metric, uint64_t* out_row_ids,
+                                       float* out_dist, uint32_t* out_counts);
+
 int32_t turdb_cuda_merge_topk_device(int32_t device, const uint64_t* d_gathered_row_ids,
                                      const float* d_gathered_dist, const uint32_t* d_gathered_counts,
                                      uint32_t n_shards, uint32_t nq, uint32_t k,

@@ -49,3 +49,28 @@ def test_merge_kernel_matches_host_spec(gpu_required):
         assert np.array_equal(o_cnt.cpu().numpy().view(np.uint32), c)
         assert np.array_equal(o_dist.cpu().numpy(), d)
         assert np.array_equal(o_rows.cpu().numpy().view(np.uint64), r)
+
+
+def test_single_process_sharded_search_matches_per_shard_oracle_merge(gpu_required):
+    """turdb_cuda_shards_search_batch: 3 sub-indexes (here on one device), device-to-device gather + merge, against
+    the per-shard oracle searches merged by the host specification of the merge (sharding.merge_topk_host)."""
+    import numpy as np
+    from oracle import binding as ob
+    from turdb_b200 import datasets as ds
+    from turdb_b200.hnsw import CudaHnswIndex, DistanceFunction, shards_search_batch
+    from turdb_b200.sharding import merge_topk_host, shard_bounds
+    x = ds.gaussian_latent(6000, 48, seed=21)
+    q = ds.gaussian_latent(100, 48, seed=22)
+    shards, o_rows, o_dist, o_cnt = [], [], [], []
+    for r in range(3):
+        lo, hi = shard_bounds(6000, 3, r)
+        g = ob.OracleGraph.build(x[lo:hi], seed=5 + r, row_ids=np.arange(lo, hi, dtype=np.uint64))
+        shards.append(CudaHnswIndex.from_graph(g.export()))
+        c = g.search(q, 10, 64, ob.COSINE, n_threads=4)
+        o_rows.append(c[0]); o_dist.append(c[2]); o_cnt.append(c[3])
+    rows, dist, counts = shards_search_batch(shards, q, 10, 64, DistanceFunction.Cosine)
+    e_rows, e_dist, e_cnt = merge_topk_host(np.stack(o_rows), np.stack(o_dist), np.stack(o_cnt), 10)
+    assert np.array_equal(counts, e_cnt) and np.array_equal(rows, e_rows)
+    assert np.array_equal(dist.view(np.uint32), e_dist.view(np.uint32))
+    for s in shards:
+        s.close()

@@ -48,7 +48,7 @@ EXPORTS = [
     "turdb_cuda_hnsw_file_open", "turdb_cuda_hnsw_file_open_memory", "turdb_cuda_hnsw_file_close",
     "turdb_cuda_hnsw_file_get_info", "turdb_cuda_hnsw_file_nodes", "turdb_cuda_hnsw_file_graph",
     "turdb_cuda_hnsw_file_upload", "turdb_cuda_sql_topk_batch", "turdb_cuda_sql_topk_batch_device",
-    "turdb_cuda_index_enable_sq8", "turdb_cuda_search_batch_sq8_device",
+    "turdb_cuda_index_enable_sq8", "turdb_cuda_search_batch_sq8_device", "turdb_cuda_shards_search_batch",
 ]
 
 _lib = None
@@ -87,6 +87,7 @@ def load():
     L.turdb_cuda_sql_topk_batch_device.argtypes = [vp, vp, u32, u32, u32, u32, u8, u32, i32, u32, vp, vp, vp, vp]
     L.turdb_cuda_index_enable_sq8.argtypes = [vp, pu8, u64, pu32]
     L.turdb_cuda_search_batch_sq8_device.argtypes = [vp, vp, u32, u32, u32, u32, u8, vp, vp, vp, vp, vp, vp]
+    L.turdb_cuda_shards_search_batch.argtypes = [C.POINTER(vp), u32, pf, u32, u32, u32, u32, u8, pu64, pf, pu32]
     L.turdb_cuda_hnsw_file_open.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.turdb_cuda_hnsw_file_open_memory.argtypes = [pu8, u64, C.POINTER(vp)]
     L.turdb_cuda_hnsw_file_close.argtypes = [vp]

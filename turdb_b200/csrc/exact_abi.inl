@@ -19,6 +19,107 @@ extern "C" int32_t turdb_cuda_merge_topk_device(int32_t device, const uint64_t* 
   return TURDB_OK;
 }
 
+// One host thread, one sub-index per GPU (turdb_cuda_shards_search_batch).  Every shard searches
+// the same replicated query batch on its own device and stream; the per-shard top-k lists are copied device to
+// device into shard 0's gather buffer ([n_shards][nq][k], the layout the NCCL all-gather of the multi-process
+// path produces) and merged there by the same merge_topk_kernel.  The two paths return identical results; this one
+// is for a single-process host (the Rust/C++ caller), the torch.distributed one for one-process-per-GPU serving.
+extern "C" int32_t turdb_cuda_shards_search_batch(turdb_cuda_index* const* shards, uint32_t n_shards, const float* queries,
+                                                  uint32_t query_dim, uint32_t nq, uint32_t k, uint32_t ef, uint8_t metric,
+                                                  uint64_t* out_row_ids, float* out_dist, uint32_t* out_counts) {
+  if (!shards || n_shards == 0 || n_shards > 32) return fail(TURDB_ERR_INVALID_ARGUMENT, "n_shards must be 1..32");
+  for (uint32_t s = 0; s < n_shards; ++s) {
+    if (!shards[s]) return fail(TURDB_ERR_INVALID_ARGUMENT, "shard %u is null", s);
+    if (query_dim != shards[s]->ix.dim)
+      return fail(TURDB_ERR_DIMENSION_MISMATCH, "query dimension %u does not match index dimension %u", query_dim, shards[s]->ix.dim);
+  }
+  if (nq == 0) return TURDB_OK;
+  if (k == 0 || !queries || !out_row_ids || !out_dist || !out_counts) return fail(TURDB_ERR_INVALID_ARGUMENT, "null pointer or k == 0");
+  struct Lane {
+    cudaStream_t stream = nullptr;
+    uint8_t* slab = nullptr;
+    cudaEvent_t done = nullptr;
+  };
+  std::vector<Lane> lanes(n_shards);
+  const size_t qbytes = (size_t)nq * query_dim * 4;
+  const size_t off_rows = (qbytes + 255) & ~(size_t)255, off_dist = off_rows + (size_t)nq * k * 8,
+               off_counts = off_dist + (size_t)nq * k * 4, local_total = off_counts + (size_t)nq * 4;
+  // shard 0 additionally holds the gathered lists and the merged result
+  const size_t g_rows = (local_total + 255) & ~(size_t)255, g_dist = g_rows + (size_t)n_shards * nq * k * 8,
+               g_cnt = g_dist + (size_t)n_shards * nq * k * 4, m_rows = (g_cnt + (size_t)n_shards * nq * 4 + 255) & ~(size_t)255,
+               m_dist = m_rows + (size_t)nq * k * 8, m_cnt = m_dist + (size_t)nq * k * 4, total0 = m_cnt + (size_t)nq * 4;
+  int32_t rc = TURDB_OK;
+  std::string err;
+  auto cleanup = [&]() {
+    for (uint32_t s = 0; s < n_shards; ++s) {
+      DeviceGuard g(shards[s]->device);
+      if (lanes[s].slab) cudaFreeAsync(lanes[s].slab, lanes[s].stream);
+      if (lanes[s].stream) {
+        cudaStreamSynchronize(lanes[s].stream);
+        cudaStreamDestroy(lanes[s].stream);
+      }
+      if (lanes[s].done) cudaEventDestroy(lanes[s].done);
+    }
+  };
+  for (uint32_t s = 0; s < n_shards && rc == TURDB_OK; ++s) {
+    turdb_cuda_index* idx = shards[s];
+    DeviceGuard g(idx->device);
+    cudaError_t e = cudaStreamCreateWithFlags(&lanes[s].stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&lanes[s].done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&lanes[s].slab, s == 0 ? total0 : local_total, idx->pool, lanes[s].stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(lanes[s].slab, queries, qbytes, cudaMemcpyHostToDevice, lanes[s].stream);
+    if (e != cudaSuccess) {
+      rc = fail(TURDB_ERR_CUDA, "shard %u setup failed: %s", s, cudaGetErrorString(e));
+      break;
+    }
+    rc = turdb_cuda_search_batch_device(idx, (const float*)lanes[s].slab, query_dim, nq, k, ef, metric, nullptr,
+                                        (uint64_t*)(lanes[s].slab + off_rows), nullptr, (float*)(lanes[s].slab + off_dist),
+                                        (uint32_t*)(lanes[s].slab + off_counts), nullptr, lanes[s].stream);
+  }
+  if (rc != TURDB_OK) {
+    err = g_last_error;
+    cleanup();
+    g_last_error = err;
+    return rc;
+  }
+  // gather into shard 0 (peer copies ordered after each shard's search), then merge on shard 0's stream
+  cudaError_t e = cudaSuccess;
+  for (uint32_t s = 0; s < n_shards && e == cudaSuccess; ++s) {
+    DeviceGuard g(shards[s]->device);
+    uint8_t* dst = lanes[0].slab;
+    e = cudaMemcpyPeerAsync(dst + g_rows + (size_t)s * nq * k * 8, shards[0]->device, lanes[s].slab + off_rows, shards[s]->device,
+                            (size_t)nq * k * 8, lanes[s].stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyPeerAsync(dst + g_dist + (size_t)s * nq * k * 4, shards[0]->device, lanes[s].slab + off_dist, shards[s]->device,
+                              (size_t)nq * k * 4, lanes[s].stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyPeerAsync(dst + g_cnt + (size_t)s * nq * 4, shards[0]->device, lanes[s].slab + off_counts, shards[s]->device,
+                              (size_t)nq * 4, lanes[s].stream);
+    if (e == cudaSuccess) e = cudaEventRecord(lanes[s].done, lanes[s].stream);
+  }
+  if (e == cudaSuccess) {
+    DeviceGuard g(shards[0]->device);
+    for (uint32_t s = 0; s < n_shards && e == cudaSuccess; ++s) e = cudaStreamWaitEvent(lanes[0].stream, lanes[s].done, 0);
+    if (e == cudaSuccess) {
+      uint8_t* b = lanes[0].slab;
+      rc = turdb_cuda_merge_topk_device(shards[0]->device, (const uint64_t*)(b + g_rows), (const float*)(b + g_dist),
+                                        (const uint32_t*)(b + g_cnt), n_shards, nq, k, (uint64_t*)(b + m_rows), (float*)(b + m_dist),
+                                        (uint32_t*)(b + m_cnt), lanes[0].stream);
+      if (rc == TURDB_OK) {
+        e = cudaMemcpyAsync(out_row_ids, b + m_rows, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, lanes[0].stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_dist, b + m_dist, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, lanes[0].stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_counts, b + m_cnt, (size_t)nq * 4, cudaMemcpyDeviceToHost, lanes[0].stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(lanes[0].stream);
+      }
+    }
+  }
+  if (rc == TURDB_OK && e != cudaSuccess) rc = fail(TURDB_ERR_CUDA, "sharded search failed: %s", cudaGetErrorString(e));
+  err = g_last_error;
+  cleanup();
+  g_last_error = err;
+  return rc;
+}
+
 // ---- TMA descriptors: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

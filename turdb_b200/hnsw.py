@@ -271,6 +271,23 @@ class CudaHnswIndex:
                                                              d_rows, d_nodes or None, d_dist, d_counts, stream or None))
 
 
+def shards_search_batch(shards, queries, k: int, ef: int, metric: DistanceFunction = DistanceFunction.L2):
+    """Single-process sharded search (turdb_cuda_shards_search_batch): `shards` = list of CudaHnswIndex (one
+    sub-index per GPU), replicated queries, device-to-device gather into shard 0, merge by (distance, row_id)."""
+    q = np.ascontiguousarray(queries, dtype=np.float32)
+    if q.ndim == 1:
+        q = q[None, :]
+    nq, qd = q.shape
+    handles = (C.c_void_p * len(shards))(*[s._h for s in shards])
+    rows = np.full((nq, k), INVALID_ROW, np.uint64)
+    dist = np.full((nq, k), np.inf, np.float32)
+    counts = np.zeros(nq, np.uint32)
+    _check(_lib.load().turdb_cuda_shards_search_batch(handles, len(shards), _ptr(q, C.c_float), qd, nq, int(k), int(ef),
+                                                      int(metric), _ptr(rows, C.c_uint64), _ptr(dist, C.c_float),
+                                                      _ptr(counts, C.c_uint32)))
+    return rows, dist, counts
+
+
 def visibility_bitmap(visible_mask) -> np.ndarray:
     """bool[n] (node order) -> u64 bitmap, bit i of word i/64."""
     v = np.asarray(visible_mask, dtype=bool)
