@@ -174,3 +174,38 @@ def test_missing_vectors_and_tombstones_rank_last(gpu_required, graph2k):
     cpu = ob.OracleGraph.from_arrays(ga).search(q, 10, 64, ob.L2, n_threads=4)
     assert np.array_equal(got[1], cpu[1]) and np.array_equal(got[2].view(np.uint32), cpu[2].view(np.uint32))
     idx.close()
+
+
+def test_reader_survives_corrupted_files(graph2k):
+    """Random byte damage and truncation: the reader either rejects the file or returns a graph whose every
+    neighbour id, entry point and count is in range (index_create re-checks them on upload)."""
+    g, _, _ = graph2k
+    data, _, _ = ob.hnsw_file_write(g, mode=1)
+    rng = np.random.default_rng(0)
+    parsed = 0
+    for it in range(120):
+        b = bytearray(data)
+        for _ in range(int(rng.integers(1, 40))):
+            b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        if it % 7 == 0:
+            b = b[: int(rng.integers(0, len(b)))]
+        try:
+            f = HnswFile.from_bytes(bytes(b))
+        except (ValueError, RuntimeError):
+            continue
+        gr = f.graph()
+        n = f.n_total
+        assert gr["l0_adj"].shape == (n, 32) and (gr["l0_cnt"] <= 32).all() and (gr["up_cnt"] <= 16).all()
+        assert (gr["l0_adj"][gr["l0_adj"] != 0xFFFFFFFF] < n).all()
+        assert (gr["up_adj"][gr["up_adj"] != 0xFFFFFFFF] < n).all()
+        assert f.info["entry"] == 0xFFFFFFFF or f.info["entry"] < n
+        f.close()
+        parsed += 1
+    assert parsed > 50
+
+
+def test_vector_literal_parser():
+    from turdb_b200.sql_operator import parse_vector_literal
+    assert parse_vector_literal(" [0.1, 2,-3.5e-1] ").tolist() == [np.float32(0.1), 2.0, np.float32(-0.35)]
+    with pytest.raises(ValueError):
+        parse_vector_literal("0.1, 0.2")
