@@ -1,4 +1,6 @@
 #!/bin/bash
+# The measurement recipe behind profiles/r01_*: bench line, ncu launch list of the bench command, ncu --set full of the
+# traversal kernel, single-GPU config runs.  Run on the GPU box: gpurun -- bash tools/profile_round.sh
 set -x
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
