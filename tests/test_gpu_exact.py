@@ -31,7 +31,8 @@ def flat_graph(x):
                 up_cnt=np.zeros(0, np.uint8), entry=0, max_level=0)
 
 
-@pytest.mark.parametrize("n,dim,nq,k", [(3000, 128, 40, 10), (5000, 384, 200, 10), (2500, 100, 17, 5), (700, 64, 130, 100)])
+@pytest.mark.parametrize("n,dim,nq,k", [(3000, 128, 40, 10), (5000, 384, 200, 10), (2500, 100, 17, 5), (700, 64, 130, 100),
+                                        (2000, 768, 150, 10), (1500, 520, 33, 7)])  # > 512 dims: streamed query block
 def test_exact_topk_matches_reference(gpu_required, n, dim, nq, k):
     x = ds.gaussian_latent(n, dim, seed=n, normalise=False)
     q = ds.gaussian_latent(nq, dim, seed=n + 1, normalise=False)

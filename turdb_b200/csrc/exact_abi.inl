@@ -190,7 +190,10 @@ extern "C" int32_t turdb_cuda_bruteforce_topk_device(turdb_cuda_index* idx, cons
   const uint32_t dim = idx->ix.dim, ds = idx->ix.ds;
   const uint32_t kp = (dim + kChunkK - 1) / kChunkK * kChunkK;
   const uint32_t k_chunks = kp / kChunkK;
-  if (k_chunks > 8) return fail(TURDB_ERR_UNSUPPORTED, "bruteforce_topk supports dim <= 512 in this build (dim %u)", dim);
+  if (k_chunks > 32) return fail(TURDB_ERR_UNSUPPORTED, "bruteforce_topk supports dim <= 2048 (dim %u)", dim);
+  // up to 512 dims the query block (128 x K BF16) stays resident in shared memory; above, its K chunks are streamed
+  // with the vector tile's (twice the TMA traffic per tile, but any K fits)
+  const uint32_t stream_a = k_chunks > 8 ? 1u : 0u;
   if (!rerank_factor) rerank_factor = 4;
   const uint64_t kprime64 = std::min<uint64_t>((uint64_t)k * rerank_factor, n);
   if (kprime64 > 4096) return fail(TURDB_ERR_UNSUPPORTED, "k * rerank_factor = %llu > 4096", (unsigned long long)kprime64);
@@ -249,10 +252,11 @@ extern "C" int32_t turdb_cuda_bruteforce_topk_device(turdb_cuda_index* idx, cons
   if (!make_bf16_map(&map_q, d_qb, nq, kp) || !make_bf16_map(&map_x, d_xb, n, kp))
     return bail(fail(TURDB_ERR_CUDA, "cuTensorMapEncodeTiled failed"));
 
-  const size_t fixed_smem = (size_t)k_chunks * kChunkBytes + 4 * kTileN * 4 + 4 * kRing * kTileM * 4 + 24 * 8 + 16;
-  const uint32_t n_stages = (uint32_t)std::min<size_t>(kMaxStages, ((size_t)idx->max_smem_optin - fixed_smem) / kChunkBytes);
+  const size_t stage_bytes = stream_a ? 2 * (size_t)kChunkBytes : (size_t)kChunkBytes;
+  const size_t fixed_smem = (stream_a ? 0 : (size_t)k_chunks * kChunkBytes) + 4 * kTileN * 4 + 4 * kRing * kTileM * 4 + 24 * 8 + 16;
+  const uint32_t n_stages = (uint32_t)std::min<size_t>(kMaxStages, ((size_t)idx->max_smem_optin - fixed_smem) / stage_bytes);
   if (n_stages < 2) return bail(fail(TURDB_ERR_UNSUPPORTED, "not enough shared memory for the exact path at dim %u", dim));
-  const size_t gemm_smem = fixed_smem + (size_t)n_stages * kChunkBytes;
+  const size_t gemm_smem = fixed_smem + (size_t)n_stages * stage_bytes;
   cudaError_t e = cudaFuncSetAttribute(exact_gemm_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(exact_gemm_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
@@ -270,6 +274,7 @@ extern "C" int32_t turdb_cuda_bruteforce_topk_device(turdb_cuda_index* idx, cons
     a.nq = nq;
     a.k_chunks = k_chunks;
     a.n_stages = n_stages;
+    a.stream_a = stream_a;
     a.tile_lo = lo;
     a.tile_hi = hi;
     const uint32_t tiles = hi - lo;

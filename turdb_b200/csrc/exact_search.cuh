@@ -176,6 +176,8 @@ constexpr uint32_t kExactThreads = 192;  // warp 0 TMA, warp 1 MMA + TMEM alloc,
 struct ExactArgs {
   uint32_t n_vec, nq, k_chunks;
   uint32_t n_stages;              // B pipeline stages (2..kMaxStages)
+  uint32_t stream_a;              // 1: A (the query block) is not resident; its K chunk travels in every stage, ahead
+                                  //    of the B chunk (dims above 512: 128 x K BF16 no longer fits beside the pipeline)
   uint32_t tile_lo, tile_hi;      // vector tiles of this pass
   uint32_t tiles_per_item;        // consecutive tiles one CTA handles for one query block
   uint32_t n_qblocks, n_items;
@@ -197,9 +199,11 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* sA = smem;
-  uint8_t* sB = sA + (size_t)a.k_chunks * kChunkBytes;
+  uint8_t* sB = sA + (a.stream_a ? 0 : (size_t)a.k_chunks * kChunkBytes);
   const uint32_t kStages = a.n_stages;
-  float* s_bias = reinterpret_cast<float*>(sB + (size_t)kStages * kChunkBytes);  // [2][128] (+ pad to 2 KB)
+  const uint32_t stage_bytes = a.stream_a ? 2 * kChunkBytes : kChunkBytes;  // [A chunk |] B chunk
+  const uint32_t b_in_stage = a.stream_a ? kChunkBytes : 0;
+  float* s_bias = reinterpret_cast<float*>(sB + (size_t)kStages * stage_bytes);  // [2][128] (+ pad to 2 KB)
   float* ring_key = s_bias + 4 * kTileN;                                              // [2][kRing][128] pending candidates
   uint32_t* ring_col = reinterpret_cast<uint32_t*>(ring_key + 2 * kRing * kTileM);    // [2][kRing][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring_col + 2 * kRing * kTileM);
@@ -240,21 +244,26 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
         const uint32_t qb = item % a.n_qblocks;
         const uint32_t t0 = a.tile_lo + (item / a.n_qblocks) * a.tiles_per_item;
         const uint32_t t1 = min(a.tile_hi, t0 + a.tiles_per_item);
-        long long c0 = a.dbg ? clock64() : 0;
-        mbar_wait(bar_a_empty, a_phase ^ 1);  // previous item's MMAs have drained A
-        if (a.dbg) atomicAdd(a.dbg + 0, (unsigned long long)(clock64() - c0));
-        mbar_expect_tx(bar_a_full, a.k_chunks * kChunkBytes);
-        for (uint32_t kc = 0; kc < a.k_chunks; ++kc)
-          tma_load_2d(smem_u32(sA + (size_t)kc * kChunkBytes), &map_q, (int32_t)(kc * kChunkK), (int32_t)(qb * kTileM), bar_a_full);
-        a_phase ^= 1;
+        if (!a.stream_a) {
+          long long c0 = a.dbg ? clock64() : 0;
+          mbar_wait(bar_a_empty, a_phase ^ 1);  // previous item's MMAs have drained A
+          if (a.dbg) atomicAdd(a.dbg + 0, (unsigned long long)(clock64() - c0));
+          mbar_expect_tx(bar_a_full, a.k_chunks * kChunkBytes);
+          for (uint32_t kc = 0; kc < a.k_chunks; ++kc)
+            tma_load_2d(smem_u32(sA + (size_t)kc * kChunkBytes), &map_q, (int32_t)(kc * kChunkK), (int32_t)(qb * kTileM), bar_a_full);
+          a_phase ^= 1;
+        }
         for (uint32_t t = t0; t < t1; ++t) {
           for (uint32_t kc = 0; kc < a.k_chunks; ++kc) {
             long long c1 = a.dbg ? clock64() : 0;
             mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
             if (a.dbg) atomicAdd(a.dbg + 1, (unsigned long long)(clock64() - c1));
-            mbar_expect_tx(bar_b_full + 8 * stage, kChunkBytes);
-            tma_load_2d(smem_u32(sB + (size_t)stage * kChunkBytes), &map_x, (int32_t)(kc * kChunkK), (int32_t)(t * kTileN),
-                        bar_b_full + 8 * stage);
+            mbar_expect_tx(bar_b_full + 8 * stage, stage_bytes);
+            if (a.stream_a)  // the query block's chunk comes from L2 (it is 128 x K BF16, re-read once per vector tile)
+              tma_load_2d(smem_u32(sB + (size_t)stage * stage_bytes), &map_q, (int32_t)(kc * kChunkK), (int32_t)(qb * kTileM),
+                          bar_b_full + 8 * stage);
+            tma_load_2d(smem_u32(sB + (size_t)stage * stage_bytes + b_in_stage), &map_x, (int32_t)(kc * kChunkK),
+                        (int32_t)(t * kTileN), bar_b_full + 8 * stage);
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
@@ -272,10 +281,12 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
       for (uint32_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
         const uint32_t t0 = a.tile_lo + (item / a.n_qblocks) * a.tiles_per_item;
         const uint32_t t1 = min(a.tile_hi, t0 + a.tiles_per_item);
-        long long c2 = a.dbg ? clock64() : 0;
-        mbar_wait(bar_a_full, a_phase);
-        if (a.dbg) atomicAdd(a.dbg + 2, (unsigned long long)(clock64() - c2));
-        a_phase ^= 1;
+        if (!a.stream_a) {
+          long long c2 = a.dbg ? clock64() : 0;
+          mbar_wait(bar_a_full, a_phase);
+          if (a.dbg) atomicAdd(a.dbg + 2, (unsigned long long)(clock64() - c2));
+          a_phase ^= 1;
+        }
         tc_fence_after();
         for (uint32_t t = t0; t < t1; ++t) {
           long long c3 = a.dbg ? clock64() : 0;
@@ -288,8 +299,9 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
             mbar_wait(bar_b_full + 8 * stage, phase);
             if (a.dbg) atomicAdd(a.dbg + 4, (unsigned long long)(clock64() - c4));
             tc_fence_after();
-            const uint64_t da = umma_desc_sw128(smem_u32(sA + (size_t)kc * kChunkBytes));
-            const uint64_t db = umma_desc_sw128(smem_u32(sB + (size_t)stage * kChunkBytes));
+            const uint64_t da = umma_desc_sw128(a.stream_a ? smem_u32(sB + (size_t)stage * stage_bytes)
+                                                           : smem_u32(sA + (size_t)kc * kChunkBytes));
+            const uint64_t db = umma_desc_sw128(smem_u32(sB + (size_t)stage * stage_bytes + b_in_stage));
 #pragma unroll
             for (uint32_t k4 = 0; k4 < kChunkK / 16; ++k4)  // UMMA_K = 16 BF16 = 32 B inside the swizzle row
               tc_mma_bf16(d_tmem, da + 2 * k4, db + 2 * k4, idesc, (kc | k4) != 0 ? 1u : 0u);
@@ -306,7 +318,7 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
             acc_phase ^= 1;
           }
         }
-        tc_commit(bar_a_empty);
+        if (!a.stream_a) tc_commit(bar_a_empty);
       }
     }
   } else {
