@@ -257,9 +257,14 @@ extern "C" int32_t turdb_cuda_bruteforce_topk_device(turdb_cuda_index* idx, cons
   const uint32_t n_stages = (uint32_t)std::min<size_t>(kMaxStages, ((size_t)idx->max_smem_optin - fixed_smem) / stage_bytes);
   if (n_stages < 2) return bail(fail(TURDB_ERR_UNSUPPORTED, "not enough shared memory for the exact path at dim %u", dim));
   const size_t gemm_smem = fixed_smem + (size_t)n_stages * stage_bytes;
-  cudaError_t e = cudaFuncSetAttribute(exact_gemm_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(exact_gemm_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
+  cudaError_t e = cudaSuccess;
+  auto set_smem = [&](auto kern) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
+  };
+  set_smem(exact_gemm_filter_kernel<true, false>);
+  set_smem(exact_gemm_filter_kernel<false, false>);
+  set_smem(exact_gemm_filter_kernel<true, true>);
+  set_smem(exact_gemm_filter_kernel<false, true>);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(exact_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cap * 8));
   if (e != cudaSuccess) return bail(fail(TURDB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)));
@@ -291,8 +296,13 @@ extern "C" int32_t turdb_cuda_bruteforce_topk_device(turdb_cuda_index* idx, cons
     a.overflow_flag = d_ovf;
     a.dbg = idx->d_dbg;
     const uint32_t grid = std::min<uint32_t>(a.n_items, (uint32_t)idx->num_sms);
-    if (metric == kL2) exact_gemm_filter_kernel<true><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
-    else exact_gemm_filter_kernel<false><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
+    if (metric == kL2) {
+      if (stream_a) exact_gemm_filter_kernel<true, true><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
+      else exact_gemm_filter_kernel<true, false><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
+    } else {
+      if (stream_a) exact_gemm_filter_kernel<false, true><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
+      else exact_gemm_filter_kernel<false, false><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
+    }
     exact_threshold_kernel<<<nq, 256, cap * 8, stream>>>(nq, kprime, cap, d_cnt, d_cid, d_ckey, d_th);
     e = cudaGetLastError();
     if (e != cudaSuccess) return bail(fail(TURDB_ERR_CUDA, "exact pass launch failed: %s", cudaGetErrorString(e)));

@@ -192,17 +192,17 @@ struct ExactArgs {
 };
 
 // smem: [A: k_chunks x 16 KB][B: n_stages x 16 KB][col bias: 2 x 128 float + pad][barriers][tmem ptr]
-template <bool BIAS>
+template <bool BIAS, bool STREAM_A>
 __global__ void __launch_bounds__(kExactThreads, 1)
 exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                          const ExactArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* sA = smem;
-  uint8_t* sB = sA + (a.stream_a ? 0 : (size_t)a.k_chunks * kChunkBytes);
+  uint8_t* sB = sA + (STREAM_A ? 0 : (size_t)a.k_chunks * kChunkBytes);
   const uint32_t kStages = a.n_stages;
-  const uint32_t stage_bytes = a.stream_a ? 2 * kChunkBytes : kChunkBytes;  // [A chunk |] B chunk
-  const uint32_t b_in_stage = a.stream_a ? kChunkBytes : 0;
+  const uint32_t stage_bytes = STREAM_A ? 2 * kChunkBytes : kChunkBytes;  // [A chunk |] B chunk
+  const uint32_t b_in_stage = STREAM_A ? kChunkBytes : 0;
   float* s_bias = reinterpret_cast<float*>(sB + (size_t)kStages * stage_bytes);  // [2][128] (+ pad to 2 KB)
   float* ring_key = s_bias + 4 * kTileN;                                              // [2][kRing][128] pending candidates
   uint32_t* ring_col = reinterpret_cast<uint32_t*>(ring_key + 2 * kRing * kTileM);    // [2][kRing][128]
@@ -244,7 +244,7 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
         const uint32_t qb = item % a.n_qblocks;
         const uint32_t t0 = a.tile_lo + (item / a.n_qblocks) * a.tiles_per_item;
         const uint32_t t1 = min(a.tile_hi, t0 + a.tiles_per_item);
-        if (!a.stream_a) {
+        if (!STREAM_A) {
           long long c0 = a.dbg ? clock64() : 0;
           mbar_wait(bar_a_empty, a_phase ^ 1);  // previous item's MMAs have drained A
           if (a.dbg) atomicAdd(a.dbg + 0, (unsigned long long)(clock64() - c0));
@@ -259,7 +259,7 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
             mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
             if (a.dbg) atomicAdd(a.dbg + 1, (unsigned long long)(clock64() - c1));
             mbar_expect_tx(bar_b_full + 8 * stage, stage_bytes);
-            if (a.stream_a)  // the query block's chunk comes from L2 (it is 128 x K BF16, re-read once per vector tile)
+            if (STREAM_A)  // the query block's chunk comes from L2 (it is 128 x K BF16, re-read once per vector tile)
               tma_load_2d(smem_u32(sB + (size_t)stage * stage_bytes), &map_q, (int32_t)(kc * kChunkK), (int32_t)(qb * kTileM),
                           bar_b_full + 8 * stage);
             tma_load_2d(smem_u32(sB + (size_t)stage * stage_bytes + b_in_stage), &map_x, (int32_t)(kc * kChunkK),
@@ -281,7 +281,7 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
       for (uint32_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
         const uint32_t t0 = a.tile_lo + (item / a.n_qblocks) * a.tiles_per_item;
         const uint32_t t1 = min(a.tile_hi, t0 + a.tiles_per_item);
-        if (!a.stream_a) {
+        if (!STREAM_A) {
           long long c2 = a.dbg ? clock64() : 0;
           mbar_wait(bar_a_full, a_phase);
           if (a.dbg) atomicAdd(a.dbg + 2, (unsigned long long)(clock64() - c2));
@@ -299,7 +299,7 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
             mbar_wait(bar_b_full + 8 * stage, phase);
             if (a.dbg) atomicAdd(a.dbg + 4, (unsigned long long)(clock64() - c4));
             tc_fence_after();
-            const uint64_t da = umma_desc_sw128(a.stream_a ? smem_u32(sB + (size_t)stage * stage_bytes)
+            const uint64_t da = umma_desc_sw128(STREAM_A ? smem_u32(sB + (size_t)stage * stage_bytes)
                                                            : smem_u32(sA + (size_t)kc * kChunkBytes));
             const uint64_t db = umma_desc_sw128(smem_u32(sB + (size_t)stage * stage_bytes + b_in_stage));
 #pragma unroll
@@ -318,7 +318,7 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
             acc_phase ^= 1;
           }
         }
-        if (!a.stream_a) tc_commit(bar_a_empty);
+        if (!STREAM_A) tc_commit(bar_a_empty);
       }
     }
   } else {
