@@ -44,6 +44,13 @@
 #define TURDB_MIN_CTAS 5
 #endif
 
+// 1: FP32 rows are gathered four at a time with TMA tile::gather4 (see team_distances_g4) instead of one bulk copy each.
+//    Measured on B200: correct (parity tests) but slower than the bulk copies (1M x 384: 9.94 vs 8.14 ms; 1M x 128: 5.18 vs
+//    4.74 ms) — the issue phase does not shrink and the reduce over piece-split rows grows.  Off by default.
+#ifndef TURDB_GATHER4
+#define TURDB_GATHER4 0
+#endif
+
 #ifndef TURDB_GATHER_MODE
 #define TURDB_GATHER_MODE 0
 #endif
@@ -65,6 +72,10 @@ struct TeamLayout {
   // a vector streams through its slot in n_segs pieces of seg_steps AVX steps (32 B each); the last piece
   // also carries the < 8-element tail.  The quad's accumulators live in registers across pieces.
   uint32_t n_segs, seg_steps;
+  // gather4 staging (g4_pieces != 0): a row travels in g4_pieces column pieces of g4_boxw floats (g4_boxw == 8 mod 32,
+  // so the four rows of a piece sit 32 B apart modulo 128 B: conflict-free quads without padding); a group of 8 slots
+  // = 2 quads x pieces regions of 16 * g4_boxw bytes
+  uint32_t g4_pieces, g4_boxw, g4_tail_pc, g4_tail_off;
   uint32_t hash_bits;  // shared visited table has 1 << hash_bits slots
   // compact table (hash16 != 0): 16-bit entries = (displacement+1) << rem_bits | remainder of a
   // bijective hash of the id, so an entry still identifies exactly one node (exact set, half the bytes)
@@ -92,6 +103,7 @@ struct SearchArgs {
   // rows the traversal gathers: the FP32 arena (row_bytes == ds * 4) or, for the SQ8 kernels, the code arena
   const uint8_t* rows;
   uint32_t row_bytes;        // bytes between rows == bytes copied per row (multiple of 16)
+  const void* row_map;       // device copy of the arena's 2-D tensor map (gather4 staging), or null
   // search_filtered (search.rs:352-398): one bit per node; candidates that do not fit the shared window
   const uint64_t* visible;   // null => unfiltered search
   uint2* f_ovf;              // [CTAs][f_ocap] (distance bits, id) overflow of the candidate window
@@ -128,6 +140,8 @@ struct Team {
   uint32_t stage_u32;
   uint32_t stride, vec_bytes, n_groups, n_segs, seg_steps;
   const uint8_t* rows;       // gather source, vec_bytes apart
+  const void* row_map;       // gather4: tensor map of the arena
+  uint32_t g4_pieces, g4_boxw, g4_tail_pc, g4_tail_off, n_rows;
   uint32_t phases;           // per-warp parity bits of the groups this warp owns
   float qnorm;
   uint32_t c_issue, c_wait, c_comp;  // diagnostics: cycles spent by this warp per phase
@@ -324,12 +338,97 @@ __device__ __forceinline__ void team_distances_ldgsts(const DeviceIndex& ix, Tea
   }
 }
 
+#if TURDB_GATHER4
+// gather4 form of the whole-row path (FP32 arena): a hop's bulk copies cost ~100 issue cycles EACH (ELECT / R2UR /
+// UBLKCP per lane); one tile::gather4 instruction moves four rows (x one column piece), so a 24-neighbour hop issues
+// 6 x pieces instructions instead of 24.  Unit (quad qd, piece pc): rows 4qd..4qd+3 of the request, columns
+// [pc * boxw, (pc + 1) * boxw); a quad with fewer than four rows left is padded with row index n — out-of-bounds rows
+// and columns read as zeros, move no data and still count the full box on the barrier (probed: tools/micro).
+template <int METRIC>
+__device__ __forceinline__ void team_distances_g4(const DeviceIndex& ix, Team& t, uint32_t m) {
+  const uint32_t lane = t.lane, p = lane & 3, G = t.n_groups, P = t.g4_pieces, BW = t.g4_boxw;
+  const uint32_t region = 16 * BW, group_bytes = 2 * P * region;
+  const uint32_t nchunks = (m + 7) >> 3;
+  auto unit = [&](uint32_t qd, uint32_t pc, bool prefetch_only) {
+    const uint32_t c = qd >> 1, g = t.group_of(c);
+    int32_t r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r[j] = (4 * qd + j < m) ? (int32_t)t.cand_ids[4 * qd + j] : (int32_t)t.n_rows;
+    if (prefetch_only) {
+      tma_gather4_prefetch(t.row_map, (int32_t)(pc * BW), r[0], r[1], r[2], r[3]);
+    } else {
+      tma_gather4(t.stage_u32 + g * group_bytes + ((qd & 1) * P + pc) * region, t.row_map, (int32_t)(pc * BW), r[0], r[1], r[2],
+                  r[3], t.bar0 + 8 * g);
+    }
+  };
+  auto chunk_bytes = [&](uint32_t c) { return ((min(8u, m - 8 * c) + 3) >> 2) * P * region; };
+  long long t0 = t.dbg ? clock64() : 0;
+  {
+    const uint32_t m1 = min(m, 8 * G);
+    for (uint32_t c = 0; c < min(G, nchunks); ++c)
+      if (t.owns(c) && lane == 0) mbar_expect_tx(t.bar0 + 8 * c, chunk_bytes(c));
+    const uint32_t n_units = ((m1 + 3) >> 2) * P;
+    const uint32_t i = t.warp + t.n_warps * lane;  // units dealt to all warps, the leader included
+    if (i < n_units) unit(i / P, i % P, false);
+#if TURDB_R2_PREFETCH
+    const uint32_t n2 = ((m - m1 + 3) >> 2) * P;
+    if (t.warp == 0 && t.n_warps >= 3 && lane < n2) unit((m1 >> 2) + lane / P, lane % P, true);
+#endif
+  }
+  if (t.dbg) t.c_issue += (uint32_t)(clock64() - t0);
+  const uint32_t steps = ix.dim >> 3, spp = BW >> 3;
+  for (uint32_t c = 0; c < nchunks; ++c) {
+    const uint32_t g = t.group_of(c);
+    if (!t.owns(c)) continue;
+    const uint32_t v = lane >> 2, slot = 8 * c + v;
+    float nb = 0.f;
+    if (METRIC == kCosine && slot < m) nb = __ldg(ix.norm2 + t.cand_ids[slot]);
+    long long w0 = t.dbg ? clock64() : 0;
+    mbar_wait(t.bar0 + 8 * g, (t.phases >> g) & 1u);
+    long long w1 = t.dbg ? clock64() : 0;
+    t.c_wait += (uint32_t)(w1 - w0);
+    t.phases ^= (1u << g);
+    const uint8_t* base = t.stage + g * group_bytes + (v >> 2) * P * region + (v & 3) * BW * 4;
+    uint64_t acc = 0ull;
+    for (uint32_t pc = 0, s0 = 0; s0 < steps; ++pc, s0 += spp) {
+      const uint32_t ns = min(spp, steps - s0);
+      const uint64_t* av = reinterpret_cast<const uint64_t*>(t.q + 8 * s0) + p;
+      const uint64_t* bv = reinterpret_cast<const uint64_t*>(base + pc * region) + p;
+      acc = (METRIC == kL2) ? quad_accum<true>(acc, av, bv, ns) : quad_accum<false>(acc, av, bv, ns);
+    }
+    const float* bt = reinterpret_cast<const float*>(base + t.g4_tail_pc * region) + t.g4_tail_off;
+    const float raw = (METRIC == kL2) ? quad_finish<true>(acc, t.q + 8 * steps, bt, ix.dim & 7)
+                                      : quad_finish<false>(acc, t.q + 8 * steps, bt, ix.dim & 7);
+    if (p == 0 && slot < m) {
+      float d = raw;
+      if (METRIC == kIP) d = -raw;
+      if (METRIC == kCosine) d = cosine_finish(raw, t.qnorm, nb);
+      t.cand_d[slot] = d;
+    }
+    __syncwarp();
+    if (t.dbg) t.c_comp += (uint32_t)(clock64() - w1);
+    if (c + G < nchunks) {  // second round: this chunk's owner issues the next chunk of its group
+      const uint32_t c2 = c + G, nq2 = (min(8u, m - 8 * c2) + 3) >> 2;
+      if (lane == 0) mbar_expect_tx(t.bar0 + 8 * g, chunk_bytes(c2));
+      __syncwarp();
+      if (lane < nq2 * P) unit(2 * c2 + lane / P, lane % P, false);
+    }
+  }
+}
+#endif
+
 template <int METRIC, bool SQ8>
 __device__ __forceinline__ void team_distances(const DeviceIndex& ix, Team& t, uint32_t m) {
   if (SQ8) {  // code rows are short: always the whole-row form (the host never splits them)
     team_distances_whole<METRIC, true>(ix, t, m);
     return;
   }
+#if TURDB_GATHER4
+  if (t.g4_pieces) {
+    team_distances_g4<METRIC>(ix, t, m);
+    return;
+  }
+#endif
 #if TURDB_GATHER_MODE == 1
   if (t.n_segs == 1) team_distances_ldgsts<METRIC>(ix, t, m);
 #else
@@ -568,6 +667,12 @@ __global__ void __launch_bounds__(128, TURDB_MIN_CTAS) hnsw_search_kernel(const 
   t.stride = a.lay.stride;
   t.vec_bytes = a.lay.vec_bytes;
   t.rows = a.rows;
+  t.row_map = a.row_map;
+  t.g4_pieces = a.lay.g4_pieces;
+  t.g4_boxw = a.lay.g4_boxw;
+  t.g4_tail_pc = a.lay.g4_tail_pc;
+  t.g4_tail_off = a.lay.g4_tail_off;
+  t.n_rows = (uint32_t)a.ix.n;
   t.n_groups = a.lay.n_groups;
   t.n_segs = a.lay.n_segs;
   t.seg_steps = a.lay.seg_steps;

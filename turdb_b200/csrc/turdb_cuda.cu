@@ -64,6 +64,8 @@ struct turdb_cuda_index {
   uint32_t* d_up_adj = nullptr;
   uint64_t* d_row_ids = nullptr;
   uint8_t* d_levels = nullptr;
+  void* d_row_map = nullptr;               // device copy of the arena's gather4 tensor map (TURDB_GATHER4 builds)
+  uint32_t g4_boxw = 0;
   uint8_t* d_arena_sq8 = nullptr;          // SQ8 rows: dim codes | pad | min | scale, sq8_row_bytes apart (enable_sq8)
   float* d_norm2_sq8 = nullptr;            // dot(decode(x), decode(x)) per row, AVX2 lane order
   uint32_t sq8_row_bytes = 0;
@@ -197,6 +199,7 @@ int32_t turdb_cuda_index_destroy(turdb_cuda_index* idx) {
     cudaFree(idx->d_up_adj);
     cudaFree(idx->d_row_ids);
     cudaFree(idx->d_levels);
+    cudaFree(idx->d_row_map);
     cudaFree(idx->d_arena_sq8);
     cudaFree(idx->d_norm2_sq8);
     cudaFree(idx->d_arena_bf16);
@@ -453,7 +456,8 @@ int32_t turdb_cuda_index_profile_read(turdb_cuda_index* idx, float* main_ms, flo
 // traversal launch
 // ------------------------------------------------------------------------------------------
 static TeamLayout make_layout(uint32_t dim, uint32_t ds, uint32_t ef, uint32_t hash_bits, uint32_t n_slots, uint32_t n_segs,
-                              bool global_visited, uint64_t n_nodes, bool filtered = false, uint32_t sq8_row_bytes = 0) {
+                              bool global_visited, uint64_t n_nodes, bool filtered = false, uint32_t sq8_row_bytes = 0,
+                              uint32_t g4_boxw = 0) {
   TeamLayout L{};
   L.vec_bytes = sq8_row_bytes ? sq8_row_bytes : ds * 4;
   const uint32_t steps = dim >> 3;
@@ -478,7 +482,21 @@ static TeamLayout make_layout(uint32_t dim, uint32_t ds, uint32_t ef, uint32_t h
   L.off_cand = off;  off += 512;  // cand_ids[32], cand_d[32], tmp_ub[32], cand_next[32]
   L.off_hash = off;  off += global_visited ? 0 : ((L.hash16 ? 2u : 4u) << hash_bits);
   off = (off + 127) & ~127u;
-  L.off_stage = off; off += n_slots * L.stride;
+  L.off_stage = off;
+  if (g4_boxw && !sq8_row_bytes && L.n_segs == 1) {
+    L.g4_boxw = g4_boxw;
+    L.g4_pieces = (ds + g4_boxw - 1) / g4_boxw;
+    const uint32_t e0 = steps * 8;  // first element of the < 8-element tail
+    L.g4_tail_pc = e0 / g4_boxw;
+    L.g4_tail_off = e0 - L.g4_tail_pc * g4_boxw;
+    if (L.g4_tail_pc >= L.g4_pieces) {  // dim % 8 == 0 and the row ends exactly at a piece boundary: never dereferenced
+      L.g4_tail_pc = L.g4_pieces - 1;
+      L.g4_tail_off = 0;
+    }
+    off += L.n_groups * 2 * L.g4_pieces * 16 * g4_boxw;
+  } else {
+    off += n_slots * L.stride;
+  }
   L.team_bytes = (off + 127) & ~127u;
   return L;
 }
@@ -560,6 +578,8 @@ __global__ void fill_empty_results_kernel(uint64_t* rows, uint32_t* nodes, float
   if (stats && i < (uint64_t)nq * 4) stats[i] = 0;
 }
 
+[[maybe_unused]] static int32_t ensure_row_map(turdb_cuda_index* idx);  // defined after the tensor-map helpers (exact_abi.inl)
+
 static int32_t search_batch_device_impl(turdb_cuda_index* idx, const float* d_queries, uint32_t query_dim, uint32_t nq,
                                         uint32_t k, uint32_t ef, uint8_t metric, const uint64_t* d_visible,
                                         uint64_t* d_out_row_ids, uint32_t* d_out_node_ids, float* d_out_dist,
@@ -602,6 +622,13 @@ static int32_t search_batch_device_impl(turdb_cuda_index* idx, const float* d_qu
   const uint32_t budget = (uint32_t)idx->max_smem_optin;
   const uint64_t nn = idx->ix.n;
   const bool filt = d_visible != nullptr;
+  uint32_t g4w = 0;
+#if TURDB_GATHER4
+  if (!sq8 && ds <= 4 * 232) {
+    if (int32_t rc = ensure_row_map(idx); rc != TURDB_OK) return rc;
+    g4w = idx->g4_boxw;
+  }
+#endif
   uint32_t slots = ts, segs = tg;
   if (sq8) {
     // code rows are short (dim + 8 B) but cost ~10 instructions per element pair to decode with the reference's
@@ -622,7 +649,7 @@ static int32_t search_batch_device_impl(turdb_cuda_index* idx, const float* d_qu
     for (uint32_t cg = tg ? tg : 1; cg <= (tg ? tg : 8); ++cg) {
       uint32_t best_occ = 0;
       for (uint32_t cs = ts ? ts : 8; cs <= (ts ? ts : 32); cs += 8) {
-        TeamLayout L = make_layout(dim, ds, ef, hash_bits, cs, cg, false, nn, filt, sq8 ? idx->sq8_row_bytes : 0);
+        TeamLayout L = make_layout(dim, ds, ef, hash_bits, cs, cg, false, nn, filt, sq8 ? idx->sq8_row_bytes : 0, g4w);
         if (L.n_segs != cg || L.team_bytes > budget) continue;
         if (cg > 1 && L.seg_steps * 32 < 512) continue;
         const uint32_t occ = std::min(8u, sm_bytes / (L.team_bytes + 1024));
@@ -640,7 +667,7 @@ static int32_t search_batch_device_impl(turdb_cuda_index* idx, const float* d_qu
     segs = bg;
   }
   const uint32_t rb8 = sq8 ? idx->sq8_row_bytes : 0;
-  TeamLayout lay = make_layout(dim, ds, ef, hash_bits, slots, segs, false, nn, filt, rb8);
+  TeamLayout lay = make_layout(dim, ds, ef, hash_bits, slots, segs, false, nn, filt, rb8, g4w);
   // Team size: warp 0 leads (control flow + speculative preparation of the next hop), the others gather and
   // reduce; every warp takes a share of a hop's bulk-copy issue.  Resident queries per SM come first (the
   // kernel is latency-bound: 1M x 128, 8 queries of 2 warps beat 7 of 3 and 5 of 4, measured); among equal
@@ -651,11 +678,11 @@ static int32_t search_batch_device_impl(turdb_cuda_index* idx, const float* d_qu
     warps = 4;
   }
   while (lay.team_bytes > budget && lay.n_segs < 16 && lay.seg_steps > 8)
-    lay = make_layout(dim, ds, ef, hash_bits, lay.n_groups * 8, lay.n_segs + 1, false, nn, filt, rb8);
+    lay = make_layout(dim, ds, ef, hash_bits, lay.n_groups * 8, lay.n_segs + 1, false, nn, filt, rb8, g4w);
   while (lay.team_bytes > budget && lay.n_groups > 1)
-    lay = make_layout(dim, ds, ef, hash_bits, lay.n_groups * 8 - 8, lay.n_segs, false, nn, filt, rb8);
+    lay = make_layout(dim, ds, ef, hash_bits, lay.n_groups * 8 - 8, lay.n_segs, false, nn, filt, rb8, g4w);
   while (lay.team_bytes > budget && hash_bits > 8)
-    lay = make_layout(dim, ds, ef, --hash_bits, lay.n_groups * 8, lay.n_segs, false, nn, filt, rb8);
+    lay = make_layout(dim, ds, ef, --hash_bits, lay.n_groups * 8, lay.n_segs, false, nn, filt, rb8, g4w);
   if (lay.team_bytes > budget)
     return fail(TURDB_ERR_UNSUPPORTED, "dim %u / ef %u need %u B of shared memory per query (> %u)", idx->ix.dim, ef, lay.team_bytes, budget);
 
@@ -682,6 +709,7 @@ static int32_t search_batch_device_impl(turdb_cuda_index* idx, const float* d_qu
   a.vis_words = 0;
   a.dbg = idx->d_dbg;
   a.visible = d_visible;
+  a.row_map = lay.g4_pieces ? idx->d_row_map : nullptr;
   a.rows = sq8 ? idx->d_arena_sq8 : reinterpret_cast<const uint8_t*>(idx->d_arena);
   a.row_bytes = lay.vec_bytes;
   if (sq8) a.ix.norm2 = idx->d_norm2_sq8;  // cosine's norm_b chain runs over the decoded row
@@ -726,7 +754,7 @@ static int32_t search_batch_device_impl(turdb_cuda_index* idx, const float* d_qu
   // exact fallback for queries whose shared visited table filled: same kernel, one bit per node in
   // global memory.  Always enqueued (no host sync); exits immediately when the list is empty.
   {
-    TeamLayout glay = make_layout(dim, ds, ef, 8, lay.n_groups * 8, lay.n_segs, true, nn, filt, rb8);
+    TeamLayout glay = make_layout(dim, ds, ef, 8, lay.n_groups * 8, lay.n_segs, true, nn, filt, rb8, g4w);
     SearchArgs b = a;
     b.lay = glay;
     b.work_counter = d_scratch + 2;
@@ -894,5 +922,28 @@ extern "C" int32_t turdb_cuda_index_gather_probe(turdb_cuda_index* idx, uint32_t
 
 // exact path + merge entry points live in exact_search.cuh / below
 #include "exact_abi.inl"
+
+// The arena as a 2-D FP32 tensor [n][ds] with box {boxw, 1} for TMA tile::gather4 (team_distances_g4).  boxw == 8 (mod
+// 32) floats keeps the four rows of a piece 32 B apart modulo 128 B in shared memory; <= 4 pieces per row.
+[[maybe_unused]] static int32_t ensure_row_map(turdb_cuda_index* idx) {
+  std::lock_guard<std::mutex> lk(idx->mu);
+  if (idx->d_row_map || idx->ix.n == 0) return TURDB_OK;
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return fail(TURDB_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  const uint32_t ds = idx->ix.ds, pieces = (ds + 231) / 232, need = (ds + pieces - 1) / pieces;
+  const uint32_t boxw = need <= 8 ? 8 : ((need - 8 + 31) / 32) * 32 + 8;
+  CUtensorMap map;
+  cuuint64_t dims[2] = {ds, idx->ix.n};
+  cuuint64_t strides[1] = {(cuuint64_t)ds * 4};
+  cuuint32_t box[2] = {boxw, 1};
+  cuuint32_t estr[2] = {1, 1};
+  if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, idx->d_arena, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return fail(TURDB_ERR_CUDA, "cuTensorMapEncodeTiled failed for the arena (ds %u, box %u)", ds, boxw);
+  CUDA_TRY(cudaMalloc(&idx->d_row_map, sizeof(CUtensorMap)));
+  CUDA_TRY(cudaMemcpy(idx->d_row_map, &map, sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+  idx->g4_boxw = boxw;
+  return TURDB_OK;
+}
 #include "sql_topk.inl"
 #include "hnsw_file.inl"
