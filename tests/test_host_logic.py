@@ -157,3 +157,14 @@ def test_partitioned_builder_keeps_structure():
     assert (a["l0_adj"][valid] < n).all() and (a["l0_adj"][~valid] == 0xFFFFFFFF).all()
     assert not (a["l0_adj"] == np.arange(n, dtype=np.uint32)[:, None]).any()  # no self loops
     assert a["levels"][a["entry"]] == a["max_level"]
+
+
+def test_bench_rank0_only_section_issues_no_collectives():
+    """bench.py keeps rank 0's GPU busy a little longer for the clock sampler; that rank-0-only section once called
+    the sharded step (all-gather) and deadlocked every N>1 run.  It may only launch rank-local work."""
+    import os
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")).read()
+    block = src[src.index("keep the GPU under the same load"):src.index("clocks = sampler.stop()")]
+    assert "local_search(" in block
+    for forbidden in ("step(", "sharded.", "dist.", "barrier("):
+        assert forbidden not in block, forbidden
