@@ -3,26 +3,29 @@
 // beam_search src/hnsw/search.rs:311-350).
 //
 // One CTA ("team" of W warps) owns one query at a time; CTAs are persistent and pull queries from an
-// atomic counter.  Warp 0 (the leader) runs the reference's control flow on one sorted ef-slot list;
-// per hop it
-//   (1) picks the closest unexpanded entry of the list (== candidates.pop() that passes d <= worst),
-//   (2) takes that node's 32-wide adjacency row (one coalesced 128 B load, usually already fetched
-//       speculatively during the previous hop),
-//   (3) filters it through an exact visited set in shared memory,
+// atomic counter.  Warp 0 (the leader) runs the reference's control flow on one sorted ef-slot list and stays
+// out of the data path; warps 1..W-1 (helpers) gather and reduce.  Per hop the leader
+//   (1) picks the closest unexpanded entry of the list (== candidates.pop() that passes d <= worst) and the
+//       runner-up,
+//   (2) if the runner-up of the PREVIOUS hop is this hop's node (81 % of hops), finds its unvisited neighbours
+//       already filtered: while the helpers gathered the previous hop, the leader took the runner-up's adjacency
+//       row and ran it through the exact visited set in shared memory as if it were this hop; on a miss the
+//       speculative keys are taken back (visited_undo restores the table exactly) and the row is filtered now,
 // then ALL warps of the team
-//   (4) gather the unvisited neighbour vectors with one TMA bulk copy each (cp.async.bulk -> shared
-//       memory staging, mbarrier completion), chunks of 8 vectors dealt round-robin to the warps, and
-//   (5) reduce distances in the reference's AVX2 lane order (bit-identical values),
+//   (3) issue one TMA bulk copy per unvisited neighbour vector (cp.async.bulk -> shared memory staging,
+//       mbarrier completion); vectors that do not fit the first round are prefetched into L2 meanwhile,
+// the helpers
+//   (4) reduce distances in the reference's AVX2 lane order (bit-identical values), chunks of 8 vectors each,
 // and the leader
-//   (6) merges the <=32 new (distance, id) pairs into the sorted list by rank counting.
+//   (5) merges the <=32 new (distance, id) pairs into the sorted list by rank counting, in place.
 //
 // Single-list equivalence with the reference's two heaps: SURVEY.md Appendix D / DESIGN.md §5.
 #pragma once
 
 #include "common.cuh"
 
-// 0: double-buffered list merge (2 x 8 B x ef of shared memory); 1: in-place merge (half the list memory,
-// one more warp sync per 32 entries).  Measured on 1M x 384: see DESIGN.md.
+// 0: double-buffered list merge (2 x 8 B x ef of shared memory); 1: in-place merge in register batches (half the
+// list memory — what lets 5 queries stay resident per SM at dim 384 — and, batched, also the faster one).
 #ifndef TURDB_MERGE_MODE
 #define TURDB_MERGE_MODE 1
 #endif
@@ -149,7 +152,7 @@ struct Team {
 };
 
 // Every warp of the team calls this between the two team barriers of a request: chunk c (candidates
-// 8c..8c+7) uses staging group c % G and is handled by warp (c % G) % W.  A chunk's vectors stream through
+// 8c..8c+7) uses staging group c % G and is handled by that group's owner (Team::owns).  A chunk's vectors stream through
 // their slots in n_segs pieces; a warp keeps one piece of every group it owns in flight, reduces a piece as
 // soon as it lands and immediately requests the next one (of the same chunk, or the first piece of the next
 // chunk mapped to that group).
@@ -282,7 +285,7 @@ __device__ __forceinline__ void team_distances_whole(const DeviceIndex& ix, Team
   }
 }
 
-// Whole-vector form with per-thread async copies: chunk c is copied AND reduced by warp (c % G) % W, so a
+// Whole-vector form with per-thread async copies: chunk c is copied AND reduced by its group's owner, so a
 // warp only ever waits on its own commit groups; a warp that owns several staging groups keeps one chunk
 // in flight in each.
 template <int METRIC>
