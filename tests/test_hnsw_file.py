@@ -209,3 +209,19 @@ def test_vector_literal_parser():
     assert parse_vector_literal(" [0.1, 2,-3.5e-1] ").tolist() == [np.float32(0.1), 2.0, np.float32(-0.35)]
     with pytest.raises(ValueError):
         parse_vector_literal("0.1, 0.2")
+
+
+def test_vector_topk_planner_rule():
+    from turdb_b200.sql_operator import VectorOp, plan_vector_topk
+    # the statements of the reference's own k-NN tests (tests/hnsw_integration.rs:229, 249, 269)
+    p = plan_vector_topk("SELECT id, name FROM embeddings ORDER BY vec <-> '[0.1, 0.1, 0.1, 0.1]' LIMIT 2")
+    assert p["table"] == "embeddings" and p["column"] == "vec" and p["op"] == VectorOp.L2Distance
+    assert p["limit"] == 2 and p["offset"] == 0 and p["projection"] == ["id", "name"] and p["literal"].tolist() == [np.float32(0.1)] * 4
+    p = plan_vector_topk("select id from embeddings order by vec <=> '[0.5,0.5]' limit 3 offset 4;")
+    assert p["op"] == VectorOp.CosineDistance and (p["limit"], p["offset"]) == (3, 4)
+    # not rewritten: <#> is a NULL sort key in the reference, DESC asks for the farthest rows, WHERE changes the input
+    assert plan_vector_topk("SELECT id FROM t ORDER BY vec <#> '[1,2]' LIMIT 5") is None
+    assert plan_vector_topk("SELECT id FROM t ORDER BY vec <-> '[1,2]' DESC LIMIT 5") is None
+    assert plan_vector_topk("SELECT id FROM t WHERE id > 3 ORDER BY vec <-> '[1,2]' LIMIT 5") is None
+    assert plan_vector_topk("SELECT id FROM t ORDER BY vec <-> '[1,2]', id LIMIT 5") is None
+    assert plan_vector_topk("SELECT id FROM t ORDER BY id LIMIT 5") is None

@@ -90,3 +90,38 @@ class VectorTopKExec:
 
     def close(self):
         self._result = None
+
+
+# ---- the planner rule (mirror of where the reference turns Limit(Sort(..)) into TopKExec, -------------------------
+# src/sql/planner/convert.rs:348-397): a statement whose ORDER BY is `column <op> vector-literal` followed by LIMIT
+# [OFFSET] is rewritten to the vector-scan operator; anything else keeps the stock plan (None).
+import re as _re
+
+_VECTOR_TOPK = _re.compile(
+    r"""^\s*SELECT\s+(?P<proj>.+?)\s+FROM\s+(?P<table>[A-Za-z_][\w.]*)\s+
+        ORDER\s+BY\s+(?P<col>[A-Za-z_][\w.]*)\s*(?P<op><->|<=>|<\#>)\s*'(?P<lit>\[[^']*\])'\s*(?P<dir>ASC|DESC)?\s+
+        LIMIT\s+(?P<limit>\d+)(?:\s+OFFSET\s+(?P<offset>\d+))?\s*;?\s*$""",
+    _re.IGNORECASE | _re.VERBOSE | _re.DOTALL)
+
+_OPS = {"<->": VectorOp.L2Distance, "<=>": VectorOp.CosineDistance, "<#>": VectorOp.InnerProduct}
+
+
+def plan_vector_topk(sql: str):
+    """`SELECT .. FROM t ORDER BY col <op> '[..]' LIMIT k [OFFSET o]` -> dict(table, column, op, literal, limit, offset,
+    projection) for VectorTopKExec, or None when the rule does not apply: a WHERE / JOIN / GROUP BY (the scan below the
+    sort is not the bare table), a descending order (the k FARTHEST rows), a second sort key, or `<#>` — a NULL sort key
+    in the reference (src/sql/executor.rs:241), which must keep the stock TopK to stay result-compatible."""
+    m = _VECTOR_TOPK.match(sql)
+    if not m:
+        return None
+    if (m.group("dir") or "ASC").upper() == "DESC":
+        return None
+    op = _OPS[m.group("op")]
+    if op == VectorOp.InnerProduct:
+        return None
+    try:
+        lit = parse_vector_literal(m.group("lit"))
+    except ValueError:
+        return None
+    return dict(table=m.group("table"), column=m.group("col"), op=op, literal=lit, limit=int(m.group("limit")),
+                offset=int(m.group("offset") or 0), projection=[c.strip() for c in m.group("proj").split(",")])
