@@ -322,22 +322,17 @@ def main():
     L = _lib.load()
     import ctypes as C
 
-    def e2e_step(i):
-        rc = L.turdb_cuda_search_batch(idx._h, C.cast(hq[i % nb].data_ptr(), C.POINTER(C.c_float)), args.dim, nq, k, ef,
-                                       int(DistanceFunction.Cosine), None,
-                                       C.cast(h_rows.data_ptr(), C.POINTER(C.c_uint64)), None,
-                                       C.cast(h_dd.data_ptr(), C.POINTER(C.c_float)),
-                                       C.cast(h_cnt.data_ptr(), C.POINTER(C.c_uint32)), None)
-        assert rc == 0, _lib.last_error()
-        if world > 1:  # merge across shards: copies back to the device are part of the step
-            rows.copy_(h_rows, non_blocking=True)
-            dd.copy_(h_dd, non_blocking=True)
-            cnt.copy_(h_cnt, non_blocking=True)
-            e2e_sharded.search_batch(None)
-            h_rows.copy_(m_rows, non_blocking=True)
-            torch.cuda.synchronize()
+    # N>1: the step is H2D of the query batch -> per-shard search -> NCCL all-gather -> merge -> D2H of the merged top-k
+    dq_e2e = torch.empty((nq, args.dim), dtype=torch.float32, device=dev)
 
-    e2e_sharded = ShardedSearch(dist, world, lambda _q: (rows, dd, cnt), merge)
+    def e2e_step_sharded(i):
+        dq_e2e.copy_(hq[i % nb], non_blocking=True)
+        sharded.search_batch(dq_e2e)
+        h_rows.copy_(m_rows, non_blocking=True)
+        h_dd.copy_(m_dd, non_blocking=True)
+        h_cnt.copy_(m_cnt, non_blocking=True)
+        torch.cuda.synchronize()
+
     # N=1: two host threads issue alternate batches through the same call.  The ABI is re-entrant (every call owns a
     # stream and its scratch), so one caller's H2D/D2H copies overlap the other's kernel — what a multi-connection
     # host does.  N>1 keeps one caller per rank: the merge's collectives must be issued in one order on all ranks.
@@ -358,7 +353,7 @@ def main():
     def e2e_run(first, count):
         if e2e_callers == 1:
             for i in range(first, first + count):
-                e2e_step(i)
+                e2e_step_sharded(i)
             return
         def worker(b):
             for i in range(first + b, first + count, e2e_callers):
