@@ -43,3 +43,19 @@ def test_no_cpu_fallback_in_product_package():
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{f} imports the oracle"
                 assert "libturdb_oracle" not in text and "hnsw_oracle" not in text, f"{f} links the oracle"
+
+
+def test_sass_shows_the_blackwell_native_paths():
+    """SASS evidence (B200_PROFILING.md): tcgen05.mma -> UTC*MMA, tcgen05.ld -> LDTM, TMA tensor loads -> UTMALDG, bulk
+    copies / prefetch of the traversal -> UBLKCP / UBLKPF; the library is built for sm_100a only."""
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        import pytest
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([exe, "-sass", _lib.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    assert "sm_100a" in out
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UBLKCP", "UBLKPF", "FFMA2"):
+        assert mnemonic in out, f"{mnemonic} missing from the SASS of libturdb_cuda.so"
+    assert "HGMMA" not in out and "HMMA." not in out  # no Hopper wgmma, no legacy mma.sync tensor path
