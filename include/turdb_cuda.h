@@ -30,12 +30,14 @@
 extern "C" {
 #endif
 
-#define TURDB_CUDA_ABI_VERSION 1u
+#define TURDB_CUDA_ABI_VERSION 2u
 
 #define TURDB_MAX_L0_NEIGHBORS 32u    /* src/hnsw/mod.rs:126 */
 #define TURDB_MAX_LEVEL_NEIGHBORS 16u /* src/hnsw/mod.rs:127 */
 #define TURDB_INVALID_NODE 0xFFFFFFFFu /* NodeId::none(), src/hnsw/mod.rs:161-166 */
 #define TURDB_INVALID_ROW 0xFFFFFFFFFFFFFFFFull
+#define TURDB_SQL_MAX_LIMIT_PLUS_OFFSET 512u /* turdb_cuda_sql_topk_batch: limit + offset */
+#define TURDB_EXACT_MAX_K 1024u              /* turdb_cuda_bruteforce_topk: k */
 
 enum turdb_metric { TURDB_METRIC_L2 = 0, TURDB_METRIC_COSINE = 1, TURDB_METRIC_IP = 2 };
 
@@ -129,13 +131,15 @@ int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const float* d_que
  * SQ8Vector::decode does (min + q * scale, :108-113) and fed to the same distance chains, so its results equal
  * the FP32 search over the decoded vectors bit for bit while it gathers dim + 8 instead of 4 dim bytes per
  * distance.  The reference declares SQ8 but never wires it into the index, so that equality is
- * the parity contract.  Distances returned are distances to the DECODED vectors.  No filtered variant.
+ * the parity contract.  Distances returned are distances to the DECODED vectors.  d_visible (nullable) as in
+ * search_batch_device: search_filtered over the code arena.
  */
 int32_t turdb_cuda_index_enable_sq8(turdb_cuda_index* idx, uint8_t* out_rows, uint64_t out_capacity,
                                     uint32_t* out_row_bytes);
 int32_t turdb_cuda_search_batch_sq8_device(turdb_cuda_index* idx, const float* d_queries,
                                            uint32_t query_dim, uint32_t nq, uint32_t k, uint32_t ef,
-                                           uint8_t metric, uint64_t* d_out_row_ids,
+                                           uint8_t metric, const uint64_t* d_visible,
+                                           uint64_t* d_out_row_ids,
                                            uint32_t* d_out_node_ids, float* d_out_dist,
                                            uint32_t* d_out_counts,
                                            turdb_cuda_search_stats* d_out_stats, void* stream);
@@ -145,6 +149,11 @@ int32_t turdb_cuda_search_batch_sq8_device(turdb_cuda_index* idx, const float* d
  * shared-memory visited table, segments = pieces a vector is streamed in through its staging slot. */
 int32_t turdb_cuda_index_set_tuning(turdb_cuda_index* idx, uint32_t warps_per_cta,
                                     uint32_t staging_slots, uint32_t hash_bits, uint32_t segments);
+
+/* Form of the traversal kernel: 0 automatic (by row length), 1 staged (a team of 2-4 warps per query, rows through
+ * shared-memory staging by TMA bulk copies — long rows), 2 direct (one warp per query, rows gathered straight into
+ * registers — short rows; FP32 arena only).  Results are identical in every form. */
+int32_t turdb_cuda_index_set_traversal_form(turdb_cuda_index* idx, uint32_t form);
 
 /*
  * ---- measurement: per-launch device times of the traversal kernel --------------------------
@@ -172,9 +181,13 @@ int32_t turdb_cuda_index_gather_probe(turdb_cuda_index* idx, uint32_t ctas_per_s
 /*
  * ---- exact path: the SQL `ORDER BY vec <op> q LIMIT k` scan (TopKExec, ---------------------
  * src/sql/executor.rs:2239-2392 with the distance of :169-212) over the index's arena.
- * Tensor-core dot-product pass keeping rerank_factor*k candidates per query, then an FP32 rerank in
- * the reference's lane order.  Distances follow the HNSW metric contract above (squared L2 /
- * 1-cos / -dot), NOT the SQL sqrt form; the host operator applies sqrt when it projects the value.
+ * Tensor-core (BF16) dot-product pass used as a CERTIFIED filter, then an FP32 rerank in the reference's lane
+ * order: a row is dropped only when its score lies below the (rerank_factor*k)-th best score so far by more than
+ * twice a bound on the BF16 score error (from the operands' actual rounding-error norms), so no row of the exact
+ * FP32 top-k can be lost; a query whose candidate buffer overflows is redone by a plain FP32 scan kernel.
+ * Result = top-k by (FP32 distance, node id).  Distances follow the HNSW metric contract above (squared L2 /
+ * 1-cos / -dot), NOT the SQL sqrt form.  k <= TURDB_EXACT_MAX_K; rerank_factor 0 = 4; k*rerank_factor is clamped
+ * to 2048.  Absent vectors (+inf rows) evaluate to +inf.
  */
 int32_t turdb_cuda_bruteforce_topk(turdb_cuda_index* idx, const float* queries, uint32_t query_dim,
                                    uint32_t nq, uint32_t k, uint8_t metric, uint32_t rerank_factor,
@@ -193,22 +206,33 @@ int32_t turdb_cuda_bruteforce_topk_device(turdb_cuda_index* idx, const float* d_
  * src/sql/executor.rs:2239-2392) when order_by[0] is Column <op> literal: one call = nq statements against
  * the same table.  op 0 = `<->` (key sqrt(sum_f64((a-b)_f32^2))), 1 = `<=>` (key 1 - dot/(|a||b|) in f64, NULL
  * when a norm is zero): executor.rs:169-212.  `<#>` is rejected with TURDB_ERR_UNSUPPORTED — the reference
- * evaluates it to NULL for every row there (executor.rs:241).  Keys are the reference's f64 values, computed
- * in its summation order for the candidate rows the FP32 exact path (or, use_index != 0, the HNSW traversal
- * with ef) selects; rows ascend by (key, scan position == dense node id), NULL keys last, as a NaN key.
- * out_* are [nq][limit]; out_counts[q] = rows returned.  The exact scan certifies that no row outside its
- * candidate window can precede the (limit+offset)-th key; the host entry widens the window and retries, the
- * _device entry reports an uncertified statement as out_counts[q] == 0xFFFFFFFD (margin 0 = default).
+ * evaluates it to NULL for every row there (executor.rs:241).
+ *
+ * Result = the reference's, row for row: its heap procedure (first limit+offset rows pushed and stably sorted worst
+ * first, a later row replaces the root iff STRICTLY smaller, left child preferred in the sift-down, final stable
+ * ascending sort, :2248-2378) is replayed over a superset of the rows it would ever have pushed, in primary-key
+ * (= dense node id) order, with keys in its f64 arithmetic and summation order — so equal keys come back in the
+ * order the reference leaves them in.  The superset comes from the certified tensor-core filter (exact scan:
+ * BF16 scores, threshold widened by a bound on the score error; a statement whose candidate buffers overflow — e.g.
+ * thousands of rows tying with the limit-th key — is redone by a kernel that runs the reference's loop over every
+ * row) or, use_index != 0, from the HNSW traversal's ef (>= limit+offset, <= 2048) best rows.  Order among NULL
+ * keys is unspecified.  limit + offset <= TURDB_SQL_MAX_LIMIT_PLUS_OFFSET.
+ *
+ * out_* are [nq][limit]; out_counts[q] = rows returned; the rest is TURDB_INVALID_ROW / NaN.  out_proj (nullable)
+ * receives the value `SELECT vec <proj_op> '[...]'` projects for each returned row (src/sql/predicate.rs:1634-1688:
+ * f32, sequential; 0 `<->` sqrt(sum (a-b)^2), 1 `<=>` 1 - dot/(|a||b|) or NULL (NaN) on a zero norm, 2 `<#>` +dot),
+ * widened to f64 as Value::Float holds it.
  */
 int32_t turdb_cuda_sql_topk_batch(turdb_cuda_index* idx, const float* queries, uint32_t query_dim,
-                                  uint32_t nq, uint32_t limit, uint32_t offset, uint8_t op,
+                                  uint32_t nq, uint32_t limit, uint32_t offset, uint8_t op, uint8_t proj_op,
                                   int32_t use_index, uint32_t ef, uint64_t* out_row_ids,
-                                  double* out_keys, uint32_t* out_counts);
+                                  double* out_keys, double* out_proj, uint32_t* out_counts);
 int32_t turdb_cuda_sql_topk_batch_device(turdb_cuda_index* idx, const float* d_queries,
                                          uint32_t query_dim, uint32_t nq, uint32_t limit,
-                                         uint32_t offset, uint8_t op, uint32_t margin,
+                                         uint32_t offset, uint8_t op, uint8_t proj_op,
                                          int32_t use_index, uint32_t ef, uint64_t* d_out_row_ids,
-                                         double* d_out_keys, uint32_t* d_out_counts, void* stream);
+                                         double* d_out_keys, double* d_out_proj,
+                                         uint32_t* d_out_counts, void* stream);
 
 /*
  * ---- multi-GPU: merge of per-shard top-k after the all-gather (one sub-index per GPU) --------

@@ -233,7 +233,7 @@ class VectorTopKExec {
       std::vector<double> keys(rows.size());
       uint32_t count = 0;
       check(turdb_cuda_sql_topk_batch(index_.handle(), literal_.data(), (uint32_t)literal_.size(), 1, limit_, offset_,
-                                      (uint8_t)op_, use_index_ ? 1 : 0, ef_, rows.data(), keys.data(), &count));
+                                      (uint8_t)op_, 0, use_index_ ? 1 : 0, ef_, rows.data(), keys.data(), nullptr, &count));
       for (uint32_t i = 0; i < count; ++i) result_.emplace_back(rows[i], keys[i]);
       computed_ = true;
     }

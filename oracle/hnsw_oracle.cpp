@@ -725,7 +725,14 @@ int tdo_search_batch(const tdo_graph* gp, const float* queries, uint32_t query_d
         tdo_stats st{0, 0, 0, 0};
         uint32_t cnt = 0;
         if (g.entry != TDO_INVALID) {  // mod.rs:1106-1109
-          auto dist = [&](uint32_t n) { return metric_distance(metric, q, g.v(n), g.dim); };
+          // compute_distance, mod.rs:1111-1121: get_vector(row_id) -> None (and an unreadable node) => f32::INFINITY,
+          // whatever the metric.  In the flattened arrays an absent vector is a row whose elements are +inf
+          // (the uploader's convention, turdb_cuda_hnsw_file_upload).
+          auto dist = [&](uint32_t n) {
+            const float* v = g.v(n);
+            if (g.dim && v[0] == std::numeric_limits<float>::infinity()) return std::numeric_limits<float>::infinity();
+            return metric_distance(metric, q, v, g.dim);
+          };
           uint32_t cur = g.entry;
           float cur_d = dist(cur);
           st.n_dist += 1;

@@ -21,7 +21,7 @@ def test_every_declared_symbol_is_exported():
     for n in names:
         assert hasattr(L, n), f"{n} declared in turdb_cuda.h but not exported"
     assert set(names) == set(_lib.EXPORTS), set(names) ^ set(_lib.EXPORTS)
-    assert L.turdb_cuda_abi_version() == 1
+    assert L.turdb_cuda_abi_version() == 2
 
 
 def test_errors_without_device_or_arguments():

@@ -79,3 +79,42 @@ def test_exact_recall_against_sql_scan(gpu_required):
     rec = np.mean([len(set(nodes[i].tolist()) & set(srows[i].tolist())) / 10 for i in range(len(q))])
     assert rec >= 0.999
     idx.close()
+
+
+def test_rows_closer_than_bf16_resolution_are_not_lost(gpu_required):
+    """Adversarial for the BF16 filter: 600 rows within 1e-4 (relative) of one another around the query — far below
+    BF16's 2^-8 resolution, so their filter keys collapse — among 6000 ordinary rows.  The certified filter widens its
+    threshold by the score-error bound, so the FP32 rerank must still return exactly the reference's top-k."""
+    rng = np.random.default_rng(0)
+    dim, n = 96, 6000
+    x = ds.gaussian_latent(n, dim, seed=21, normalise=False)
+    centre = x[17].copy()
+    near = rng.choice(np.arange(100, n), 600, replace=False)
+    x[near] = centre * (1.0 + 1e-4 * rng.standard_normal((600, 1)).astype(np.float32)) \
+        + 1e-4 * rng.standard_normal((600, dim)).astype(np.float32)
+    q = np.stack([centre * (1.0 + 1e-4 * rng.standard_normal()) + 1e-4 * rng.standard_normal(dim).astype(np.float32)
+                  for _ in range(24)]).astype(np.float32)
+    idx = CudaHnswIndex.from_graph(flat_graph(x))
+    for metric in (ob.L2, ob.COSINE, ob.IP):
+        for k, rf in ((10, 4), (10, 1), (50, 2)):
+            rows, nodes, dist, cnt = idx.bruteforce_topk(q, k, DistanceFunction(metric), rerank_factor=rf)
+            ref_ids, ref_d = exact_reference(x, q, k, metric)
+            assert np.array_equal(dist.view(np.uint32), ref_d.view(np.uint32)), (metric, k, rf)
+            assert np.array_equal(nodes, ref_ids), (metric, k, rf)
+    idx.close()
+
+
+def test_mass_duplicates_fall_back_to_the_scan(gpu_required):
+    """3000 identical rows tie at distance 0: more equal keys than the candidate buffer holds.  The flagged queries are
+    redone by the streaming FP32 scan; ties order by node id."""
+    dim, n = 64, 8000
+    x = ds.gaussian_latent(n, dim, seed=5, normalise=False)
+    dup = np.arange(1000, 4000)
+    x[dup] = x[999]
+    q = np.concatenate([x[999:1000], ds.gaussian_latent(7, dim, seed=6, normalise=False)])
+    idx = CudaHnswIndex.from_graph(flat_graph(x))
+    for metric in (ob.L2, ob.COSINE):
+        rows, nodes, dist, cnt = idx.bruteforce_topk(q, 20, DistanceFunction(metric))
+        ref_ids, ref_d = exact_reference(x, q, 20, metric)
+        assert np.array_equal(nodes, ref_ids) and np.array_equal(dist.view(np.uint32), ref_d.view(np.uint32))
+    idx.close()

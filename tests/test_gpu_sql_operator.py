@@ -83,3 +83,58 @@ def test_index_backed_scan_agrees_on_a_good_graph(gpu_required, small_graph):
     assert agree >= 0.97
     same = exact[0] == approx[0]
     assert np.array_equal(exact[1][same].view(np.uint64), approx[1][same].view(np.uint64))
+
+
+def test_tied_keys_come_back_in_the_reference_heap_order(gpu_required):
+    """Integer-valued vectors: many exactly equal keys inside and across the LIMIT boundary.  Which of them survive and
+    in which order follows from the reference's heap procedure (executor.rs:2248-2378) — replayed on the device."""
+    rng = np.random.default_rng(3)
+    x = rng.integers(0, 4, (5000, 6)).astype(np.float32)
+    q = rng.integers(0, 4, (40, 6)).astype(np.float32)
+    idx = table_index(x)
+    for op, oop in ((VectorOp.L2Distance, ob.L2), (VectorOp.CosineDistance, ob.COSINE)):
+        for limit, offset in ((10, 0), (7, 5), (1, 0), (100, 20), (300, 212)):
+            rows, keys, counts = VectorScanBatch(idx, op, limit, offset).execute(q)
+            o_rows, o_keys, o_counts = ob.sql_topk(x, q, limit, op=oop, offset=offset, n_threads=8)
+            assert np.array_equal(counts, o_counts)
+            ok = ~np.isnan(o_keys)
+            assert np.array_equal(np.isnan(keys), np.isnan(o_keys))
+            assert np.array_equal(keys[ok].view(np.uint64), o_keys[ok].view(np.uint64))
+            nn = np.array([not np.isnan(o_keys[i]).any() for i in range(len(q))])  # NULL keys: order unspecified
+            assert np.array_equal(rows[nn], o_rows[nn].astype(np.uint64)), (op, limit, offset)
+    idx.close()
+
+
+def test_thousands_of_rows_tying_with_the_limit_th_key(gpu_required):
+    """4000 duplicates of the nearest row: the filter's buffers overflow and the statement is redone by the kernel that
+    runs the reference's loop over every row — same rows, same order, no error."""
+    x = ds.gaussian_latent(9000, 32, seed=41)
+    x[500:4500] = x[499]
+    q = np.concatenate([x[499:500] + 1e-3, ds.gaussian_latent(5, 32, seed=42)])
+    idx = table_index(x)
+    for limit, offset in ((10, 0), (25, 10)):
+        rows, keys, counts = VectorScanBatch(idx, VectorOp.L2Distance, limit, offset).execute(q)
+        o_rows, o_keys, o_counts = ob.sql_topk(x, q, limit, op=ob.L2, offset=offset, n_threads=8)
+        assert np.array_equal(counts, o_counts) and np.array_equal(rows, o_rows.astype(np.uint64))
+        assert np.array_equal(keys.view(np.uint64), o_keys.view(np.uint64))
+    idx.close()
+
+
+@pytest.mark.parametrize("op,proj", [(VectorOp.L2Distance, VectorOp.L2Distance), (VectorOp.CosineDistance, VectorOp.CosineDistance),
+                                     (VectorOp.L2Distance, VectorOp.InnerProduct)])
+def test_projected_distance_matches_predicate_eval(gpu_required, op, proj):
+    """SELECT id, vec <proj> q AS d ... ORDER BY vec <op> q LIMIT 8: the projected value is the f32 sequential arithmetic of
+    src/sql/predicate.rs:1634-1688 (sqrt L2, cosine with NULL on a zero norm, +dot for <#>), bit for bit."""
+    x = ds.gaussian_latent(3000, 100, seed=51)
+    x[7] = 0.0  # zero norm: cosine projects NULL
+    q = np.concatenate([ds.gaussian_latent(30, 100, seed=52), x[7:8] + 1e-3])
+    sb = VectorScanBatch(table_index(x), op, 8, project=proj)
+    rows, keys, counts = sb.execute(q)
+    for i in range(len(q)):
+        for j in range(int(counts[i])):
+            want = ob.sql_projection_distance(int(proj), x[int(rows[i, j])], q[i])
+            got = sb.projected[i, j]
+            if want is None:
+                assert np.isnan(got)
+            else:
+                assert np.float64(want) == got, (i, j, want, got)

@@ -162,17 +162,23 @@ def test_missing_vectors_and_tombstones_rank_last(gpu_required, graph2k):
     table = {int(r): x[i] for i, r in enumerate(arrays["row_ids"])}
     idx = f.upload(get_vector=lambda r: None if r in gone else table.get(r))
     q = ds.gaussian_latent(200, 32, seed=8)
-    got = idx.search_batch(q, 10, 64, DistanceFunction.L2)
-    assert np.isfinite(got[2]).all()
     bad_rows = gone | {int(arrays["row_ids"][50]), int(arrays["row_ids"][900])}
-    assert not (set(got[0].ravel().tolist()) & bad_rows)
     # same graph arrays + same +inf rows through the oracle: identical results
     ga = f.graph()
     vec = np.stack([np.full(32, np.inf, np.float32) if (int(r) in gone or i >= f.info["n_nodes"]) else table[int(r)]
                     for i, r in enumerate(rows)])
     ga["vectors"] = vec
-    cpu = ob.OracleGraph.from_arrays(ga).search(q, 10, 64, ob.L2, n_threads=4)
-    assert np.array_equal(got[1], cpu[1]) and np.array_equal(got[2].view(np.uint32), cpu[2].view(np.uint32))
+    og = ob.OracleGraph.from_arrays(ga)
+    # the reference's closure yields INFINITY for such nodes whatever the metric (mod.rs:1111-1121): cosine and inner
+    # product must not turn the +inf row into NaN / -inf and rank it first
+    for form in (0, 1, 2):
+        idx.set_traversal_form(form)
+        for metric in (DistanceFunction.L2, DistanceFunction.Cosine, DistanceFunction.InnerProduct):
+            got = idx.search_batch(q, 10, 64, metric)
+            assert np.isfinite(got[2]).all()
+            assert not (set(got[0].ravel().tolist()) & bad_rows)
+            cpu = og.search(q, 10, 64, int(metric), n_threads=4)
+            assert np.array_equal(got[1], cpu[1]) and np.array_equal(got[2].view(np.uint32), cpu[2].view(np.uint32))
     idx.close()
 
 

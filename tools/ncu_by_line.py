@@ -6,7 +6,10 @@ rep, lib, sym = sys.argv[1:4]
 hops = float(sys.argv[4]) if len(sys.argv) > 4 else 1.0
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
-dis = subprocess.run(["nvdisasm", "-g", "-c", glob.glob(tmp + "/*.cubin")[0]], capture_output=True, text=True).stdout.split("\n")
+for cubin in sorted(glob.glob(tmp + "/*.cubin")):  # one cubin per translation unit
+    dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.split("\n")
+    if any(".section" in l and ".text." in l and sym in l for l in dis):
+        break
 start = [i for i, l in enumerate(dis) if ".section" in l and ".text." in l and sym in l][0]
 ends = [i for i, l in enumerate(dis) if i > start and ".section" in l]
 end = ends[0] if ends else len(dis)
@@ -33,7 +36,7 @@ srcs = {}
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:50]:
     f, ln = k if k else ("?", 0)
     if f not in srcs:
-        p = os.path.join(os.path.dirname(os.path.abspath(lib)), "csrc", f)
+        p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "turdb_b200", "csrc", f)
         srcs[f] = open(p).read().split("\n") if os.path.exists(p) else None
     code = srcs[f][ln - 1].strip()[:64] if srcs[f] else ""
     print("%5.1f%% samp %5.1f%% inst %7.1f inst/hop  %s:%d  %s" % (100 * v[0] / ts, 100 * v[1] / ti, v[1] / hops, f, ln, code))

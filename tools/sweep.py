@@ -28,6 +28,7 @@ ap.add_argument("--libs", default="", help="A/B: comma-separated library files; 
                 "library is measured in a child process (TURDB_CUDA_LIB)")
 ap.add_argument("--graph", default="", help="(internal) npz with a prebuilt graph")
 ap.add_argument("--sq8", action="store_true", help="traverse the SQ8 arena (enable_sq8 + search_batch_sq8_device)")
+ap.add_argument("--genkw", default="{}", help="JSON keyword arguments of the generator (clustered: corpus_n defaults to --n)")
 ap.add_argument("--probe", default="", help="gather-ceiling probe settings: ctas_per_sm,slots,cta_smem_bytes;...")
 args = ap.parse_args()
 
@@ -36,8 +37,11 @@ if args.gen == "gaussian_latent":
     x = ds.gaussian_latent(args.n, args.dim, seed=1, latent=args.latent, normalise=norm)
     q = ds.gaussian_latent(args.nq, args.dim, seed=2, latent=args.latent, normalise=norm)
 else:
-    x = ds.make(args.gen, args.n, args.dim, seed=1)
-    q = ds.make(args.gen, args.nq, args.dim, seed=2)
+    kw = json.loads(args.genkw)
+    if args.gen == "clustered":
+        kw.setdefault("corpus_n", args.n)
+    x = ds.make(args.gen, args.n, args.dim, seed=1, **kw)
+    q = ds.make(args.gen, args.nq, args.dim, seed=2, **kw)
 t = time.time()
 if args.graph:
     z = np.load(args.graph)
@@ -97,9 +101,10 @@ for pr in [p for p in args.probe.split(";") if p]:
     probes.append(dict(ctas_per_sm=c, slots=sl, cta_smem_bytes=sm, gbs=gbs, ms=ms))
     print("gather probe", probes[-1], flush=True)
 for tun in args.tunings.split(";"):
-    warps, slots, hb, segs = ([int(v) for v in tun.split(",")] + [0])[:4]
+    warps, slots, hb, segs, form = ([int(v) for v in tun.split(",")] + [0, 0])[:5]
     try:
         idx.set_tuning(warps, slots, hb, segs)
+        idx.set_traversal_form(form)
         if args.sq8:
             idx.enable_sq8()
         def run():
@@ -138,7 +143,7 @@ for tun in args.tunings.split(";"):
         rec = None
         if gt is not None:
             rec = float(np.mean([len(set(nd[i].tolist()) & set(gt[i].tolist())) / args.k for i in range(1000)]))
-        r = dict(warps=warps, slots=slots, hash_bits=hb, segs=segs, kernel_ms=ms, overflow_ms=float(om.mean()), qps=args.nq / ms * 1e3,
+        r = dict(warps=warps, slots=slots, hash_bits=hb, segs=segs, form=form, kernel_ms=ms, overflow_ms=float(om.mean()), qps=args.nq / ms * 1e3,
                  gbs=nbytes / ms / 1e6, n_dist=float(st[:, 0].mean()), n_exp=float(st[:, 2].mean()), recall=rec,
                  same_as_first=bool(np.array_equal(nd, ref_nodes)))
         print(json.dumps(r), flush=True)

@@ -42,7 +42,7 @@ GET_VECTOR_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_uint64, C.POINTER(C.c_flo
 EXPORTS = [
     "turdb_cuda_abi_version", "turdb_cuda_last_error", "turdb_cuda_device_count", "turdb_cuda_index_create",
     "turdb_cuda_index_destroy", "turdb_cuda_index_info", "turdb_cuda_search_batch", "turdb_cuda_search_batch_device",
-    "turdb_cuda_index_set_tuning", "turdb_cuda_index_profile_begin", "turdb_cuda_index_profile_read",
+    "turdb_cuda_index_set_tuning", "turdb_cuda_index_set_traversal_form", "turdb_cuda_index_profile_begin", "turdb_cuda_index_profile_read",
     "turdb_cuda_index_debug_counters", "turdb_cuda_bruteforce_topk", "turdb_cuda_bruteforce_topk_device",
     "turdb_cuda_merge_topk_device", "turdb_cuda_index_gather_probe",
     "turdb_cuda_hnsw_file_open", "turdb_cuda_hnsw_file_open_memory", "turdb_cuda_hnsw_file_close",
@@ -72,6 +72,7 @@ def load():
     L.turdb_cuda_index_destroy.argtypes = [vp]
     L.turdb_cuda_index_info.argtypes = [vp, pu64, pu32, pu32, pu32, pu64]
     L.turdb_cuda_index_set_tuning.argtypes = [vp, u32, u32, u32, u32]
+    L.turdb_cuda_index_set_traversal_form.argtypes = [vp, u32]
     L.turdb_cuda_index_debug_counters.argtypes = [vp, i32, pu64]
     L.turdb_cuda_index_profile_begin.argtypes = [vp, u32]
     L.turdb_cuda_index_profile_read.argtypes = [vp, pf, pf, u32, pu32]
@@ -83,10 +84,11 @@ def load():
     L.turdb_cuda_bruteforce_topk.argtypes = [vp, pf, u32, u32, u32, u8, u32, pu64, pu32, pf, pu32]
     L.turdb_cuda_bruteforce_topk_device.argtypes = [vp, vp, u32, u32, u32, u8, u32, vp, vp, vp, vp, vp]
     L.turdb_cuda_merge_topk_device.argtypes = [i32, vp, vp, vp, u32, u32, u32, vp, vp, vp, vp]
-    L.turdb_cuda_sql_topk_batch.argtypes = [vp, pf, u32, u32, u32, u32, u8, i32, u32, pu64, C.POINTER(C.c_double), pu32]
-    L.turdb_cuda_sql_topk_batch_device.argtypes = [vp, vp, u32, u32, u32, u32, u8, u32, i32, u32, vp, vp, vp, vp]
+    L.turdb_cuda_sql_topk_batch.argtypes = [vp, pf, u32, u32, u32, u32, u8, u8, i32, u32, pu64, C.POINTER(C.c_double),
+                                            C.POINTER(C.c_double), pu32]
+    L.turdb_cuda_sql_topk_batch_device.argtypes = [vp, vp, u32, u32, u32, u32, u8, u8, i32, u32, vp, vp, vp, vp, vp]
     L.turdb_cuda_index_enable_sq8.argtypes = [vp, pu8, u64, pu32]
-    L.turdb_cuda_search_batch_sq8_device.argtypes = [vp, vp, u32, u32, u32, u32, u8, vp, vp, vp, vp, vp, vp]
+    L.turdb_cuda_search_batch_sq8_device.argtypes = [vp, vp, u32, u32, u32, u32, u8, vp, vp, vp, vp, vp, vp, vp]
     L.turdb_cuda_shards_search_batch.argtypes = [C.POINTER(vp), u32, pf, u32, u32, u32, u32, u8, pu64, pf, pu32]
     L.turdb_cuda_hnsw_file_open.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.turdb_cuda_hnsw_file_open_memory.argtypes = [pu8, u64, C.POINTER(vp)]

@@ -151,18 +151,185 @@ static bool make_bf16_map(CUtensorMap* map, const void* base, uint64_t rows, uin
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-__global__ void exact_init_kernel(float* thresh, uint32_t* cand_cnt, uint32_t nq, uint32_t* overflow_flag) {
+__global__ void exact_init_kernel(float* thresh, uint32_t* cand_cnt, uint32_t* kept, uint32_t* qflags, uint32_t* arch_cnt,
+                                  uint32_t nq) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nq) {
     thresh[i] = -INFINITY;
     cand_cnt[i] = 0;
+    kept[i] = 0;
+    qflags[i] = 0;
+    if (arch_cnt) arch_cnt[i] = 0;
   }
-  if (i == 0) *overflow_flag = 0;
 }
 
-__global__ void exact_overflow_mark_kernel(const uint32_t* overflow_flag, uint32_t* out_counts, uint32_t nq) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (*overflow_flag && i < nq) out_counts[i] = 0xFFFFFFFFu;  // candidate buffer overflowed: result invalid
+// What the filter leaves behind for its caller (device pointers into one scratch allocation, freed by the caller).
+struct ExactFilterResult {
+  uint8_t* scr = nullptr;
+  uint32_t* cand_cnt = nullptr;  // [nq]       entries kept per query (sorted best first)
+  uint32_t* cand_id = nullptr;   // [nq][cap]
+  uint32_t cap = 0;
+};
+
+// The certified tensor-core filter (exact_search.cuh): BF16 scores over geometrically growing slices of the corpus, per
+// query threshold = kprime-th best filter key so far minus twice the score-error bound e(q) (query_slack_kernel) — a
+// rejected row's exact key lies below the exact keys of kprime admitted rows.  With an archive every arrival's id is
+// also appended to [nq][arch_cap] (the SQL operator replays them).  qflags[q] != 0: a buffer of query q overflowed.
+static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, uint32_t nq, uint32_t kprime, uint8_t metric,
+                                uint32_t cap, uint32_t first_rows, uint32_t arch_cap, uint32_t* d_arch_cnt,
+                                uint32_t* d_arch_id, uint32_t* d_qflags, ExactFilterResult* out, cudaStream_t stream) {
+  const uint64_t n = idx->ix.n;
+  const uint32_t dim = idx->ix.dim, ds = idx->ix.ds;
+  const uint32_t kp = (dim + kChunkK - 1) / kChunkK * kChunkK;
+  const uint32_t k_chunks = kp / kChunkK;
+  if (k_chunks > 32) return fail(TURDB_ERR_UNSUPPORTED, "the exact path supports dim <= 2048 (dim %u)", dim);
+  // up to 512 dims the query block (128 x K BF16) stays resident in shared memory; above, its K chunks are streamed
+  // with the vector tile's (twice the TMA traffic per tile, but any K fits)
+  const uint32_t stream_a = k_chunks > 8 ? 1u : 0u;
+
+  // BF16 copies of the arena, built once per index: raw rows (L2, IP) and rows scaled by 1/|x| (cosine), each with the
+  // maxima of its rounding-error and row norms (the inputs of the filter's error bound)
+  const int copy = metric == kCosine ? 1 : 0;
+  {
+    std::lock_guard<std::mutex> lk(idx->mu);
+    __nv_bfloat16*& dst = copy ? idx->d_arena_bf16n : idx->d_arena_bf16;
+    if (!dst) {
+      if (!idx->d_bf16_max2) {
+        CUDA_TRY(cudaMalloc(&idx->d_bf16_max2, 4 * 4));
+        CUDA_TRY(cudaMemsetAsync(idx->d_bf16_max2, 0, 4 * 4, stream));
+      }
+      CUDA_TRY(cudaMalloc(&dst, (size_t)n * kp * 2));
+      const uint64_t total = n * kp;
+      to_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(idx->d_arena, dim, ds, kp, n,
+                                                                            copy ? idx->d_norm2 : nullptr, dst);
+      bf16_rowerr_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(idx->d_arena, dim, ds, kp, n,
+                                                                                 copy ? idx->d_norm2 : nullptr, dst,
+                                                                                 idx->d_bf16_max2 + 2 * copy);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      idx->device_bytes += (size_t)n * kp * 2;
+    }
+  }
+  const __nv_bfloat16* d_xb = copy ? idx->d_arena_bf16n : idx->d_arena_bf16;
+
+  // scratch: Qb | col bias | thresh | cand_cnt | kept | slack | cand_id | cand_key
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = (off + bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  const size_t o_qb = take((size_t)nq * kp * 2), o_ab = take((size_t)n * 4), o_th = take((size_t)nq * 4),
+               o_cnt = take((size_t)nq * 4), o_kept = take((size_t)nq * 4), o_slack = take((size_t)nq * 4),
+               o_id = take((size_t)nq * cap * 4), o_key = take((size_t)nq * cap * 4);
+  uint8_t* scr = nullptr;
+  CUDA_TRY(cudaMallocFromPoolAsync(&scr, off, idx->pool, stream));
+  __nv_bfloat16* d_qb = (__nv_bfloat16*)(scr + o_qb);
+  float* d_bias = (float*)(scr + o_ab);
+  float* d_th = (float*)(scr + o_th);
+  uint32_t* d_cnt = (uint32_t*)(scr + o_cnt);
+  uint32_t* d_kept = (uint32_t*)(scr + o_kept);
+  float* d_slack = (float*)(scr + o_slack);
+  uint32_t* d_cid = (uint32_t*)(scr + o_id);
+  float* d_ckey = (float*)(scr + o_key);
+  auto bail = [&](int32_t rc) {
+    cudaFreeAsync(scr, stream);
+    return rc;
+  };
+
+  {
+    const uint64_t total = (uint64_t)nq * kp;
+    to_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_queries, dim, dim, kp, nq, nullptr, d_qb);
+    if (metric == kL2) col_bias_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(idx->d_norm2, n, d_bias);
+    exact_init_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(d_th, d_cnt, d_kept, d_qflags, d_arch_cnt, nq);
+    query_slack_kernel<<<(unsigned)(((uint64_t)nq * 32 + 255) / 256), 256, 0, stream>>>(d_queries, dim, kp, nq, d_qb,
+                                                                                         idx->d_bf16_max2 + 2 * copy, metric, d_slack);
+  }
+  CUtensorMap map_q, map_x;
+  if (!make_bf16_map(&map_q, d_qb, nq, kp) || !make_bf16_map(&map_x, d_xb, n, kp))
+    return bail(fail(TURDB_ERR_CUDA, "cuTensorMapEncodeTiled failed"));
+
+  const size_t stage_bytes = stream_a ? 2 * (size_t)kChunkBytes : (size_t)kChunkBytes;
+  const size_t fixed_smem = (stream_a ? 0 : (size_t)k_chunks * kChunkBytes) + 4 * kTileN * 4 + 4 * kRing * kTileM * 4 + 24 * 8 + 16;
+  const uint32_t n_stages = (uint32_t)std::min<size_t>(kMaxStages, ((size_t)idx->max_smem_optin - fixed_smem) / stage_bytes);
+  if (n_stages < 2) return bail(fail(TURDB_ERR_UNSUPPORTED, "not enough shared memory for the exact path at dim %u", dim));
+  const size_t gemm_smem = fixed_smem + (size_t)n_stages * stage_bytes;
+  cudaError_t e = cudaSuccess;
+  {
+    static std::mutex attr_mu;  // cudaFuncSetAttribute is process-wide state
+    std::lock_guard<std::mutex> lk(attr_mu);
+    auto set_smem = [&](auto kern, size_t bytes) {
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    };
+    set_smem(exact_gemm_filter_kernel<true, false>, (size_t)idx->max_smem_optin);
+    set_smem(exact_gemm_filter_kernel<false, false>, (size_t)idx->max_smem_optin);
+    set_smem(exact_gemm_filter_kernel<true, true>, (size_t)idx->max_smem_optin);
+    set_smem(exact_gemm_filter_kernel<false, true>, (size_t)idx->max_smem_optin);
+    set_smem(exact_threshold_kernel, (size_t)16384 * 8);
+  }
+  if (e != cudaSuccess) return bail(fail(TURDB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)));
+
+  const uint32_t n_tiles = (uint32_t)((n + kTileN - 1) / kTileN);
+  const uint32_t n_qblocks = (nq + kTileM - 1) / kTileM;
+  // first slice: every column becomes a candidate (threshold -inf), so it must fit the buffer
+  uint32_t lo = 0, span = std::max(1u, std::min(first_rows, cap / 2) / kTileN);
+  while (lo < n_tiles) {
+    const uint32_t hi = std::min(n_tiles, lo + span);
+    ExactArgs a{};
+    a.n_vec = (uint32_t)n;
+    a.nq = nq;
+    a.k_chunks = k_chunks;
+    a.n_stages = n_stages;
+    a.stream_a = stream_a;
+    a.tile_lo = lo;
+    a.tile_hi = hi;
+    const uint32_t tiles = hi - lo;
+    uint32_t tpi = (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(1, ((uint64_t)tiles * n_qblocks) / (4ull * idx->num_sms)));
+    a.tiles_per_item = tpi;
+    a.n_qblocks = n_qblocks;
+    a.n_items = n_qblocks * ((tiles + tpi - 1) / tpi);
+    a.col_bias = d_bias;
+    a.thresh = d_th;
+    a.cand_cnt = d_cnt;
+    a.cand_id = d_cid;
+    a.cand_key = d_ckey;
+    a.cap = cap;
+    a.qflags = d_qflags;
+    a.dbg = idx->d_dbg;
+    const uint32_t grid = std::min<uint32_t>(a.n_items, (uint32_t)idx->num_sms);
+    if (metric == kL2) {
+      if (stream_a) exact_gemm_filter_kernel<true, true><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
+      else exact_gemm_filter_kernel<true, false><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
+    } else {
+      if (stream_a) exact_gemm_filter_kernel<false, true><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
+      else exact_gemm_filter_kernel<false, false><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
+    }
+    exact_threshold_kernel<<<nq, 256, cap * 8, stream>>>(nq, kprime, cap, d_cnt, d_cid, d_ckey, d_th, d_slack, d_kept, d_qflags,
+                                                         d_arch_cnt, d_arch_id, arch_cap);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return bail(fail(TURDB_ERR_CUDA, "exact pass launch failed: %s", cudaGetErrorString(e)));
+    lo = hi;
+    span = hi * 3;  // the next slice is 3x everything seen so far: ~ln(4) * kprime arrivals per query plus the slack band
+  }
+  out->scr = scr;
+  out->cand_cnt = d_cnt;
+  out->cand_id = d_cid;
+  out->cap = cap;
+  return TURDB_OK;
+}
+
+static int32_t exact_filter_archive(turdb_cuda_index* idx, const float* d_queries, uint32_t nq, uint32_t K, uint8_t metric,
+                                    uint32_t arch_cap, uint32_t* d_arch_cnt, uint32_t* d_arch_id, uint32_t* d_qflags,
+                                    cudaStream_t stream) {
+  const uint32_t kprime = (uint32_t)std::min<uint64_t>(std::max(K, 1u), std::max<uint64_t>(idx->ix.n, 1));
+  uint32_t cap = 2048;
+  while (cap < 8 * kprime) cap <<= 1;
+  ExactFilterResult r;
+  int32_t rc = exact_filter_run(idx, d_queries, nq, kprime, metric, cap, std::max(256u, 2 * K), arch_cap, d_arch_cnt, d_arch_id,
+                                d_qflags, &r, stream);
+  if (rc != TURDB_OK) return rc;
+  CUDA_TRY(cudaFreeAsync(r.scr, stream));
+  return TURDB_OK;
 }
 
 extern "C" int32_t turdb_cuda_bruteforce_topk_device(turdb_cuda_index* idx, const float* d_queries, uint32_t query_dim,
@@ -187,149 +354,45 @@ extern "C" int32_t turdb_cuda_bruteforce_topk_device(turdb_cuda_index* idx, cons
     CUDA_TRY(cudaGetLastError());
     return TURDB_OK;
   }
-  const uint32_t dim = idx->ix.dim, ds = idx->ix.ds;
-  const uint32_t kp = (dim + kChunkK - 1) / kChunkK * kChunkK;
-  const uint32_t k_chunks = kp / kChunkK;
-  if (k_chunks > 32) return fail(TURDB_ERR_UNSUPPORTED, "bruteforce_topk supports dim <= 2048 (dim %u)", dim);
-  // up to 512 dims the query block (128 x K BF16) stays resident in shared memory; above, its K chunks are streamed
-  // with the vector tile's (twice the TMA traffic per tile, but any K fits)
-  const uint32_t stream_a = k_chunks > 8 ? 1u : 0u;
+  if (k > TURDB_EXACT_MAX_K) return fail(TURDB_ERR_UNSUPPORTED, "bruteforce_topk: k = %u > %u", k, TURDB_EXACT_MAX_K);
   if (!rerank_factor) rerank_factor = 4;
-  const uint64_t kprime64 = std::min<uint64_t>((uint64_t)k * rerank_factor, n);
-  if (kprime64 > 4096) return fail(TURDB_ERR_UNSUPPORTED, "k * rerank_factor = %llu > 4096", (unsigned long long)kprime64);
-  const uint32_t kprime = (uint32_t)std::max<uint64_t>(kprime64, std::min<uint64_t>(k, n));
+  // kprime >= k rows stay in the working set: the slack band around the kprime-th key is what makes the filter exact;
+  // a larger kprime only makes the band's lower edge less sensitive to outliers
+  const uint32_t kprime = (uint32_t)std::min<uint64_t>(std::min<uint64_t>((uint64_t)k * rerank_factor, 2048), n);
   uint32_t cap = 2048;
-  while (cap < 8 * kprime) cap <<= 1;
-
-  // BF16 copies of the arena, built once per index: raw rows (L2, IP) and rows scaled by 1/|x| (cosine)
-  const int copy = metric == kCosine ? 1 : 0;
-  {
-    std::lock_guard<std::mutex> lk(idx->mu);
-    __nv_bfloat16*& dst = copy ? idx->d_arena_bf16n : idx->d_arena_bf16;
-    if (!dst) {
-      CUDA_TRY(cudaMalloc(&dst, (size_t)n * kp * 2));
-      const uint64_t total = n * kp;
-      to_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(idx->d_arena, dim, ds, kp, n,
-                                                                            copy ? idx->d_norm2 : nullptr, dst);
-      CUDA_TRY(cudaGetLastError());
-      CUDA_TRY(cudaStreamSynchronize(stream));
-      idx->device_bytes += (size_t)n * kp * 2;
-    }
-  }
-  const __nv_bfloat16* d_xb = copy ? idx->d_arena_bf16n : idx->d_arena_bf16;
-
-  // scratch: Qb | col_ab | thresh | cand_cnt | overflow | cand_id | cand_key
-  size_t off = 0;
-  auto take = [&](size_t bytes) {
-    size_t o = off;
-    off = (off + bytes + 255) & ~(size_t)255;
-    return o;
-  };
-  const size_t o_qb = take((size_t)nq * kp * 2), o_ab = take((size_t)n * 4), o_th = take((size_t)nq * 4),
-               o_cnt = take((size_t)nq * 4), o_ovf = take(4), o_id = take((size_t)nq * cap * 4),
-               o_key = take((size_t)nq * cap * 4);
-  uint8_t* scr = nullptr;
-  CUDA_TRY(cudaMallocFromPoolAsync(&scr, off, idx->pool, stream));
-  __nv_bfloat16* d_qb = (__nv_bfloat16*)(scr + o_qb);
-  float* d_bias = (float*)(scr + o_ab);
-  float* d_th = (float*)(scr + o_th);
-  uint32_t* d_cnt = (uint32_t*)(scr + o_cnt);
-  uint32_t* d_ovf = (uint32_t*)(scr + o_ovf);
-  uint32_t* d_cid = (uint32_t*)(scr + o_id);
-  float* d_ckey = (float*)(scr + o_key);
-  auto bail = [&](int32_t rc) {
-    cudaFreeAsync(scr, stream);
+  while (cap < 8 * std::max(kprime, k)) cap <<= 1;
+  uint32_t* d_qflags = nullptr;
+  CUDA_TRY(cudaMallocFromPoolAsync(&d_qflags, (size_t)nq * 4, idx->pool, stream));
+  ExactFilterResult r;
+  int32_t rc = exact_filter_run(idx, d_queries, nq, std::max(kprime, std::min<uint32_t>(k, (uint32_t)n)), metric, cap, cap / 2, 0,
+                                nullptr, nullptr, d_qflags, &r, stream);
+  if (rc != TURDB_OK) {
+    cudaFreeAsync(d_qflags, stream);
     return rc;
-  };
-
-  {
-    const uint64_t total = (uint64_t)nq * kp;
-    to_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_queries, dim, dim, kp, nq, nullptr, d_qb);
-    if (metric == kL2) col_bias_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(idx->d_norm2, n, d_bias);
-    exact_init_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(d_th, d_cnt, nq, d_ovf);
   }
-  CUtensorMap map_q, map_x;
-  if (!make_bf16_map(&map_q, d_qb, nq, kp) || !make_bf16_map(&map_x, d_xb, n, kp))
-    return bail(fail(TURDB_ERR_CUDA, "cuTensorMapEncodeTiled failed"));
-
-  const size_t stage_bytes = stream_a ? 2 * (size_t)kChunkBytes : (size_t)kChunkBytes;
-  const size_t fixed_smem = (stream_a ? 0 : (size_t)k_chunks * kChunkBytes) + 4 * kTileN * 4 + 4 * kRing * kTileM * 4 + 24 * 8 + 16;
-  const uint32_t n_stages = (uint32_t)std::min<size_t>(kMaxStages, ((size_t)idx->max_smem_optin - fixed_smem) / stage_bytes);
-  if (n_stages < 2) return bail(fail(TURDB_ERR_UNSUPPORTED, "not enough shared memory for the exact path at dim %u", dim));
-  const size_t gemm_smem = fixed_smem + (size_t)n_stages * stage_bytes;
+  const uint32_t ds = idx->ix.ds;
+  const size_t rr_smem = (size_t)ds * 4 + (size_t)(cap / 2) * 8, st_smem = (size_t)ds * 4 + (size_t)k * 8 + 64 * 4;
   cudaError_t e = cudaSuccess;
-  auto set_smem = [&](auto kern) {
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
+  auto launch = [&](auto rerank, auto scan) {
+    if (rr_smem > 48 * 1024) e = cudaFuncSetAttribute(rerank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem);
+    if (e == cudaSuccess && st_smem > 48 * 1024) e = cudaFuncSetAttribute(scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem);
+    if (e != cudaSuccess) return;
+    rerank<<<nq, 128, rr_smem, stream>>>(idx->ix, d_queries, nq, k, cap, r.cand_cnt, r.cand_id, d_qflags, d_out_row_ids,
+                                         d_out_node_ids, d_out_dist, d_out_counts);
+    // queries whose buffers overflowed: the scan itself (exits at once when none is flagged)
+    scan<<<(unsigned)std::min<uint64_t>(nq, 2ull * idx->num_sms), 256, st_smem, stream>>>(idx->ix, d_queries, nq, k, d_qflags,
+                                                                                          d_out_row_ids, d_out_node_ids,
+                                                                                          d_out_dist, d_out_counts);
   };
-  set_smem(exact_gemm_filter_kernel<true, false>);
-  set_smem(exact_gemm_filter_kernel<false, false>);
-  set_smem(exact_gemm_filter_kernel<true, true>);
-  set_smem(exact_gemm_filter_kernel<false, true>);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(exact_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cap * 8));
-  if (e != cudaSuccess) return bail(fail(TURDB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)));
-
-  const uint32_t n_tiles = (uint32_t)((n + kTileN - 1) / kTileN);
-  const uint32_t n_qblocks = (nq + kTileM - 1) / kTileM;
-  uint32_t lo = 0, span = std::max(1u, (cap / 2) / kTileN);  // first slice: every column becomes a candidate
-  while (lo < n_tiles) {
-    const uint32_t hi = std::min(n_tiles, lo + span);
-    ExactArgs a{};
-    a.n_vec = (uint32_t)n;
-    a.nq = nq;
-    a.k_chunks = k_chunks;
-    a.n_stages = n_stages;
-    a.stream_a = stream_a;
-    a.tile_lo = lo;
-    a.tile_hi = hi;
-    const uint32_t tiles = hi - lo;
-    uint32_t tpi = (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(1, ((uint64_t)tiles * n_qblocks) / (4ull * idx->num_sms)));
-    a.tiles_per_item = tpi;
-    a.n_qblocks = n_qblocks;
-    a.n_items = n_qblocks * ((tiles + tpi - 1) / tpi);
-    a.col_bias = d_bias;
-    a.thresh = d_th;
-    a.cand_cnt = d_cnt;
-    a.cand_id = d_cid;
-    a.cand_key = d_ckey;
-    a.cap = cap;
-    a.overflow_flag = d_ovf;
-    a.dbg = idx->d_dbg;
-    const uint32_t grid = std::min<uint32_t>(a.n_items, (uint32_t)idx->num_sms);
-    if (metric == kL2) {
-      if (stream_a) exact_gemm_filter_kernel<true, true><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
-      else exact_gemm_filter_kernel<true, false><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
-    } else {
-      if (stream_a) exact_gemm_filter_kernel<false, true><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
-      else exact_gemm_filter_kernel<false, false><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
-    }
-    exact_threshold_kernel<<<nq, 256, cap * 8, stream>>>(nq, kprime, cap, d_cnt, d_cid, d_ckey, d_th);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return bail(fail(TURDB_ERR_CUDA, "exact pass launch failed: %s", cudaGetErrorString(e)));
-    lo = hi;
-    span = hi * 3;  // the next slice is 3x everything seen so far: ~3 * kprime new candidates per query
-  }
-
-  uint32_t n2 = 1;
-  while (n2 < kprime) n2 <<= 1;
-  const size_t rr_smem = (size_t)ds * 4 + (size_t)n2 * 8;
   switch (metric) {
-    case kCosine:
-      exact_rerank_kernel<kCosine><<<nq, 128, rr_smem, stream>>>(idx->ix, d_queries, nq, k, cap, d_cnt, d_cid, d_out_row_ids,
-                                                                 d_out_node_ids, d_out_dist, d_out_counts);
-      break;
-    case kIP:
-      exact_rerank_kernel<kIP><<<nq, 128, rr_smem, stream>>>(idx->ix, d_queries, nq, k, cap, d_cnt, d_cid, d_out_row_ids,
-                                                             d_out_node_ids, d_out_dist, d_out_counts);
-      break;
-    default:
-      exact_rerank_kernel<kL2><<<nq, 128, rr_smem, stream>>>(idx->ix, d_queries, nq, k, cap, d_cnt, d_cid, d_out_row_ids,
-                                                             d_out_node_ids, d_out_dist, d_out_counts);
+    case kCosine: launch(exact_rerank_kernel<kCosine>, exact_stream_topk_kernel<kCosine>); break;
+    case kIP: launch(exact_rerank_kernel<kIP>, exact_stream_topk_kernel<kIP>); break;
+    default: launch(exact_rerank_kernel<kL2>, exact_stream_topk_kernel<kL2>);
   }
-  exact_overflow_mark_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(d_ovf, d_out_counts, nq);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return bail(fail(TURDB_ERR_CUDA, "rerank launch failed: %s", cudaGetErrorString(e)));
-  CUDA_TRY(cudaFreeAsync(scr, stream));
+  if (e == cudaSuccess) e = cudaGetLastError();
+  cudaFreeAsync(r.scr, stream);
+  cudaFreeAsync(d_qflags, stream);
+  if (e != cudaSuccess) return fail(TURDB_ERR_CUDA, "rerank launch failed: %s", cudaGetErrorString(e));
   return TURDB_OK;
 }
 
@@ -384,8 +447,5 @@ extern "C" int32_t turdb_cuda_bruteforce_topk(turdb_cuda_index* idx, const float
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
   cleanup();
   if (e != cudaSuccess) return fail(TURDB_ERR_CUDA, "bruteforce_topk failed: %s", cudaGetErrorString(e));
-  for (uint32_t i = 0; i < nq; ++i)
-    if (out_counts[i] == 0xFFFFFFFFu)
-      return fail(TURDB_ERR_UNSUPPORTED, "bruteforce_topk: candidate buffer overflow (corpus ordered by distance?); raise rerank_factor");
   return TURDB_OK;
 }

@@ -94,6 +94,76 @@ __global__ void to_bf16_kernel(const float* __restrict__ src, uint32_t dim, uint
   dst[i] = __float2bfloat16_rn(v);
 }
 
+// What the BF16 rounding cost, per operand set: max over rows of |v - bf16(v)|_2 and of |bf16(v)|_2 (v = the FP32 row
+// that was converted: raw, or scaled by 1/|x| for the cosine copy).  One warp per row; the maxima are kept as the bit
+// patterns of non-negative floats (atomicMax on uint32).  They bound the filter's score error (query_slack_kernel), so
+// that the tensor-core pass is a CERTIFIED filter: it never drops a row the exact ranking would keep.
+__global__ void bf16_rowerr_kernel(const float* __restrict__ src, uint32_t dim, uint32_t ds, uint32_t kp, uint64_t rows,
+                                   const float* __restrict__ norm2, const __nv_bfloat16* __restrict__ conv,
+                                   uint32_t* __restrict__ out_max2) {
+  const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float sc = 1.f;
+  if (norm2) {
+    const float n2 = norm2[r];
+    sc = n2 > 0.f ? rsqrtf(n2) : 0.f;
+  }
+  float e2 = 0.f, n2b = 0.f;
+  for (uint32_t c = lane; c < dim; c += 32) {
+    const float v = src[r * ds + c] * sc, b = __bfloat162float(conv[r * kp + c]);
+    e2 = fmaf(v - b, v - b, e2);
+    n2b = fmaf(b, b, n2b);
+  }
+  for (uint32_t off = 16; off >= 1; off >>= 1) {
+    e2 += __shfl_xor_sync(kFullMask, e2, off);
+    n2b += __shfl_xor_sync(kFullMask, n2b, off);
+  }
+  if (lane == 0) {
+    atomicMax(out_max2 + 0, __float_as_uint(sqrtf(e2) * 1.0001f));
+    atomicMax(out_max2 + 1, __float_as_uint(sqrtf(n2b) * 1.0001f));
+  }
+}
+
+// Per query: 2 e(q), where e(q) bounds |filter key - exact key| for EVERY row of the corpus (key as defined below,
+// larger = closer).  With q~, x~ the BF16-rounded operands, dq = |q - q~|, Dx = max |x - x~|, Xn = max |x~|:
+//   |q~.x~ - q.x| <= |q| Dx + dq Xn                       (rounding of the operands)
+//                  + kp 2^-22 (|q| + dq) Xn               (FP32 accumulation inside the tensor core, generous)
+//   + FP32 evaluation of the bias / of the value the exact ranking uses (AVX2-order FP32 or the SQL operator's f64 of
+//     f32 differences): 2^-22 (dim/8 + 8) (|q| + Xn + Dx)^2 for L2, 2^-20 |q| for the pre-scaled cosine rows.
+// The filter admits a key >= tau - 2 e(q) where tau is the kprime-th best FILTER key seen so far; a rejected row then
+// has an exact key below the exact keys of kprime admitted rows.
+__global__ void query_slack_kernel(const float* __restrict__ queries, uint32_t dim, uint32_t kp, uint32_t nq,
+                                   const __nv_bfloat16* __restrict__ qconv, const uint32_t* __restrict__ arena_max2,
+                                   int metric, float* __restrict__ slack) {
+  const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (q >= nq) return;
+  float e2 = 0.f, n2 = 0.f;
+  for (uint32_t c = lane; c < dim; c += 32) {
+    const float v = queries[(size_t)q * dim + c], b = __bfloat162float(qconv[(size_t)q * kp + c]);
+    e2 = fmaf(v - b, v - b, e2);
+    n2 = fmaf(v, v, n2);
+  }
+  for (uint32_t off = 16; off >= 1; off >>= 1) {
+    e2 += __shfl_xor_sync(kFullMask, e2, off);
+    n2 += __shfl_xor_sync(kFullMask, n2, off);
+  }
+  if (lane == 0) {
+    const float dq = sqrtf(e2) * 1.0001f, qn = sqrtf(n2) * 1.0001f;
+    const float Dx = __uint_as_float(arena_max2[0]), Xn = __uint_as_float(arena_max2[1]);
+    float e = qn * Dx + dq * Xn + (float)kp * 2.3841858e-7f * (qn + dq) * Xn;
+    if (metric == kL2) {
+      const float s = qn + Xn + Dx;
+      e += 2.3841858e-7f * (float)(dim / 8 + 8) * s * s;
+    } else if (metric == kCosine) {
+      e += 9.5367432e-7f * qn;
+    } else {
+      e += 2.3841858e-7f * (float)(dim / 8 + 8) * qn * (Xn + Dx);
+    }
+    slack[q] = 2.02f * e;
+  }
+}
+
 // Ranking key of a score s for column (vector) j, larger = closer (the query's own norm does not change ranks):
 //   L2: s - |x|^2 / 2  (bias array below)      cosine: s on rows pre-scaled by 1/|x|      IP: s
 __global__ void col_bias_kernel(const float* __restrict__ norm2, uint64_t n, float* __restrict__ bias) {
@@ -187,7 +257,7 @@ struct ExactArgs {
   uint32_t* cand_id;              // [nq][cap]
   float* cand_key;                // [nq][cap]
   uint32_t cap;
-  uint32_t* overflow_flag;
+  uint32_t* qflags;               // [nq] bit 0: this query lost a candidate (buffer full) -> redone by the streaming scan
   unsigned long long* dbg;  // optional [16] cycle counters (diagnostics)
 };
 
@@ -342,7 +412,7 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
           a.cand_id[(size_t)p_q * a.cap + p_pos + i] = ring_col[(base + i) * kTileM + et];
           a.cand_key[(size_t)p_q * a.cap + p_pos + i] = ring_key[(base + i) * kTileM + et];
         } else {
-          *a.overflow_flag = 1u;
+          a.qflags[p_q] = 1u;
         }
       }
       p_n = 0;
@@ -428,7 +498,7 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
                     a.cand_id[(size_t)q * a.cap + o] = t * kTileN + cb * 32 + j;
                     a.cand_key[(size_t)q * a.cap + o] = key;
                   } else {
-                    *a.overflow_flag = 1u;
+                    a.qflags[q] = 1u;
                   }
                   ++o;
                 }
@@ -467,24 +537,45 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
 }
 
 // ------------------------------------------------------------------------------------------------
-// pass (2): keep the kprime best keys per query, publish the kprime-th as the new threshold
+// pass (2): per query, new threshold = (kprime-th best filter key so far) - slack; keep every key above it
 // ------------------------------------------------------------------------------------------------
-// One CTA per query; bitonic sort (descending key, ascending id on ties) of up to `cap` candidates in smem.
+// One CTA per query; bitonic sort (descending key, ascending id on ties) of the query's buffer in shared memory.
+// The buffer holds [0, kept[q]) = what the previous call kept, then this slice's arrivals.  With `arch_id` the
+// arrivals are first appended to the query's archive (ids only, never pruned): the union of all arrivals is a superset
+// of the rows a sequential scan would ever have pushed into its top-K heap (sql_topk.inl replays exactly that).
+// A query whose buffer or archive overflowed is flagged (qflags[q]) and redone by the streaming scan.
 __global__ void __launch_bounds__(256) exact_threshold_kernel(uint32_t nq, uint32_t kprime, uint32_t cap,
                                                               uint32_t* cand_cnt, uint32_t* cand_id, float* cand_key,
-                                                              float* thresh) {
+                                                              float* thresh, const float* __restrict__ slack,
+                                                              uint32_t* kept, uint32_t* qflags, uint32_t* arch_cnt,
+                                                              uint32_t* arch_id, uint32_t arch_cap) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float* sk = reinterpret_cast<float*>(smem_raw);
   uint32_t* si = reinterpret_cast<uint32_t*>(sk + cap);
+  __shared__ uint32_t s_keep;
   const uint32_t q = blockIdx.x;
   if (q >= nq) return;
-  const uint32_t cnt = min(cand_cnt[q], cap);
+  const uint32_t raw_cnt = cand_cnt[q];
+  const uint32_t cnt = min(raw_cnt, cap);
+  const uint32_t prev = min(kept[q], cnt);
+  if (raw_cnt > cap && threadIdx.x == 0) qflags[q] = 1u;
+  if (arch_id) {
+    const uint32_t base = arch_cnt[q], n_new = cnt - prev;
+    for (uint32_t i = threadIdx.x; i < n_new; i += blockDim.x) {
+      if (base + i < arch_cap) arch_id[(size_t)q * arch_cap + base + i] = cand_id[(size_t)q * cap + prev + i];
+    }
+    if (threadIdx.x == 0) {
+      arch_cnt[q] = min(base + n_new, arch_cap);
+      if (base + n_new > arch_cap) qflags[q] = 1u;
+    }
+  }
   uint32_t n2 = 1;
   while (n2 < cnt) n2 <<= 1;
   for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) {
     sk[i] = i < cnt ? cand_key[(size_t)q * cap + i] : -INFINITY;
     si[i] = i < cnt ? cand_id[(size_t)q * cap + i] : 0xFFFFFFFFu;
   }
+  if (threadIdx.x == 0) s_keep = 0;
   __syncthreads();
   for (uint32_t size = 2; size <= n2; size <<= 1) {
     for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
@@ -504,14 +595,25 @@ __global__ void __launch_bounds__(256) exact_threshold_kernel(uint32_t nq, uint3
       __syncthreads();
     }
   }
-  const uint32_t keep = min(cnt, kprime);
+  // tau' = kprime-th best key - 2 e(q); everything at or above it stays (>= kprime entries)
+  const float tau = cnt >= kprime ? sk[kprime - 1] - (slack ? slack[q] : 0.f) : -INFINITY;
+  uint32_t mine = 0;
+  for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) mine += (sk[i] >= tau) ? 1u : 0u;
+  if (mine) atomicAdd(&s_keep, mine);
+  __syncthreads();
+  uint32_t keep = s_keep;  // a prefix of the sorted buffer
+  if (keep > cap / 2) {    // no room left for the next slice's arrivals: give the query to the streaming scan
+    keep = cap / 2;
+    if (threadIdx.x == 0) qflags[q] = 1u;
+  }
   for (uint32_t i = threadIdx.x; i < keep; i += blockDim.x) {
     cand_key[(size_t)q * cap + i] = sk[i];
     cand_id[(size_t)q * cap + i] = si[i];
   }
   if (threadIdx.x == 0) {
     cand_cnt[q] = keep;
-    thresh[q] = keep == kprime ? sk[kprime - 1] : -INFINITY;
+    kept[q] = keep;
+    thresh[q] = tau;
   }
 }
 
@@ -522,11 +624,13 @@ __global__ void __launch_bounds__(256) exact_threshold_kernel(uint32_t nq, uint3
 template <int METRIC>
 __global__ void __launch_bounds__(128) exact_rerank_kernel(DeviceIndex ix, const float* __restrict__ queries, uint32_t nq,
                                                            uint32_t k, uint32_t cap, const uint32_t* __restrict__ cand_cnt,
-                                                           const uint32_t* __restrict__ cand_id, uint64_t* out_rows,
+                                                           const uint32_t* __restrict__ cand_id,
+                                                           const uint32_t* __restrict__ qflags, uint64_t* out_rows,
                                                            uint32_t* out_nodes, float* out_dist, uint32_t* out_counts) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint32_t q = blockIdx.x;
   if (q >= nq) return;
+  if (qflags[q]) return;  // a candidate was lost (buffer full): exact_stream_topk_kernel redoes this query
   const uint32_t cnt = min(cand_cnt[q], cap);
   uint32_t n2 = 1;
   while (n2 < cnt) n2 <<= 1;
@@ -546,6 +650,7 @@ __global__ void __launch_bounds__(128) exact_rerank_kernel(DeviceIndex ix, const
       float d = raw;
       if (METRIC == kIP) d = -raw;
       if (METRIC == kCosine) d = cosine_finish(raw, qn, ix.norm2[id]);
+      if (b[0] == INFINITY) d = INFINITY;  // absent vector
       sd[c] = c < cnt ? d : INFINITY;
       si[c] = c < cnt ? id : 0xFFFFFFFFu;
     }
@@ -583,6 +688,101 @@ __global__ void __launch_bounds__(128) exact_rerank_kernel(DeviceIndex ix, const
     }
   }
   if (threadIdx.x == 0) out_counts[q] = count;
+}
+
+// The scan itself, for the queries the filter could not serve (qflags[q] != 0): FP32 distances in the reference's lane
+// order over ALL rows, top-k by (distance, node id).  CTAs stride over the queries and skip unflagged ones; always
+// enqueued, exits at once when nothing is flagged.  smem: query [ds] | list d [k] | list id [k] | chunk d [64]
+template <int METRIC>
+__global__ void __launch_bounds__(256) exact_stream_topk_kernel(DeviceIndex ix, const float* __restrict__ queries, uint32_t nq,
+                                                                uint32_t k, const uint32_t* __restrict__ qflags,
+                                                                uint64_t* out_rows, uint32_t* out_nodes, float* out_dist,
+                                                                uint32_t* out_counts) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float* qs = reinterpret_cast<float*>(smem_raw);
+  float* ld = qs + ix.ds;
+  uint32_t* li = reinterpret_cast<uint32_t*>(ld + k);
+  float* cd = reinterpret_cast<float*>(li + k);
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, p = tid & 3, quad = tid >> 2;
+  for (uint32_t q = blockIdx.x; q < nq; q += gridDim.x) {
+    if (!qflags[q]) continue;
+    __syncthreads();
+    for (uint32_t i = tid; i < ix.ds; i += blockDim.x) qs[i] = i < ix.dim ? queries[(size_t)q * ix.dim + i] : 0.f;
+    __syncthreads();
+    const float qn = (METRIC == kCosine) ? quad_dot(qs, qs, ix.dim, p) : 0.f;
+    uint32_t len = 0;  // meaningful in warp 0
+    for (uint64_t base = 0; base < ix.n; base += 64) {
+      const uint64_t r = min(base + quad, ix.n - 1);
+      const float* b = ix.arena + r * ix.ds;
+      const float raw = (METRIC == kL2) ? quad_l2sq(qs, b, ix.dim, p) : quad_dot(qs, b, ix.dim, p);
+      if (p == 0) {
+        float d = raw;
+        if (METRIC == kIP) d = -raw;
+        if (METRIC == kCosine) d = cosine_finish(raw, qn, ix.norm2[r]);
+        if (b[0] == INFINITY) d = INFINITY;
+        cd[quad] = d;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        const uint32_t cnt = (uint32_t)min((uint64_t)64, (uint64_t)(ix.n - base));
+        for (uint32_t half = 0; half < cnt; half += 32) {
+          const uint32_t j = half + lane;
+          const float dj = j < cnt ? cd[j] : INFINITY;
+          uint32_t mask = __ballot_sync(kFullMask, j < cnt && (len < k || dj < ld[k - 1]));
+          while (mask) {
+            const uint32_t l = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float d = cd[half + l];
+            const uint32_t id = (uint32_t)(base + half + l);
+            if (len < k || d < ld[len - 1]) {
+              // position = entries with distance <= d (they hold smaller node ids: rows arrive in ascending order)
+              uint32_t c = 0;
+              for (uint32_t i = lane; i < len; i += 32) c += (ld[i] <= d) ? 1u : 0u;
+              const uint32_t pos = __reduce_add_sync(kFullMask, c);
+              const uint32_t last = min(len, k - 1);  // entries [pos, last) move up by one
+              for (int32_t top = (int32_t)last - 1; top >= (int32_t)pos; top -= 32) {
+                const int32_t i = top - (int32_t)lane;
+                float td = 0.f;
+                uint32_t ti = 0;
+                if (i >= (int32_t)pos) {
+                  td = ld[i];
+                  ti = li[i];
+                }
+                __syncwarp();
+                if (i >= (int32_t)pos) {
+                  ld[i + 1] = td;
+                  li[i + 1] = ti;
+                }
+                __syncwarp();
+              }
+              if (lane == 0) {
+                ld[pos] = d;
+                li[pos] = id;
+              }
+              len = min(len + 1, k);
+              __syncwarp();
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (warp == 0) {
+      for (uint32_t i = lane; i < k; i += 32) {
+        const size_t o = (size_t)q * k + i;
+        if (i < len) {
+          out_rows[o] = ix.row_ids[li[i]];
+          if (out_nodes) out_nodes[o] = li[i];
+          out_dist[o] = ld[i];
+        } else {
+          out_rows[o] = 0xFFFFFFFFFFFFFFFFull;
+          if (out_nodes) out_nodes[o] = kInvalid;
+          out_dist[o] = INFINITY;
+        }
+      }
+      if (lane == 0) out_counts[q] = len;
+    }
+  }
 }
 
 }  // namespace turdb

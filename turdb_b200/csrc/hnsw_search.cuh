@@ -58,6 +58,12 @@
 #define TURDB_GATHER_MODE 0
 #endif
 
+// Rows up to this many bytes are traversed by the direct form (one warp per query, hnsw_search_warp_kernel) unless the
+// caller forces a form (turdb_cuda_index_set_traversal_form)
+#ifndef TURDB_DIRECT_MAX_ROW_BYTES
+#define TURDB_DIRECT_MAX_ROW_BYTES 1024
+#endif
+
 namespace turdb {
 
 constexpr uint32_t kDone = 0xFFFFFFFFu;
@@ -66,8 +72,11 @@ constexpr uint32_t kDone = 0xFFFFFFFFu;
 #endif
 constexpr int kMergeBatch = TURDB_MERGE_BATCH;
 
+// fixed offsets of the small per-query arrays (the variable-size ones follow: list, filtered window, query, table, staging)
+constexpr uint32_t kOffBar = 0, kOffCtl = 32, kOffCand = 64, kOffList = 576;
+
 struct TeamLayout {
-  uint32_t off_bar, off_ctl, off_q, off_list, off_clist, off_cand, off_hash, off_stage;
+  uint32_t off_q, off_clist, off_hash, off_stage;
   uint32_t team_bytes;
   uint32_t n_groups;   // staging groups of 8 slots (1..4), one mbarrier each
   uint32_t stride;     // bytes between staging slots; stride/4 == 8 (mod 32) -> conflict-free quads
@@ -111,6 +120,7 @@ struct SearchArgs {
   const uint64_t* visible;   // null => unfiltered search
   uint2* f_ovf;              // [CTAs][f_ocap] (distance bits, id) overflow of the candidate window
   uint32_t f_ocap;
+  uint32_t* vis_max;         // optional: running maximum of visited-set keys per query (sizes the next launch's table)
 };
 
 // Per-team shared state handed to every warp.
@@ -188,7 +198,7 @@ __device__ __forceinline__ void team_distances_pieces(const DeviceIndex& ix, Tea
     if (METRIC == kCosine && slot < m) nb = __ldg(ix.norm2 + t.cand_ids[slot]);
     const uint8_t* sb = t.stage + (g * 8 + (lane >> 2)) * t.stride;
     uint64_t acc = 0ull;
-    float raw = 0.f;
+    float raw = 0.f, first = 0.f;
     for (uint32_t sgm = 0; sgm < S; ++sgm) {
       long long w0 = t.dbg ? clock64() : 0;
       mbar_wait(t.bar0 + 8 * g, (t.phases >> g) & 1u);
@@ -196,6 +206,7 @@ __device__ __forceinline__ void team_distances_pieces(const DeviceIndex& ix, Tea
       t.c_wait += (uint32_t)(w1 - w0);
       t.phases ^= (1u << g);
       const uint32_t s0 = seg_lo(sgm), s1 = (sgm + 1 == S) ? steps : seg_lo(sgm + 1);
+      if (sgm == 0) first = *reinterpret_cast<const float*>(sb);
       const uint64_t* av = reinterpret_cast<const uint64_t*>(t.q + 8 * s0) + p;
       const uint64_t* bv = reinterpret_cast<const uint64_t*>(sb) + p;
       acc = (METRIC == kL2) ? quad_accum<true>(acc, av, bv, s1 - s0) : quad_accum<false>(acc, av, bv, s1 - s0);
@@ -213,6 +224,7 @@ __device__ __forceinline__ void team_distances_pieces(const DeviceIndex& ix, Tea
       float d = raw;
       if (METRIC == kIP) d = -raw;  // inner_product_avx2, distance.rs:240-242
       if (METRIC == kCosine) d = cosine_finish(raw, t.qnorm, nb);
+      if (first == INFINITY) d = INFINITY;  // absent vector (+inf row): get_vector -> None, mod.rs:1111-1121
       t.cand_d[slot] = d;
     }
   }
@@ -277,6 +289,8 @@ __device__ __forceinline__ void team_distances_whole(const DeviceIndex& ix, Team
       float d = raw;
       if (METRIC == kIP) d = -raw;  // inner_product_avx2, distance.rs:240-242
       if (METRIC == kCosine) d = cosine_finish(raw, t.qnorm, nb);
+      // absent vector (uploaded as a +inf row; SQ8: min == +inf): get_vector -> None => INFINITY, mod.rs:1111-1121
+      if ((SQ8 ? *reinterpret_cast<const float*>(bs + ((ix.dim + 3) & ~3u)) : b[0]) == INFINITY) d = INFINITY;
       t.cand_d[slot] = d;
     }
     __syncwarp();
@@ -330,6 +344,7 @@ __device__ __forceinline__ void team_distances_ldgsts(const DeviceIndex& ix, Tea
       float d = raw;
       if (METRIC == kIP) d = -raw;  // inner_product_avx2, distance.rs:240-242
       if (METRIC == kCosine) d = cosine_finish(raw, t.qnorm, nb);
+      if (b[0] == INFINITY) d = INFINITY;  // absent vector
       t.cand_d[slot] = d;
     }
     __syncwarp();                     // the group's slots are free again
@@ -406,6 +421,7 @@ __device__ __forceinline__ void team_distances_g4(const DeviceIndex& ix, Team& t
       float d = raw;
       if (METRIC == kIP) d = -raw;
       if (METRIC == kCosine) d = cosine_finish(raw, t.qnorm, nb);
+      if (*reinterpret_cast<const float*>(base) == INFINITY) d = INFINITY;  // absent vector
       t.cand_d[slot] = d;
     }
     __syncwarp();
@@ -454,6 +470,173 @@ __device__ __forceinline__ float leader_request(const DeviceIndex& ix, Team& t, 
 template <int METRIC, bool SQ8>
 __device__ __forceinline__ float leader_request(const DeviceIndex& ix, Team& t, uint32_t m) {
   return leader_request<METRIC, SQ8>(ix, t, m, [] {});
+}
+
+// ---- direct mode: ONE WARP per query, neighbour rows gathered straight into registers --------------------
+// For short rows (dim <= ~256) a hop moves only a few KB, and what bounds the kernel is how many hops an SM
+// keeps in flight, not how fast one hop runs.  The direct form drops the team: no staging slots, no mbarriers,
+// no CTA barriers — a 32-thread CTA per query (16-20 resident per SM), the registers are the landing zone.
+// A quad of lanes owns one neighbour row per pass (8 rows per pass); lane p of the quad loads the 8 bytes
+// (elements 8t+2p, 8t+2p+1) of AVX step t with one LDG.64, so the quad reads one 32 B sector per step and every
+// lane's accumulator is exactly the reference's AVX2 lane pair (distance.rs:105-129).  A row streams through in
+// column chunks of 16 steps (128 floats, 16 registers pairs); two chunks are in flight per warp.
+// step S of a unit: base + 32 S bytes, the offset folded into the instruction (a register operand per load would
+// cost an address register pair each)
+template <int S, int US>
+struct LoadSteps {
+  static __device__ __forceinline__ void run(uint64_t (&b)[US], const uint64_t* base, uint32_t ns) {
+    if ((uint32_t)S < ns) asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1+%2];" : "=l"(b[S]) : "l"(base), "n"(32 * S));
+    LoadSteps<S + 1, US>::run(b, base, ns);
+  }
+};
+template <int US>
+struct LoadSteps<US, US> {
+  static __device__ __forceinline__ void run(uint64_t (&)[US], const uint64_t*, uint32_t) {}
+};
+
+// steps (of 8 floats) per unit and units in flight per warp: registers for the landing zone = 2 * US * NBUF
+#ifndef TURDB_DIRECT_DBG
+#define TURDB_DIRECT_DBG 0
+#endif
+#ifndef TURDB_DIRECT_US
+#define TURDB_DIRECT_US 8
+#endif
+// 1: rows of a request beyond the first pass (candidates 8..m-1) are prefetched into L2 when the request starts,
+// one 128 B line per lane and instruction: their loads then pay an L2 hit instead of a second and third DRAM
+// round trip, without holding registers for them meanwhile.  Same DRAM bytes: every line is consumed for certain.
+#ifndef TURDB_DIRECT_PREFETCH
+#define TURDB_DIRECT_PREFETCH 1
+#endif
+#ifndef TURDB_DIRECT_NBUF
+#define TURDB_DIRECT_NBUF 1
+#endif
+
+template <int METRIC, typename F>
+__device__ __forceinline__ float warp_request(const DeviceIndex& ix, Team& t, uint32_t m, F&& overlap) {
+  constexpr int US = TURDB_DIRECT_US, NBUF = TURDB_DIRECT_NBUF;
+  const uint32_t lane = t.lane, p = lane & 3, qd = lane >> 2;
+  const uint32_t steps = ix.dim >> 3, ntail = ix.dim & 7;
+  const uint32_t nch = max(1u, (steps + US - 1) / US);
+  const bool full = steps != 0 && steps % US == 0;  // every unit carries US steps: the loops below run unpredicated
+  const uint32_t npass = (m + 7) >> 3, nunits = npass * nch;
+  uint64_t b[NBUF][US];
+  // Quads beyond the request's last candidate gather (and reduce) that last candidate again: every lane then runs
+  // the same unpredicated instruction stream; their result is discarded.
+  uint32_t l_pass = 0, l_ch = 0;  // next unit to load
+  auto load = [&](uint64_t (&bb)[US]) {
+    const uint32_t id = t.cand_ids[min(8 * l_pass + qd, m - 1)];
+    const uint64_t* src = reinterpret_cast<const uint64_t*>(t.rows + (size_t)id * t.vec_bytes) + 4 * US * l_ch + p;
+    if (full) LoadSteps<0, US>::run(bb, src, US);
+    else LoadSteps<0, US>::run(bb, src, min((uint32_t)US, steps - US * l_ch));
+    if (++l_ch == nch) {
+      l_ch = 0;
+      ++l_pass;
+    }
+  };
+  uint32_t c_pass = 0, c_ch = 0;  // next unit to reduce
+  uint64_t acc = 0ull;
+  float out = INFINITY, first = 0.f;
+  auto consume = [&](const uint64_t (&bb)[US]) {
+    const uint64_t* av = reinterpret_cast<const uint64_t*>(t.q + 8 * US * c_ch) + p;
+    if (full) {
+      if (c_ch == 0) first = __uint_as_float((uint32_t)bb[0]);  // element 0 of the row, in the quad's lane 0
+#pragma unroll
+      for (int s = 0; s < US; ++s) {
+        if (METRIC == kL2) {
+          const uint64_t d = sub2(av[4 * s], bb[s]);
+          acc = fma2(d, d, acc);
+        } else {
+          acc = fma2(av[4 * s], bb[s], acc);
+        }
+      }
+    } else {
+      const uint32_t ns = min((uint32_t)US, steps - US * c_ch);
+      if (c_ch == 0) first = ns ? __uint_as_float((uint32_t)bb[0]) : 0.f;
+#pragma unroll
+      for (int s = 0; s < US; ++s)
+        if ((uint32_t)s < ns) {
+          if (METRIC == kL2) {
+            const uint64_t d = sub2(av[4 * s], bb[s]);
+            acc = fma2(d, d, acc);
+          } else {
+            acc = fma2(av[4 * s], bb[s], acc);
+          }
+        }
+    }
+    if (++c_ch == nch) {
+      // row complete: horizontal sum in the reference's order, the unfused scalar tail, the metric's epilogue
+      float r = quad_hsum(unpack2(acc));
+      const uint32_t id = t.cand_ids[min(8 * c_pass + qd, m - 1)];
+      if (ntail | (steps == 0)) {
+        const float* row = reinterpret_cast<const float*>(t.rows + (size_t)id * t.vec_bytes);
+        for (uint32_t i = 0; i < ntail; ++i) {
+          const float a = t.q[8 * steps + i], bv = __ldg(row + 8 * steps + i);
+          if (METRIC == kL2) {
+            const float d = __fsub_rn(a, bv);
+            r = __fadd_rn(r, __fmul_rn(d, d));
+          } else {
+            r = __fadd_rn(r, __fmul_rn(a, bv));
+          }
+        }
+        if (steps == 0) first = __ldg(row);
+      }
+      float d = r;
+      if (METRIC == kIP) d = -r;  // inner_product_avx2, distance.rs:240-242
+      if (METRIC == kCosine) d = cosine_finish(r, t.qnorm, __ldg(ix.norm2 + id));
+      // absent vector (uploaded as a +inf row): get_vector -> None => distance INFINITY for every metric, mod.rs:1111-1121
+      if (__shfl_sync(kFullMask, first, lane & ~3u) == INFINITY) d = INFINITY;
+      // lane i of the warp receives candidate i: candidate 8*pass + j lives in quad j
+      const float v = __shfl_sync(kFullMask, d, (lane & 7) << 2);
+      if ((lane >> 3) == c_pass) out = v;
+      acc = 0ull;
+      c_ch = 0;
+      ++c_pass;
+    }
+  };
+#pragma unroll
+  for (int i = 0; i < NBUF; ++i)
+    if ((uint32_t)i < nunits) load(b[i]);
+#if TURDB_DIRECT_PREFETCH
+  if (nunits > (uint32_t)NBUF) {
+    // everything the first NBUF units do not cover is pulled into L2 now, one 128 B line per lane and instruction
+    // (whole rows of the later candidates; with rows longer than the buffers, the rest of every row)
+    const uint32_t r0 = nch > (uint32_t)NBUF ? 0u : 8u * ((uint32_t)NBUF / nch);
+    const uint32_t lpr = ((t.vec_bytes + 127) >> 7) + ((t.vec_bytes & 127) ? 1u : 0u);  // lines a row can touch
+    const uint32_t sh = 32 - __clz(lpr - 1), total = (m - min(m, r0)) << sh;             // rounded up to a power of two
+    for (uint32_t j = lane; j < total; j += 32) {
+      const uint32_t r = r0 + (j >> sh), l = j & ((1u << sh) - 1);
+      const uint8_t* row = t.rows + (size_t)t.cand_ids[r] * t.vec_bytes;
+      const uintptr_t a = (reinterpret_cast<uintptr_t>(row) & ~(uintptr_t)127) + 128 * l;
+      if (a < reinterpret_cast<uintptr_t>(row) + t.vec_bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+    }
+  }
+#endif
+  overlap();
+  for (uint32_t u = 0; u < nunits; u += NBUF) {
+#pragma unroll
+    for (int i = 0; i < NBUF; ++i)
+      if (u + i < nunits) {
+        consume(b[i]);
+        if (u + i + NBUF < nunits) load(b[i]);
+      }
+  }
+  return lane < m ? out : INFINITY;
+}
+
+// One request, either form.
+template <int METRIC, bool SQ8, bool DIRECT, typename F>
+__device__ __forceinline__ float request(const DeviceIndex& ix, Team& t, uint32_t m, F&& overlap) {
+  if (DIRECT) return warp_request<METRIC>(ix, t, m, overlap);
+  return leader_request<METRIC, SQ8>(ix, t, m, overlap);
+}
+template <int METRIC, bool SQ8, bool DIRECT>
+__device__ __forceinline__ float request(const DeviceIndex& ix, Team& t, uint32_t m) {
+  return request<METRIC, SQ8, DIRECT>(ix, t, m, [] {});
+}
+template <bool DIRECT>
+__device__ __forceinline__ void team_sync() {
+  if (DIRECT) __syncwarp();
+  else __syncthreads();
 }
 
 // Exact visited set, called by all 32 lanes of the leader with one (distinct) id per active lane.
@@ -632,14 +815,14 @@ __device__ __forceinline__ uint32_t rank_merge(const float* src_d, const uint32_
   return min(n_old + mp, cap);
 }
 
-template <int METRIC, bool GLOBAL_VISITED, bool FILTERED, bool SQ8 = false>
-__global__ void __launch_bounds__(128, TURDB_MIN_CTAS) hnsw_search_kernel(const SearchArgs a) {
+template <int METRIC, bool GLOBAL_VISITED, bool FILTERED, bool SQ8, bool DIRECT>
+__device__ __forceinline__ void hnsw_search_body(const SearchArgs& a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const DeviceIndex& ix = a.ix;
   const uint32_t tid = threadIdx.x, nthreads = blockDim.x;
   const uint32_t lane = tid & 31, warp = tid >> 5;
   float* qs = reinterpret_cast<float*>(smem + a.lay.off_q);
-  float* A_d = reinterpret_cast<float*>(smem + a.lay.off_list);  // result list (sorted, ef slots)
+  float* A_d = reinterpret_cast<float*>(smem + kOffList);  // result list (sorted, ef slots)
   uint32_t* A_id = reinterpret_cast<uint32_t*>(A_d + a.ef);
   float* B_d = reinterpret_cast<float*>(A_id + a.ef);             // second buffer: filtered search only
   uint32_t* B_id = reinterpret_cast<uint32_t*>(B_d + a.ef);
@@ -647,7 +830,7 @@ __global__ void __launch_bounds__(128, TURDB_MIN_CTAS) hnsw_search_kernel(const 
   uint32_t* C_id = reinterpret_cast<uint32_t*>(C_d + a.ef);
   float* D_d = reinterpret_cast<float*>(C_id + a.ef);
   uint32_t* D_id = reinterpret_cast<uint32_t*>(D_d + a.ef);
-  uint32_t* cand_ids = reinterpret_cast<uint32_t*>(smem + a.lay.off_cand);
+  uint32_t* cand_ids = reinterpret_cast<uint32_t*>(smem + kOffCand);
   float* cand_d = reinterpret_cast<float*>(cand_ids + 32);
   uint32_t* tmp_ub = cand_ids + 64;
   uint32_t* cand_next = cand_ids + 96;  // ids of the speculatively prepared next request
@@ -660,8 +843,8 @@ __global__ void __launch_bounds__(128, TURDB_MIN_CTAS) hnsw_search_kernel(const 
   t.lane = lane;
   t.warp = warp;
   t.n_warps = nthreads >> 5;
-  t.bar0 = smem_u32(smem + a.lay.off_bar);
-  t.ctl = reinterpret_cast<volatile uint32_t*>(smem + a.lay.off_ctl);
+  t.bar0 = smem_u32(smem + kOffBar);
+  t.ctl = reinterpret_cast<volatile uint32_t*>(smem + kOffCtl);
   t.q = qs;
   t.cand_ids = cand_ids;
   t.cand_d = cand_d;
@@ -682,21 +865,21 @@ __global__ void __launch_bounds__(128, TURDB_MIN_CTAS) hnsw_search_kernel(const 
   t.phases = 0;
   t.qnorm = 0.f;
   t.c_issue = t.c_wait = t.c_comp = 0;
-  t.dbg = a.dbg != nullptr;
-  t.tabulate();
+  t.dbg = (DIRECT && !TURDB_DIRECT_DBG) ? false : a.dbg != nullptr;  // the direct form's register budget has no room for the counters
+  if (!DIRECT) t.tabulate();
 
-  if (tid == 0) {
+  if (!DIRECT && tid == 0) {
     for (uint32_t g = 0; g < a.lay.n_groups; ++g) mbar_init(t.bar0 + 8 * g, 1);
     mbar_fence_init();
   }
-  __syncthreads();
+  team_sync<DIRECT>();
 
   const uint32_t ef = a.ef;
   const uint32_t n_work = GLOBAL_VISITED ? *a.overflow_count : a.nq;
 
   for (;;) {
     if (tid == 0) t.ctl[1] = atomicAdd(a.work_counter, 1u);
-    __syncthreads();
+    team_sync<DIRECT>();
     const uint32_t wi = t.ctl[1];
     if (wi >= n_work) break;
     const uint32_t qi = GLOBAL_VISITED ? a.overflow_list[wi] : wi;
@@ -710,17 +893,17 @@ __global__ void __launch_bounds__(128, TURDB_MIN_CTAS) hnsw_search_kernel(const 
       const uint32_t fill = (GLOBAL_VISITED || a.lay.hash16) ? 0u : kInvalid;
       for (uint32_t i = tid; i < n16; i += nthreads) v4[i] = make_uint4(fill, fill, fill, fill);
     }
-    __syncthreads();
+    team_sync<DIRECT>();
     if (METRIC == kCosine) t.qnorm = quad_dot(qs, qs, ix.dim, lane & 3);
 
-    if (warp != 0) {
+    if (!DIRECT && warp != 0) {
       // ---- helper warps: serve distance requests until the leader is done with this query ----
       for (;;) {
-        __syncthreads();
+        team_sync<DIRECT>();
         const uint32_t m = t.ctl[0];
         if (m == kDone) break;
         team_distances<METRIC, SQ8>(ix, t, m);
-        __syncthreads();
+        team_sync<DIRECT>();
       }
       if (t.dbg && warp == 1 && lane == 0) {  // diagnostics: the first helper's share of the data path
         atomicAdd(a.dbg + 13, (unsigned long long)t.c_issue);
@@ -744,7 +927,7 @@ __global__ void __launch_bounds__(128, TURDB_MIN_CTAS) hnsw_search_kernel(const 
       // entry distance (mod.rs:1129)
       uint32_t cur = ix.entry;
       if (lane == 0) cand_ids[0] = cur;
-      float cur_d = __shfl_sync(kFullMask, leader_request<METRIC, SQ8>(ix, t, 1), 0);
+      float cur_d = __shfl_sync(kFullMask, request<METRIC, SQ8, DIRECT>(ix, t, 1), 0);
       n_dist = 1;
       n_dist_upper = 1;
 
@@ -760,7 +943,7 @@ __global__ void __launch_bounds__(128, TURDB_MIN_CTAS) hnsw_search_kernel(const 
           const uint32_t m = __popc(__ballot_sync(kFullMask, nid != kInvalid));
           if (m == 0) break;
           if (lane < m) cand_ids[lane] = nid;
-          const float d = leader_request<METRIC, SQ8>(ix, t, m);
+          const float d = request<METRIC, SQ8, DIRECT>(ix, t, m);
           n_dist += m;
           n_dist_upper += m;
           // arg-min, strict `<`, first stored neighbour wins ties (search.rs:272-277)
@@ -860,7 +1043,7 @@ __global__ void __launch_bounds__(128, TURDB_MIN_CTAS) hnsw_search_kernel(const 
           if (m == 0) continue;
           n_visited += m;
           if (isnew) cand_ids[__popc(newmask & ((1u << lane) - 1))] = nid;
-          const float d = leader_request<METRIC, SQ8>(ix, t, m);
+          const float d = request<METRIC, SQ8, DIRECT>(ix, t, m);
           const uint32_t cid = lane < m ? cand_ids[lane] : kInvalid;
           n_dist += m;
           // results: visible && (d < worst || |R| < ef), search.rs:391-395 (batch form)
@@ -903,7 +1086,11 @@ __global__ void __launch_bounds__(128, TURDB_MIN_CTAS) hnsw_search_kernel(const 
           if (o_overflow) break;
         }
         len = r_len;
-        if (o_overflow) len = 0xFFFFFFFEu;  // candidate overflow buffer exhausted: reported through out_counts
+        // candidate overflow buffer exhausted: the query is redone by the fallback pass, whose buffer holds every node
+        if (o_overflow) {
+          if (GLOBAL_VISITED) len = 0xFFFFFFFEu;  // cannot happen there (f_ocap == n)
+          else overflow = true;
+        }
       } else {
       // level-0 beam search (search.rs:311-350) on one sorted list
       if (lane == 0) {
@@ -994,7 +1181,7 @@ __global__ void __launch_bounds__(128, TURDB_MIN_CTAS) hnsw_search_kernel(const 
         }
         n_visited += m;
         const long long h2 = t.dbg ? clock64() : 0;
-        const float d = leader_request<METRIC, SQ8>(ix, t, m, [&] {
+        const float d = request<METRIC, SQ8, DIRECT>(ix, t, m, [&] {
           // hop h+1 prepared under hop h's gather (leader only; cand_ids belongs to the helpers meanwhile)
           if (row_node == kInvalid) return;
           if (!GLOBAL_VISITED && n_visited + kL0 > hash_limit) return;  // the real hop reports the overflow
@@ -1143,7 +1330,7 @@ __global__ void __launch_bounds__(128, TURDB_MIN_CTAS) hnsw_search_kernel(const 
 
     // release the helper warps
     if (lane == 0) t.ctl[0] = kDone;
-    __syncthreads();
+    team_sync<DIRECT>();
 
     if (overflow) {
       // shared visited table cannot take more keys: hand the query to the global-bitset pass (exact, rare)
@@ -1169,6 +1356,7 @@ __global__ void __launch_bounds__(128, TURDB_MIN_CTAS) hnsw_search_kernel(const 
       }
     }
     if (lane == 0) {
+      if (a.vis_max) atomicMax(a.vis_max, n_dist - n_dist_upper + 1);
       a.out_counts[qi] = f_fail ? 0xFFFFFFFEu : count;
       if (a.out_stats) {
         uint32_t* s = a.out_stats + (size_t)qi * 4;
@@ -1179,6 +1367,21 @@ __global__ void __launch_bounds__(128, TURDB_MIN_CTAS) hnsw_search_kernel(const 
       }
     }
   }
+}
+
+// staged form: a team of 2-4 warps per query, rows through shared-memory staging (TMA bulk copies)
+template <int METRIC, bool GLOBAL_VISITED, bool FILTERED, bool SQ8 = false>
+__global__ void __launch_bounds__(128, TURDB_MIN_CTAS) hnsw_search_kernel(const SearchArgs a) {
+  hnsw_search_body<METRIC, GLOBAL_VISITED, FILTERED, SQ8, false>(a);
+}
+
+// direct form: one warp per query, rows straight into registers (short rows)
+#ifndef TURDB_WARP_MIN_CTAS
+#define TURDB_WARP_MIN_CTAS 20
+#endif
+template <int METRIC, bool GLOBAL_VISITED, bool FILTERED>
+__global__ void __launch_bounds__(32, TURDB_WARP_MIN_CTAS) hnsw_search_warp_kernel(const SearchArgs a) {
+  hnsw_search_body<METRIC, GLOBAL_VISITED, FILTERED, false, true>(a);
 }
 
 }  // namespace turdb

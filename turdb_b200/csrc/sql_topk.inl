@@ -1,202 +1,402 @@
 // sql_topk.inl — the SQL vector-scan operator: `ORDER BY vec <op> '[...]' LIMIT k OFFSET o` for a batch of
-// statements (TopKExec, src/sql/executor.rs:2239-2392; sort-key arithmetic :169-212).  SURVEY.md §8(f) rank 3,
-// BASELINE.json config 5's "SQL ORDER BY distance LIMIT 10 batch path".  Included by turdb_cuda.cu.
+// statements (TopKExec, src/sql/executor.rs:2239-2392; sort-key arithmetic :169-212; projected value
+// src/sql/predicate.rs:1634-1688).  SURVEY.md §8(f) rank 3, BASELINE.json config 5's "SQL ORDER BY distance LIMIT 10
+// batch path".  Included by turdb_cuda.cu.
 //
-// The reference evaluates an f64 sort key per row (L2: sqrt(sum_f64(((a-b) as f32 -> f64)^2)); cosine:
-// 1 - dot/(|a||b|) in f64, NULL when a norm is 0) and keeps the limit+offset smallest.  Here the candidate
-// rows come from the HNSW metric contract in FP32 (exact path: tensor-core filter + FP32 rerank; or the graph
-// traversal when use_index != 0), a margin wider than limit+offset, and the f64 key is then evaluated for
-// those candidates only, in the reference's summation order, and the rows re-sorted by (key, scan position).
-// Exact scan: a query is CERTIFIED when its (limit+offset)-th f64 key lies below every row outside the
-// candidate set by more than the FP32/f64 discrepancy bound; an uncertified query is reported
-// (count 0xFFFFFFFD) and the host retries it with a wider margin.
+// The reference streams the table in primary-key order through a (limit+offset)-row max-heap: the first K rows are
+// pushed and stably sorted worst-first, every later row replaces the root iff its key is STRICTLY smaller (sift-down
+// preferring the left child on ties), and a final stable ascending sort yields rows [offset, offset+limit).  Which of
+// several equal keys survive, and in which order they are returned, follows from that procedure alone — so it is
+// REPLAYED here, exactly, over a SUPERSET of the rows the reference would ever have pushed:
+//   exact scan : the certified tensor-core filter (exact_search.cuh) — every slice's arrivals, archived;
+//   use_index  : the HNSW traversal's ef best rows ("TopKExec over the rows the index returns").
+// Rows the reference would not have pushed are ignored by the replay itself (their key is not below the root), so
+// feeding a superset in scan order reproduces the reference's heap state step by step.  Keys are its f64 values in its
+// summation order.  A query whose candidate buffers overflowed is redone by sql_stream_scan_kernel, which IS the
+// reference's loop over all rows.  Order among NULL (NaN) keys is unspecified, as Rust's sort_by is for them.
 
 namespace turdb {
 
-// One warp per statement; lane j evaluates candidates j, j+32, ...  Keys in shared memory, bitonic sort by
-// (key, node id) with NULL (NaN) keys last, rows [offset, offset+limit) written out.
+// ORDER BY key (executor.rs:169-212).  OP 0: sqrt(sum_f64(((row - literal) as f32 -> f64)^2)); OP 1: 1 - dot/(|l||r|)
+// in f64, NULL (NaN) when a norm is zero.  mag_q = |literal| (OP 1).
 template <int OP>
-__global__ void __launch_bounds__(128) sql_rekey_kernel(DeviceIndex ix, const float* __restrict__ queries, uint32_t nq,
-                                                        uint32_t kq, uint32_t limit, uint32_t offset,
-                                                        const uint32_t* __restrict__ cand_nodes,
-                                                        const float* __restrict__ cand_dist,
-                                                        const uint32_t* __restrict__ cand_counts, int certify,
-                                                        uint64_t* out_rows, double* out_keys, uint32_t* out_counts) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  const uint32_t q = blockIdx.x * wpb + warp;
-  uint32_t n2 = 1;
-  while (n2 < kq) n2 <<= 1;
-  double* sk = reinterpret_cast<double*>(smem_raw) + (size_t)warp * n2;                 // [wpb][n2]
-  uint32_t* si = reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(smem_raw) + (size_t)wpb * n2) + (size_t)warp * n2;
-  if (q >= nq) return;
-  const uint32_t cnt = min(cand_counts[q], kq);
-  const float* a = queries + (size_t)q * ix.dim;
-  const double nan = __longlong_as_double(0x7FF8000000000000ll);
-  double mag_q = 0.0;
-  if (OP == 1) {  // mag_r of the literal: sum of x.powi(2) in f64, sequential (executor.rs:198)
+__device__ __forceinline__ double sql_key64(const float* __restrict__ q, const float* __restrict__ row, uint32_t dim,
+                                            double mag_q) {
+  if (OP == 0) {
     double s = 0.0;
-    for (uint32_t i = 0; i < ix.dim; ++i) {
-      const double x = (double)__ldg(a + i);
-      s = __dadd_rn(s, __dmul_rn(x, x));
+    for (uint32_t i = 0; i < dim; ++i) {
+      const double d = (double)__fsub_rn(row[i], q[i]);
+      s = __dadd_rn(s, __dmul_rn(d, d));
     }
-    mag_q = __dsqrt_rn(s);
+    return __dsqrt_rn(s);
   }
-  for (uint32_t c = lane; c < n2; c += 32) {
-    double key = nan;
-    uint32_t id = 0xFFFFFFFFu;
-    if (c < cnt) {
-      id = cand_nodes[(size_t)q * kq + c];
-      const float* b = ix.arena + (size_t)id * ix.ds;
-      if (OP == 0) {  // executor.rs:174-183: row - literal in f32, squared and summed in f64, sqrt
-        double s = 0.0;
-        for (uint32_t i = 0; i < ix.dim; ++i) {
-          const double d = (double)__fsub_rn(b[i], __ldg(a + i));
-          s = __dadd_rn(s, __dmul_rn(d, d));
+  double dot = 0.0, sl = 0.0;
+  for (uint32_t i = 0; i < dim; ++i) {
+    const double x = (double)row[i];
+    dot = __dadd_rn(dot, __dmul_rn(x, (double)q[i]));
+    sl = __dadd_rn(sl, __dmul_rn(x, x));
+  }
+  const double mag_l = __dsqrt_rn(sl);
+  if (mag_l > 0.0 && mag_q > 0.0) return __dsub_rn(1.0, __ddiv_rn(dot, __dmul_rn(mag_l, mag_q)));
+  return __longlong_as_double(0x7FF8000000000000ll);
+}
+__device__ __forceinline__ double sql_mag64(const float* __restrict__ q, uint32_t dim) {
+  double s = 0.0;
+  for (uint32_t i = 0; i < dim; ++i) {
+    const double x = (double)q[i];
+    s = __dadd_rn(s, __dmul_rn(x, x));
+  }
+  return __dsqrt_rn(s);
+}
+
+// Projected value of `vec <op> literal` (predicate.rs:1634-1688): f32, sequential, unfused; returned as f64.
+// op 0: sqrt(sum (a-b)*(a-b)); 1: 1 - dot/(|a||b|) with each norm's own sqrt, NULL (NaN) on a zero norm; 2: +dot.
+__device__ __forceinline__ double sql_projection(int op, const float* __restrict__ a, const float* __restrict__ b, uint32_t dim) {
+  if (op == 0) {
+    float s = 0.f;
+    for (uint32_t i = 0; i < dim; ++i) {
+      const float d = __fsub_rn(a[i], b[i]);
+      s = __fadd_rn(s, __fmul_rn(d, d));
+    }
+    return (double)__fsqrt_rn(s);
+  }
+  float dot = 0.f;
+  for (uint32_t i = 0; i < dim; ++i) dot = __fadd_rn(dot, __fmul_rn(a[i], b[i]));
+  if (op == 2) return (double)dot;
+  float n1 = 0.f, n2 = 0.f;
+  for (uint32_t i = 0; i < dim; ++i) n1 = __fadd_rn(n1, __fmul_rn(a[i], a[i]));
+  for (uint32_t i = 0; i < dim; ++i) n2 = __fadd_rn(n2, __fmul_rn(b[i], b[i]));
+  n1 = __fsqrt_rn(n1);
+  n2 = __fsqrt_rn(n2);
+  if (n1 == 0.f || n2 == 0.f) return __longlong_as_double(0x7FF8000000000000ll);
+  return (double)__fsub_rn(1.0f, __fdiv_rn(dot, __fmul_rn(n1, n2)));
+}
+
+// TopKExec's heap, driven by one warp.  hk/hid: the heap (K entries); tk/tid: scratch of the same size for the two
+// stable sorts.  All state lives in shared memory; `len` is warp-uniform.
+struct TopKReplay {
+  double* hk;
+  uint32_t* hid;
+  double* tk;
+  uint32_t* tid;
+  uint32_t K, len;
+
+  // total preorder used by the two sorts: numbers by value, NULL (NaN) keys after every number, equal among themselves
+  static __device__ __forceinline__ bool lt(double a, double b) { return a < b || (b != b && a == a); }
+
+  // stable sort of the heap array: DESC (worst first, executor.rs:2260-2275) or ascending (:2360-2370).  Rank sort:
+  // position = elements strictly before + equivalent elements with a smaller index.
+  __device__ __forceinline__ void stable_sort(bool desc, uint32_t lane) {
+    __syncwarp();
+    for (uint32_t i = lane; i < len; i += 32) {
+      const double ki = hk[i];
+      uint32_t pos = 0;
+      for (uint32_t j = 0; j < len; ++j) {
+        const double kj = hk[j];
+        const bool before = desc ? lt(ki, kj) : lt(kj, ki);
+        const bool after = desc ? lt(kj, ki) : lt(ki, kj);
+        pos += (before || (!after && j < i)) ? 1u : 0u;
+      }
+      tk[pos] = ki;
+      tid[pos] = hid[i];
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < len; i += 32) {
+      hk[i] = tk[i];
+      hid[i] = tid[i];
+    }
+    __syncwarp();
+  }
+
+  // rows in scan order (ascending id); keys[i] belongs to ids[i].  n <= whatever the caller staged.
+  __device__ __forceinline__ void feed(const uint32_t* ids, const double* keys, uint32_t n, uint32_t lane) {
+    uint32_t c = 0;
+    if (len < K) {  // executor.rs:2248-2259: push until the heap holds limit + offset rows
+      const uint32_t take = min(K - len, n);
+      for (uint32_t i = lane; i < take; i += 32) {
+        hk[len + i] = keys[i];
+        hid[len + i] = ids[i];
+      }
+      len += take;
+      c = take;
+      __syncwarp();
+      if (len == K) stable_sort(true, lane);
+    }
+    for (uint32_t base = c; base < n; base += 32) {
+      const uint32_t i = base + lane;
+      const double kc = i < n ? keys[i] : 0.0;
+      // the root only ever decreases: a row that fails now can never pass later
+      uint32_t mask = __ballot_sync(kFullMask, i < n && kc < hk[0]);
+      while (mask) {
+        const uint32_t l = __ffs(mask) - 1;
+        mask &= mask - 1;
+        if (lane == 0) {
+          const double k = keys[base + l];
+          if (k < hk[0]) {  // strictly less replaces the root (executor.rs:2277-2290), then sift down (:2292-2357)
+            hk[0] = k;
+            hid[0] = ids[base + l];
+            uint32_t p = 0;
+            for (;;) {
+              const uint32_t left = 2 * p + 1, right = 2 * p + 2;
+              uint32_t largest = p;
+              if (left < len && hk[left] > hk[largest]) largest = left;
+              if (right < len && hk[right] > hk[largest]) largest = right;
+              if (largest == p) break;
+              const double tkk = hk[p];
+              const uint32_t tii = hid[p];
+              hk[p] = hk[largest];
+              hid[p] = hid[largest];
+              hk[largest] = tkk;
+              hid[largest] = tii;
+              p = largest;
+            }
+          }
         }
-        key = __dsqrt_rn(s);
-      } else {        // executor.rs:188-206
-        double dot = 0.0, sl = 0.0;
-        for (uint32_t i = 0; i < ix.dim; ++i) {
-          const double x = (double)b[i];
-          dot = __dadd_rn(dot, __dmul_rn(x, (double)__ldg(a + i)));
-          sl = __dadd_rn(sl, __dmul_rn(x, x));
-        }
-        const double mag_l = __dsqrt_rn(sl);
-        if (mag_l > 0.0 && mag_q > 0.0) key = __dsub_rn(1.0, __ddiv_rn(dot, __dmul_rn(mag_l, mag_q)));
+        __syncwarp();
       }
     }
-    sk[c] = key;
-    si[c] = id;
   }
+};
+
+// rows [offset, offset + limit) of the finished heap -> outputs (one warp)
+__device__ __forceinline__ void sql_emit(const DeviceIndex& ix, TopKReplay& h, const float* __restrict__ qv, uint32_t q,
+                                         uint32_t limit, uint32_t offset, int proj_op, uint64_t* out_rows, double* out_keys,
+                                         double* out_proj, uint32_t* out_counts, uint32_t lane) {
+  h.stable_sort(false, lane);
+  const double nan = __longlong_as_double(0x7FF8000000000000ll);
+  const uint32_t have = h.len > offset ? min(h.len - offset, limit) : 0u;
+  for (uint32_t i = lane; i < limit; i += 32) {
+    const size_t o = (size_t)q * limit + i;
+    if (i < have) {
+      const uint32_t id = h.hid[offset + i];
+      out_rows[o] = ix.row_ids[id];
+      out_keys[o] = h.hk[offset + i];
+      if (out_proj) out_proj[o] = sql_projection(proj_op, ix.arena + (size_t)id * ix.ds, qv, ix.dim);
+    } else {
+      out_rows[o] = 0xFFFFFFFFFFFFFFFFull;
+      out_keys[o] = nan;
+      if (out_proj) out_proj[o] = nan;
+    }
+  }
+  if (lane == 0) out_counts[q] = have;
+}
+
+// One warp (= one CTA) per statement: candidate ids -> ascending (scan order) -> f64 keys -> replay -> output.
+// smem: ids [n2] u32 | keys [n2] f64 | heap 2 x K x (f64 + u32)
+template <int OP>
+__global__ void __launch_bounds__(32) sql_replay_kernel(DeviceIndex ix, const float* __restrict__ queries, uint32_t nq,
+                                                        uint32_t limit, uint32_t offset, const uint32_t* __restrict__ cand_ids,
+                                                        const uint32_t* __restrict__ cand_counts, uint32_t cand_stride,
+                                                        uint32_t n2max, const uint32_t* __restrict__ qflags, int proj_op,
+                                                        uint64_t* out_rows, double* out_keys, double* out_proj,
+                                                        uint32_t* out_counts) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const uint32_t lane = threadIdx.x, q = blockIdx.x;
+  if (q >= nq) return;
+  if (qflags && qflags[q]) return;  // redone by the streaming scan
+  const uint32_t K = limit + offset;
+  double* keys = reinterpret_cast<double*>(smem_raw);
+  TopKReplay h;
+  h.hk = keys + n2max;
+  h.tk = h.hk + K;
+  uint32_t* ids = reinterpret_cast<uint32_t*>(h.tk + K);
+  h.hid = ids + n2max;
+  h.tid = h.hid + K;
+  h.K = K;
+  h.len = 0;
+  const uint32_t cnt = min(cand_counts[q], min(cand_stride, n2max));
+  uint32_t n2 = 1;
+  while (n2 < cnt) n2 <<= 1;
+  for (uint32_t i = lane; i < n2; i += 32) ids[i] = i < cnt ? cand_ids[(size_t)q * cand_stride + i] : 0xFFFFFFFFu;
   __syncwarp();
-  auto first = [](double ka, uint32_t ia, double kb, uint32_t ib) {
-    const bool na = ka != ka, nb = kb != kb;  // NULL keys after every number; absent entries (id INVALID) last
-    if (na != nb) return nb;
-    if (!na && ka != kb) return ka < kb;
-    return ia < ib;
-  };
   for (uint32_t size = 2; size <= n2; size <<= 1) {
     for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
       for (uint32_t i = lane; i < n2; i += 32) {
         const uint32_t j = i ^ stride;
         if (j > i) {
           const bool asc = (i & size) == 0;
-          const double ki = sk[i], kj = sk[j];
-          const uint32_t ii = si[i], ij = si[j];
-          if (first(ki, ii, kj, ij) != asc) {
-            sk[i] = kj; sk[j] = ki;
-            si[i] = ij; si[j] = ii;
+          const uint32_t a = ids[i], b = ids[j];
+          if ((a < b) != asc) {
+            ids[i] = b;
+            ids[j] = a;
           }
         }
       }
       __syncwarp();
     }
   }
+  const float* qv = queries + (size_t)q * ix.dim;
+  const double mag_q = OP == 1 ? sql_mag64(qv, ix.dim) : 0.0;
+  for (uint32_t i = lane; i < cnt; i += 32) keys[i] = sql_key64<OP>(qv, ix.arena + (size_t)ids[i] * ix.ds, ix.dim, mag_q);
+  __syncwarp();
+  if (K) h.feed(ids, keys, cnt, lane);
+  sql_emit(ix, h, qv, q, limit, offset, proj_op, out_rows, out_keys, out_proj, out_counts, lane);
+}
+
+// The reference's loop itself, for the statements the filter could not serve (qflags[q] != 0; e.g. thousands of rows
+// tying with the limit-th key, or data on which the BF16 error bound admits too many candidates): every row's f64 key
+// in primary-key order through the same heap.  CTAs stride over the statements and skip the unflagged ones; always
+// enqueued, exits at once when nothing is flagged.  smem: chunk ids [256] | chunk keys [256] | heap.
+template <int OP>
+__global__ void __launch_bounds__(256) sql_stream_scan_kernel(DeviceIndex ix, const float* __restrict__ queries, uint32_t nq,
+                                                              uint32_t limit, uint32_t offset,
+                                                              const uint32_t* __restrict__ qflags, int proj_op,
+                                                              uint64_t* out_rows, double* out_keys, double* out_proj,
+                                                              uint32_t* out_counts) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t K = limit + offset;
-  bool certified = true;
-  if (certify && cnt == kq && K > 0 && cnt > 0) {
-    // rows outside the candidate set have an FP32 metric >= the largest candidate's (cand_dist is ascending)
-    const float worst32 = cand_dist[(size_t)q * kq + cnt - 1];
-    const uint32_t kth = min(K, cnt) - 1;
-    const double kth_key = sk[kth];
-    double bound;
-    if (OP == 0) bound = sqrt(fmax(0.0, (double)worst32 * (1.0 - 1e-4)));  // squared L2 in FP32 vs f64: rel. 1e-4 >> dim * 2^-24
-    else bound = (double)worst32 - 1e-5;
-    certified = !(kth_key != kth_key) && kth_key < bound;
-  }
-  const uint32_t have = cnt > offset ? min(cnt - offset, limit) : 0u;
-  for (uint32_t i = lane; i < limit; i += 32) {
-    const size_t o = (size_t)q * limit + i;
-    if (i < have && certified) {
-      out_rows[o] = ix.row_ids[si[offset + i]];
-      out_keys[o] = sk[offset + i];
-    } else {
-      out_rows[o] = 0xFFFFFFFFFFFFFFFFull;
-      out_keys[o] = nan;
+  double* ckeys = reinterpret_cast<double*>(smem_raw);
+  TopKReplay h;
+  h.hk = ckeys + 256;
+  h.tk = h.hk + K;
+  uint32_t* cids = reinterpret_cast<uint32_t*>(h.tk + K);
+  h.hid = cids + 256;
+  h.tid = h.hid + K;
+  h.K = K;
+  for (uint32_t q = blockIdx.x; q < nq; q += gridDim.x) {
+    if (!qflags[q]) continue;
+    const float* qv = queries + (size_t)q * ix.dim;
+    const double mag_q = OP == 1 ? sql_mag64(qv, ix.dim) : 0.0;
+    h.len = 0;
+    __syncthreads();
+    for (uint64_t base = 0; base < ix.n && K; base += 256) {
+      const uint64_t r = base + tid;
+      if (r < ix.n) {
+        ckeys[tid] = sql_key64<OP>(qv, ix.arena + r * ix.ds, ix.dim, mag_q);
+        cids[tid] = (uint32_t)r;
+      }
+      __syncthreads();
+      if (warp == 0) h.feed(cids, ckeys, (uint32_t)min((uint64_t)256, (uint64_t)(ix.n - base)), lane);
+      __syncthreads();
     }
+    if (warp == 0) sql_emit(ix, h, qv, q, limit, offset, proj_op, out_rows, out_keys, out_proj, out_counts, lane);
+    __syncthreads();
   }
-  if (lane == 0) out_counts[q] = certified ? have : 0xFFFFFFFDu;
+}
+
+__global__ void fill_empty_sql_kernel(uint64_t* rows, double* keys, double* proj, uint32_t* counts, uint32_t nq, uint32_t limit) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (uint64_t)nq * limit) {
+    rows[i] = 0xFFFFFFFFFFFFFFFFull;
+    keys[i] = __longlong_as_double(0x7FF8000000000000ll);
+    if (proj) proj[i] = __longlong_as_double(0x7FF8000000000000ll);
+  }
+  if (i < nq) counts[i] = 0;
 }
 
 }  // namespace turdb
 
+// defined in exact_abi.inl: the certified filter, archiving every arrival (ids) per query
+static int32_t exact_filter_archive(turdb_cuda_index* idx, const float* d_queries, uint32_t nq, uint32_t K, uint8_t metric,
+                                    uint32_t arch_cap, uint32_t* d_arch_cnt, uint32_t* d_arch_id, uint32_t* d_qflags,
+                                    cudaStream_t stream);
+
 extern "C" int32_t turdb_cuda_sql_topk_batch_device(turdb_cuda_index* idx, const float* d_queries, uint32_t query_dim,
                                                     uint32_t nq, uint32_t limit, uint32_t offset, uint8_t op,
-                                                    uint32_t margin, int32_t use_index, uint32_t ef,
-                                                    uint64_t* d_out_row_ids, double* d_out_keys, uint32_t* d_out_counts,
-                                                    void* stream_) {
+                                                    uint8_t proj_op, int32_t use_index, uint32_t ef,
+                                                    uint64_t* d_out_row_ids, double* d_out_keys, double* d_out_proj,
+                                                    uint32_t* d_out_counts, void* stream_) {
   if (!idx) return fail(TURDB_ERR_INVALID_ARGUMENT, "idx is null");
   if (query_dim != idx->ix.dim)
     return fail(TURDB_ERR_DIMENSION_MISMATCH, "query dimension %u does not match index dimension %u", query_dim, idx->ix.dim);
   if (op > 1)
     return fail(TURDB_ERR_UNSUPPORTED, "ORDER BY <#> evaluates to NULL for every row in the reference (executor.rs:241); "
                                        "only <-> (0) and <=> (1) are sort keys");
+  if (d_out_proj && proj_op > 2) return fail(TURDB_ERR_INVALID_ARGUMENT, "proj_op %u unknown (0 <->, 1 <=>, 2 <#>)", proj_op);
   if (nq == 0) return TURDB_OK;
   if (!d_queries || !d_out_counts || (limit && (!d_out_row_ids || !d_out_keys)))
     return fail(TURDB_ERR_INVALID_ARGUMENT, "null query/output pointer");
-  const uint64_t K = (uint64_t)limit + offset;
-  if (K > 1024) return fail(TURDB_ERR_UNSUPPORTED, "limit + offset = %llu > 1024", (unsigned long long)K);
+  const uint64_t K64 = (uint64_t)limit + offset;
+  if (K64 > TURDB_SQL_MAX_LIMIT_PLUS_OFFSET)
+    return fail(TURDB_ERR_UNSUPPORTED, "limit + offset = %llu > %u", (unsigned long long)K64, TURDB_SQL_MAX_LIMIT_PLUS_OFFSET);
+  const uint32_t K = (uint32_t)K64;
   cudaStream_t stream = (cudaStream_t)stream_;
   DeviceGuard guard(idx->device);
   if (!guard.ok) return fail(TURDB_ERR_CUDA, "cudaSetDevice(%d) failed", idx->device);
   const uint64_t n = idx->ix.n;
-  if (!margin) margin = (uint32_t)std::max<uint64_t>(8, K / 4);
-  const uint32_t kq = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(K + margin, 1), std::max<uint64_t>(n, 1));
-  if (use_index && ef < kq) ef = kq;
+  if (n == 0 || limit == 0) {
+    uint64_t total = std::max<uint64_t>((uint64_t)nq * std::max(limit, 1u), nq);
+    fill_empty_sql_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_out_row_ids, d_out_keys, d_out_proj, d_out_counts, nq, limit);
+    CUDA_TRY(cudaGetLastError());
+    return TURDB_OK;
+  }
 
+  // candidate ids per statement: [nq][stride]
+  uint32_t stride;
+  if (use_index) {
+    if (ef < K) ef = K;
+    if (ef > 2048) return fail(TURDB_ERR_UNSUPPORTED, "index-backed scan needs ef >= limit + offset = %u > 2048", K);
+    stride = ef;  // TopKExec over every row the index's beam returns
+  } else {
+    // first slice (>= 2K rows, all archived) + the arrivals of ~log3(n) later slices (~1.1 K each without slack)
+    uint32_t want = std::max(256u, 2 * K) + 12 * K + 512;
+    stride = 1024;
+    while (stride < want) stride <<= 1;
+  }
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
     off = (off + bytes + 255) & ~(size_t)255;
     return o;
   };
-  const size_t o_rows = take((size_t)nq * kq * 8), o_nodes = take((size_t)nq * kq * 4), o_dist = take((size_t)nq * kq * 4),
-               o_cnt = take((size_t)nq * 4);
+  const size_t o_ids = take((size_t)nq * stride * 4), o_cnt = take((size_t)nq * 4), o_flags = take((size_t)nq * 4),
+               o_rows = take(use_index ? (size_t)nq * stride * 8 : 0), o_dist = take(use_index ? (size_t)nq * stride * 4 : 0);
   uint8_t* scr = nullptr;
   CUDA_TRY(cudaMallocFromPoolAsync(&scr, off, idx->pool, stream));
-  uint64_t* c_rows = (uint64_t*)(scr + o_rows);
-  uint32_t* c_nodes = (uint32_t*)(scr + o_nodes);
-  float* c_dist = (float*)(scr + o_dist);
+  uint32_t* c_ids = (uint32_t*)(scr + o_ids);
   uint32_t* c_cnt = (uint32_t*)(scr + o_cnt);
+  uint32_t* c_flags = (uint32_t*)(scr + o_flags);
   int32_t rc;
-  if (use_index)
-    rc = turdb_cuda_search_batch_device(idx, d_queries, query_dim, nq, kq, ef, op, nullptr, c_rows, c_nodes, c_dist, c_cnt,
-                                        nullptr, stream);
-  else
-    rc = turdb_cuda_bruteforce_topk_device(idx, d_queries, query_dim, nq, kq, op, 0, c_rows, c_nodes, c_dist, c_cnt, stream);
+  if (use_index) {
+    cudaMemsetAsync(c_flags, 0, (size_t)nq * 4, stream);
+    rc = turdb_cuda_search_batch_device(idx, d_queries, query_dim, nq, stride, ef, op, nullptr, (uint64_t*)(scr + o_rows), c_ids,
+                                        (float*)(scr + o_dist), c_cnt, nullptr, stream);
+  } else {
+    rc = exact_filter_archive(idx, d_queries, nq, K, op, stride, c_cnt, c_ids, c_flags, stream);
+  }
   if (rc != TURDB_OK) {
     cudaFreeAsync(scr, stream);
     return rc;
   }
-  uint32_t n2 = 1;
-  while (n2 < kq) n2 <<= 1;
-  const uint32_t wpb = 4;
-  const size_t smem = (size_t)wpb * n2 * 12;
-  const uint32_t blocks = (nq + wpb - 1) / wpb;
-  const int certify = (!use_index && kq < n) ? 1 : 0;
+  const size_t heap_bytes = (size_t)2 * K * 12 + 32;
+  const size_t smem_replay = (size_t)stride * 12 + heap_bytes, smem_scan = (size_t)256 * 12 + heap_bytes;
   cudaError_t e = cudaSuccess;
-  if (smem > 48 * 1024) {
-    e = cudaFuncSetAttribute(sql_rekey_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sql_rekey_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto raise = [&](auto kern, size_t smem) {
+    if (e == cudaSuccess && smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  };
+  const uint32_t scan_grid = (uint32_t)std::min<uint64_t>(nq, 2ull * idx->num_sms);
+  if (op == 0) {
+    raise(sql_replay_kernel<0>, smem_replay);
+    raise(sql_stream_scan_kernel<0>, smem_scan);
+    if (e == cudaSuccess) {
+      sql_replay_kernel<0><<<nq, 32, smem_replay, stream>>>(idx->ix, d_queries, nq, limit, offset, c_ids, c_cnt, stride, stride, c_flags,
+                                                           proj_op, d_out_row_ids, d_out_keys, d_out_proj, d_out_counts);
+      if (!use_index)
+        sql_stream_scan_kernel<0><<<scan_grid, 256, smem_scan, stream>>>(idx->ix, d_queries, nq, limit, offset, c_flags, proj_op,
+                                                                        d_out_row_ids, d_out_keys, d_out_proj, d_out_counts);
+    }
+  } else {
+    raise(sql_replay_kernel<1>, smem_replay);
+    raise(sql_stream_scan_kernel<1>, smem_scan);
+    if (e == cudaSuccess) {
+      sql_replay_kernel<1><<<nq, 32, smem_replay, stream>>>(idx->ix, d_queries, nq, limit, offset, c_ids, c_cnt, stride, stride, c_flags,
+                                                           proj_op, d_out_row_ids, d_out_keys, d_out_proj, d_out_counts);
+      if (!use_index)
+        sql_stream_scan_kernel<1><<<scan_grid, 256, smem_scan, stream>>>(idx->ix, d_queries, nq, limit, offset, c_flags, proj_op,
+                                                                        d_out_row_ids, d_out_keys, d_out_proj, d_out_counts);
+    }
   }
-  if (e == cudaSuccess) {
-    if (op == 0)
-      sql_rekey_kernel<0><<<blocks, wpb * 32, smem, stream>>>(idx->ix, d_queries, nq, kq, limit, offset, c_nodes, c_dist, c_cnt,
-                                                              certify, d_out_row_ids, d_out_keys, d_out_counts);
-    else
-      sql_rekey_kernel<1><<<blocks, wpb * 32, smem, stream>>>(idx->ix, d_queries, nq, kq, limit, offset, c_nodes, c_dist, c_cnt,
-                                                              certify, d_out_row_ids, d_out_keys, d_out_counts);
-    e = cudaGetLastError();
-  }
+  if (e == cudaSuccess) e = cudaGetLastError();
   cudaFreeAsync(scr, stream);
-  if (e != cudaSuccess) return fail(TURDB_ERR_CUDA, "sql_rekey launch failed: %s", cudaGetErrorString(e));
+  if (e != cudaSuccess) return fail(TURDB_ERR_CUDA, "sql_topk launch failed: %s", cudaGetErrorString(e));
   return TURDB_OK;
 }
 
 extern "C" int32_t turdb_cuda_sql_topk_batch(turdb_cuda_index* idx, const float* queries, uint32_t query_dim, uint32_t nq,
-                                             uint32_t limit, uint32_t offset, uint8_t op, int32_t use_index, uint32_t ef,
-                                             uint64_t* out_row_ids, double* out_keys, uint32_t* out_counts) {
+                                             uint32_t limit, uint32_t offset, uint8_t op, uint8_t proj_op, int32_t use_index,
+                                             uint32_t ef, uint64_t* out_row_ids, double* out_keys, double* out_proj,
+                                             uint32_t* out_counts) {
   if (!idx) return fail(TURDB_ERR_INVALID_ARGUMENT, "idx is null");
   if (query_dim != idx->ix.dim)
     return fail(TURDB_ERR_DIMENSION_MISMATCH, "query dimension %u does not match index dimension %u", query_dim, idx->ix.dim);
@@ -209,8 +409,8 @@ extern "C" int32_t turdb_cuda_sql_topk_batch(turdb_cuda_index* idx, const float*
   CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   const size_t ll = std::max(limit, 1u);
   const size_t qbytes = (size_t)nq * query_dim * 4;
-  const size_t off_rows = (qbytes + 255) & ~(size_t)255, off_keys = off_rows + nq * ll * 8, off_counts = off_keys + nq * ll * 8,
-               total = off_counts + (size_t)nq * 4;
+  const size_t off_rows = (qbytes + 255) & ~(size_t)255, off_keys = off_rows + nq * ll * 8, off_proj = off_keys + nq * ll * 8,
+               off_counts = off_proj + nq * ll * 8, total = off_counts + (size_t)nq * 4;
   uint8_t* slab = nullptr;
   cudaError_t e = cudaMallocFromPoolAsync(&slab, total, idx->pool, stream);
   if (e != cudaSuccess) {
@@ -227,35 +427,21 @@ extern "C" int32_t turdb_cuda_sql_topk_batch(turdb_cuda_index* idx, const float*
     cleanup();
     return fail(TURDB_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
   }
-  // a query the exact scan cannot certify at the default margin is retried with 4x, then 16x the margin
-  uint32_t margin = 0;
-  const uint64_t K = (uint64_t)limit + offset;
-  for (int attempt = 0;; ++attempt) {
-    int32_t rc = turdb_cuda_sql_topk_batch_device(idx, (const float*)slab, query_dim, nq, limit, offset, op, margin, use_index,
-                                                  ef, (uint64_t*)(slab + off_rows), (double*)(slab + off_keys),
-                                                  (uint32_t*)(slab + off_counts), stream);
-    if (rc != TURDB_OK) {
-      cleanup();
-      return rc;
-    }
-    e = cudaMemcpyAsync(out_counts, slab + off_counts, (size_t)nq * 4, cudaMemcpyDeviceToHost, stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-    if (e != cudaSuccess) break;
-    bool uncertified = false;
-    for (uint32_t i = 0; i < nq; ++i) uncertified |= out_counts[i] == 0xFFFFFFFDu;
-    if (!uncertified) break;
-    if (attempt == 2) {
-      cleanup();
-      return fail(TURDB_ERR_UNSUPPORTED, "sql_topk: result not certifiable (more than %llu rows tie with the limit-th key)",
-                  (unsigned long long)(K + margin));
-    }
-    margin = (uint32_t)std::max<uint64_t>(8, K / 4) * (attempt == 0 ? 4u : 16u);
+  int32_t rc = turdb_cuda_sql_topk_batch_device(idx, (const float*)slab, query_dim, nq, limit, offset, op, proj_op, use_index, ef,
+                                                (uint64_t*)(slab + off_rows), (double*)(slab + off_keys),
+                                                out_proj ? (double*)(slab + off_proj) : nullptr, (uint32_t*)(slab + off_counts),
+                                                stream);
+  if (rc != TURDB_OK) {
+    cleanup();
+    return rc;
   }
+  e = cudaMemcpyAsync(out_counts, slab + off_counts, (size_t)nq * 4, cudaMemcpyDeviceToHost, stream);
   if (e == cudaSuccess && limit) {
     e = cudaMemcpyAsync(out_row_ids, slab + off_rows, (size_t)nq * limit * 8, cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out_keys, slab + off_keys, (size_t)nq * limit * 8, cudaMemcpyDeviceToHost, stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess && out_proj) e = cudaMemcpyAsync(out_proj, slab + off_proj, (size_t)nq * limit * 8, cudaMemcpyDeviceToHost, stream);
   }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
   cleanup();
   if (e != cudaSuccess) return fail(TURDB_ERR_CUDA, "sql_topk failed: %s", cudaGetErrorString(e));
   return TURDB_OK;

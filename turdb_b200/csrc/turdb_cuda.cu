@@ -15,7 +15,7 @@
 #include "common.cuh"
 #include "exact_search.cuh"
 #include "gather_probe.cuh"
-#include "hnsw_search.cuh"
+#include "search_kernels.h"
 
 using namespace turdb;
 
@@ -71,9 +71,15 @@ struct turdb_cuda_index {
   uint32_t sq8_row_bytes = 0;
   __nv_bfloat16* d_arena_bf16 = nullptr;   // exact path operand (raw rows: L2, IP), built lazily
   __nv_bfloat16* d_arena_bf16n = nullptr;  // exact path operand (rows scaled by 1/|x|: cosine), built lazily
+  uint32_t* d_bf16_max2 = nullptr;         // [2 copies][2]: max |v - bf16(v)|_2, max |bf16(v)|_2 over rows (float bits)
   cudaMemPool_t pool = nullptr;            // per-index stream-ordered scratch pool (never trimmed)
   uint64_t device_bytes = 0;
   uint32_t tune_warps = 0, tune_slots = 0, tune_hash_bits = 0, tune_segs = 0;
+  uint32_t tune_mode = 0;                  // 0 automatic, 1 staged (team + TMA staging), 2 direct (one warp per query)
+  // visited-set sizing: running maximum of keys per query, one counter per ceil(log2(ef)) (device + pinned mirror
+  // refreshed by an async copy after every launch; the next launch sizes its shared-memory table from it)
+  uint32_t* d_vis_max = nullptr;
+  uint32_t* h_vis_max = nullptr;
   // profiling ring: 3 events per call (before main, after main, after overflow pass)
   std::vector<cudaEvent_t> prof_events;
   uint32_t prof_capacity = 0, prof_used = 0;
@@ -204,8 +210,11 @@ int32_t turdb_cuda_index_destroy(turdb_cuda_index* idx) {
     cudaFree(idx->d_norm2_sq8);
     cudaFree(idx->d_arena_bf16);
     cudaFree(idx->d_arena_bf16n);
+    cudaFree(idx->d_bf16_max2);
     for (cudaEvent_t ev : idx->prof_events) cudaEventDestroy(ev);
     cudaFree(idx->d_dbg);
+    cudaFree(idx->d_vis_max);
+    if (idx->h_vis_max) cudaFreeHost(idx->h_vis_max);
     if (idx->pool) cudaMemPoolDestroy(idx->pool);
   }
   delete idx;
@@ -265,6 +274,12 @@ int32_t turdb_cuda_index_create(const turdb_cuda_graph* g, int32_t device, turdb
     uint64_t keep = ~0ull;  // keep freed scratch cached across synchronisations
     cudaMemPoolSetAttribute(idx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
   }
+  if (cudaMalloc(&idx->d_vis_max, 16 * 4) != cudaSuccess || cudaMemset(idx->d_vis_max, 0, 16 * 4) != cudaSuccess ||
+      cudaMallocHost(&idx->h_vis_max, 16 * 4) != cudaSuccess) {
+    turdb_cuda_index_destroy(idx);
+    return fail(TURDB_ERR_OUT_OF_MEMORY, "visited-set statistics allocation failed");
+  }
+  memset(idx->h_vis_max, 0, 16 * 4);
   const uint64_t n = g->n;
   const uint32_t dim = g->dim, ds = (dim + 3) & ~3u;
   idx->ix.n = n;
@@ -397,6 +412,14 @@ int32_t turdb_cuda_index_set_tuning(turdb_cuda_index* idx, uint32_t warps_per_ct
   return TURDB_OK;
 }
 
+int32_t turdb_cuda_index_set_traversal_form(turdb_cuda_index* idx, uint32_t form) {
+  if (!idx) return fail(TURDB_ERR_INVALID_ARGUMENT, "idx is null");
+  if (form > 2) return fail(TURDB_ERR_INVALID_ARGUMENT, "form must be 0 (automatic), 1 (staged) or 2 (direct)");
+  std::lock_guard<std::mutex> lk(idx->mu);
+  idx->tune_mode = form;
+  return TURDB_OK;
+}
+
 int32_t turdb_cuda_index_debug_counters(turdb_cuda_index* idx, int32_t enable, uint64_t* out16) {
   if (!idx) return fail(TURDB_ERR_INVALID_ARGUMENT, "idx is null");
   DeviceGuard guard(idx->device);
@@ -455,13 +478,14 @@ int32_t turdb_cuda_index_profile_read(turdb_cuda_index* idx, float* main_ms, flo
 // ------------------------------------------------------------------------------------------
 // traversal launch
 // ------------------------------------------------------------------------------------------
+// n_slots == 0: the direct form (one warp per query, no staging)
 static TeamLayout make_layout(uint32_t dim, uint32_t ds, uint32_t ef, uint32_t hash_bits, uint32_t n_slots, uint32_t n_segs,
                               bool global_visited, uint64_t n_nodes, bool filtered = false, uint32_t sq8_row_bytes = 0,
-                              uint32_t g4_boxw = 0) {
+                              uint32_t g4_boxw = 0, bool entries32 = false) {
   TeamLayout L{};
   L.vec_bytes = sq8_row_bytes ? sq8_row_bytes : ds * 4;
   const uint32_t steps = dim >> 3;
-  if (sq8_row_bytes) n_segs = 1;  // code rows are never split
+  if (sq8_row_bytes || n_slots == 0) n_segs = 1;  // code rows are never split
   n_segs = std::max(1u, std::min(n_segs, std::max(1u, steps)));
   L.seg_steps = steps ? (steps + n_segs - 1) / n_segs : 0;
   L.n_segs = L.seg_steps ? (steps + L.seg_steps - 1) / L.seg_steps : 1;
@@ -472,18 +496,18 @@ static TeamLayout make_layout(uint32_t dim, uint32_t ds, uint32_t ef, uint32_t h
   L.n_groups = n_slots / 8;
   L.key_bits = std::max(hash_bits, ceil_log2((uint32_t)std::max<uint64_t>(n_nodes, 2)));
   L.rem_bits = L.key_bits - hash_bits;
-  L.hash16 = (!global_visited && L.rem_bits <= 11) ? 1u : 0u;  // displacement field >= 5 bits
-  uint32_t off = 0;
-  L.off_bar = off;   off += 32;
-  L.off_ctl = off;   off += 32;
-  L.off_q = off;     off += (ds * 4 + 15) & ~15u;
-  L.off_list = off;  off += (filtered || TURDB_MERGE_MODE == 0) ? ef * 16 : ef * 8;  // result list (x2 when double-buffered)
+  L.hash16 = (!global_visited && !entries32 && L.rem_bits <= 11) ? 1u : 0u;  // displacement field >= 5 bits
+  // [0] mbarriers, [32] control words, [64] cand_ids[32] cand_d[32] tmp_ub[32] cand_next[32], [576] result list: fixed
+  // offsets (kOffBar .. kOffList); then the filtered window, the query, the visited table, the staging slots
+  uint32_t off = kOffList;
+  off += (filtered || TURDB_MERGE_MODE == 0) ? ef * 16 : ef * 8;  // result list (x2 when double-buffered)
   L.off_clist = off; off += filtered ? ef * 16 : 0;       // search_filtered: candidate window (double-buffered)
-  L.off_cand = off;  off += 512;  // cand_ids[32], cand_d[32], tmp_ub[32], cand_next[32]
+  off = (off + 15) & ~15u;
+  L.off_q = off;     off += (ds * 4 + 15) & ~15u;
   L.off_hash = off;  off += global_visited ? 0 : ((L.hash16 ? 2u : 4u) << hash_bits);
   off = (off + 127) & ~127u;
   L.off_stage = off;
-  if (g4_boxw && !sq8_row_bytes && L.n_segs == 1) {
+  if (g4_boxw && !sq8_row_bytes && L.n_segs == 1 && n_slots) {
     L.g4_boxw = g4_boxw;
     L.g4_pieces = (ds + g4_boxw - 1) / g4_boxw;
     const uint32_t e0 = steps * 8;  // first element of the < 8-element tail
@@ -501,69 +525,33 @@ static TeamLayout make_layout(uint32_t dim, uint32_t ds, uint32_t ef, uint32_t h
   return L;
 }
 
-template <int METRIC, bool GV, bool FILT, bool SQ8 = false>
-static cudaError_t launch_search(const SearchArgs& a, uint32_t warps, int num_sms, uint32_t max_ctas,
-                                 cudaStream_t stream, uint32_t* resident_warps) {
-  auto kern = hnsw_search_kernel<METRIC, GV, FILT, SQ8>;
-  const size_t smem = (size_t)a.lay.team_bytes;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * warps, smem);
-  if (e != cudaSuccess) return e;
-  if (occ < 1) return cudaErrorInvalidConfiguration;
-  uint32_t grid = (uint32_t)occ * num_sms;
-  if (max_ctas && grid > max_ctas) grid = max_ctas;
-  if (grid < 1) grid = 1;
-  if (resident_warps) *resident_warps = grid;
-  kern<<<grid, 32 * warps, smem, stream>>>(a);
-  return cudaGetLastError();
-}
-
-template <bool GV, bool FILT>
-static cudaError_t launch_metric2(int metric, const SearchArgs& a, uint32_t warps, int num_sms, uint32_t max_ctas,
-                                  cudaStream_t stream, uint32_t* rw) {
-  switch (metric) {
-    case kCosine: return launch_search<kCosine, GV, FILT>(a, warps, num_sms, max_ctas, stream, rw);
-    case kIP: return launch_search<kIP, GV, FILT>(a, warps, num_sms, max_ctas, stream, rw);
-    default: return launch_search<kL2, GV, FILT>(a, warps, num_sms, max_ctas, stream, rw);
-  }
-}
-template <bool GV>
-static cudaError_t launch_metric(int metric, const SearchArgs& a, uint32_t warps, int num_sms, uint32_t max_ctas,
-                                 cudaStream_t stream, uint32_t* rw, bool sq8 = false) {
-  if (sq8) {  // code-arena kernels: unfiltered search only
-    switch (metric) {
-      case kCosine: return launch_search<kCosine, GV, false, true>(a, warps, num_sms, max_ctas, stream, rw);
-      case kIP: return launch_search<kIP, GV, false, true>(a, warps, num_sms, max_ctas, stream, rw);
-      default: return launch_search<kL2, GV, false, true>(a, warps, num_sms, max_ctas, stream, rw);
+// Per-kernel state of the launch path: the dynamic shared-memory opt-in is raised once per kernel (monotonically,
+// under a lock — concurrent callers with different ef no longer race on cudaFuncSetAttribute), occupancy is queried
+// per launch.
+static std::mutex g_kernel_mu;
+static cudaError_t kernel_prepare(SearchKernelFn kern, size_t smem, uint32_t threads, int* occ) {
+  static std::vector<std::pair<const void*, size_t>> raised;
+  {
+    std::lock_guard<std::mutex> lk(g_kernel_mu);
+    size_t* cur = nullptr;
+    for (auto& kv : raised)
+      if (kv.first == (const void*)kern) cur = &kv.second;
+    if (!cur) {
+      raised.emplace_back((const void*)kern, 0);
+      cur = &raised.back().second;
+    }
+    if (smem > *cur) {
+      cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      *cur = smem;
     }
   }
-  return a.visible ? launch_metric2<GV, true>(metric, a, warps, num_sms, max_ctas, stream, rw)
-                   : launch_metric2<GV, false>(metric, a, warps, num_sms, max_ctas, stream, rw);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, (const void*)kern, (int)threads, smem);
 }
 
-template <int METRIC, bool FILT>
-static cudaError_t search_occupancy_t(uint32_t warps, size_t smem, int* occ) {
-  auto kern = hnsw_search_kernel<METRIC, false, FILT>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, 32 * warps, smem);
-}
-// resident CTAs per SM of the traversal kernel for a team of `warps` warps
-static cudaError_t search_occupancy(int metric, bool filt, uint32_t warps, size_t smem, int* occ) {
-  if (filt) {
-    switch (metric) {
-      case kCosine: return search_occupancy_t<kCosine, true>(warps, smem, occ);
-      case kIP: return search_occupancy_t<kIP, true>(warps, smem, occ);
-      default: return search_occupancy_t<kL2, true>(warps, smem, occ);
-    }
-  }
-  switch (metric) {
-    case kCosine: return search_occupancy_t<kCosine, false>(warps, smem, occ);
-    case kIP: return search_occupancy_t<kIP, false>(warps, smem, occ);
-    default: return search_occupancy_t<kL2, false>(warps, smem, occ);
-  }
+static cudaError_t kernel_launch(SearchKernelFn kern, const SearchArgs& a, uint32_t grid, uint32_t threads, cudaStream_t stream) {
+  void* params[1] = {const_cast<SearchArgs*>(&a)};
+  return cudaLaunchKernel((const void*)kern, dim3(grid), dim3(threads), params, (size_t)a.lay.team_bytes, stream);
 }
 
 __global__ void fill_empty_results_kernel(uint64_t* rows, uint32_t* nodes, float* dist, uint32_t* counts,
@@ -586,7 +574,6 @@ static int32_t search_batch_device_impl(turdb_cuda_index* idx, const float* d_qu
                                         uint32_t* d_out_counts, turdb_cuda_search_stats* d_out_stats, void* stream_,
                                         bool sq8) {
   if (!idx) return fail(TURDB_ERR_INVALID_ARGUMENT, "idx is null");
-  if (sq8 && d_visible) return fail(TURDB_ERR_UNSUPPORTED, "search_filtered over the SQ8 arena is not built");
   if (sq8 && idx->ix.n && !idx->d_arena_sq8) return fail(TURDB_ERR_INVALID_ARGUMENT, "call turdb_cuda_index_enable_sq8 first");
   if (query_dim != idx->ix.dim)
     return fail(TURDB_ERR_DIMENSION_MISMATCH, "query dimension %u does not match index dimension %u", query_dim, idx->ix.dim);
@@ -608,87 +595,171 @@ static int32_t search_batch_device_impl(turdb_cuda_index* idx, const float* d_qu
     return TURDB_OK;
   }
 
-  uint32_t tw, ts, th, tg;
+  uint32_t tw, ts, th, tg, tm, vis_seen;
+  const uint32_t ef_bucket = std::min(15u, ceil_log2(ef));
   {
     std::lock_guard<std::mutex> lk(idx->mu);
     tw = idx->tune_warps;
     ts = idx->tune_slots;
     th = idx->tune_hash_bits;
     tg = idx->tune_segs;
+    tm = idx->tune_mode;
+    vis_seen = idx->h_vis_max[ef_bucket];  // pinned mirror; refreshed asynchronously after every launch
   }
   const uint32_t ds = idx->ix.ds, dim = idx->ix.dim;
-  uint32_t hash_bits = th ? th : std::min(15u, std::max(9u, ceil_log2(ef * 64)));
-  uint32_t warps = tw ? std::min(tw, 4u) : 0u;  // team size (0: leader + one helper per staging group, below)
+  // Visited table: 2 << hash_bits bytes of shared memory per resident query — the item that decides how many
+  // queries an SM holds at small dims.  Before anything is known about the corpus it is sized for the worst case
+  // (ef * 64 keys); afterwards from the largest key count any query of this ef class has produced (+25 %: the
+  // table is declared full at 7/8).  Results never depend on it: a query that outgrows its table is redone
+  // exactly by the global-bitset pass below.
+  // 16-bit entries need key_bits - hash_bits remainder bits and at least 6 displacement bits at the loads chosen
+  // here (load <= 0.6 at the largest query); 32-bit entries have no displacement limit and may fill to 7/8.  Whichever
+  // form takes fewer bytes wins (large corpora with short traversals: 32-bit entries in a small table).
+  uint32_t hash_bits = std::min(15u, std::max(9u, ceil_log2(ef * 64)));
+  bool entries32 = false;
+  if (th) {
+    hash_bits = th;
+  } else if (vis_seen) {
+    const uint32_t key_bits = ceil_log2((uint32_t)std::max<uint64_t>(idx->ix.n, 2));
+    const uint32_t hb16 = std::min(15u, std::max({8u, ceil_log2((uint32_t)((uint64_t)vis_seen * 17 / 10 + 64)), key_bits > 10 ? key_bits - 10 : 0u}));
+    const uint32_t hb32 = std::min(15u, std::max(8u, ceil_log2((uint32_t)(((uint64_t)vis_seen + 40) * 5 / 4))));
+    const bool ok16 = key_bits <= hb16 + 10;
+    if (ok16 && (2u << hb16) <= (4u << hb32)) {
+      hash_bits = hb16;
+    } else {
+      hash_bits = hb32;
+      entries32 = true;
+    }
+  }
   const uint32_t budget = (uint32_t)idx->max_smem_optin;
   const uint64_t nn = idx->ix.n;
   const bool filt = d_visible != nullptr;
+  // form: short FP32 rows -> one warp per query, registers as the landing zone; long rows -> team + TMA staging
+  const bool direct = !sq8 && (tm == 2 || (tm == 0 && ds * 4 <= TURDB_DIRECT_MAX_ROW_BYTES));
+  uint32_t warps = direct ? 1u : (tw ? std::min(tw, 4u) : 0u);  // staged team size (0: chosen below)
   uint32_t g4w = 0;
 #if TURDB_GATHER4
-  if (!sq8 && ds <= 4 * 232) {
+  if (!sq8 && !direct && ds <= 4 * 232) {
     if (int32_t rc = ensure_row_map(idx); rc != TURDB_OK) return rc;
     g4w = idx->g4_boxw;
   }
 #endif
-  uint32_t slots = ts, segs = tg;
-  if (sq8) {
-    // code rows are short (dim + 8 B) but cost ~10 instructions per element pair to decode with the reference's
-    // roundings: the reduce phase, not the gather, bounds a hop -> one gather round (32 slots) and the full team
-    // (measured at 1M x 384: 4 warps x 32 slots 7.97 ms, 2 x 16 8.92 ms)
-    if (!slots) slots = 32;
-    segs = 1;
-    if (!warps) warps = 4;
-  }
-  if (!slots || !segs) {
-    // Measured at 1M x 384 (tools/sweep.py): whole vectors (1 piece) through 16 slots with 5 resident queries
-    // per SM beat every split; pieces only pay when a whole vector leaves fewer than 4 queries resident
-    // (large dim / large ef).  Within a piece count: resident queries x min(slots, 16) — beyond 16 slots the
-    // lost residency costs more than the saved second gather round (measured) —, ties to the deeper staging.
-    const uint32_t sm_bytes = budget + 1024;
-    double best = -1.0;
-    uint32_t bs = 8, bg = 1;
-    for (uint32_t cg = tg ? tg : 1; cg <= (tg ? tg : 8); ++cg) {
-      uint32_t best_occ = 0;
-      for (uint32_t cs = ts ? ts : 8; cs <= (ts ? ts : 32); cs += 8) {
-        TeamLayout L = make_layout(dim, ds, ef, hash_bits, cs, cg, false, nn, filt, sq8 ? idx->sq8_row_bytes : 0, g4w);
-        if (L.n_segs != cg || L.team_bytes > budget) continue;
-        if (cg > 1 && L.seg_steps * 32 < 512) continue;
-        const uint32_t occ = std::min(8u, sm_bytes / (L.team_bytes + 1024));
-        const double score = (double)occ * std::min(cs, 16u) / cg + 1e-6 * cs;
-        if (score > best) {
-          best = score;
-          bs = cs;
-          bg = cg;
-        }
-        best_occ = std::max(best_occ, occ);
-      }
-      if (best_occ >= 4) break;  // enough resident queries without (further) splitting
-    }
-    slots = bs;
-    segs = bg;
-  }
   const uint32_t rb8 = sq8 ? idx->sq8_row_bytes : 0;
-  TeamLayout lay = make_layout(dim, ds, ef, hash_bits, slots, segs, false, nn, filt, rb8, g4w);
-  // Team size: warp 0 leads (control flow + speculative preparation of the next hop), the others gather and
-  // reduce; every warp takes a share of a hop's bulk-copy issue.  Resident queries per SM come first (the
-  // kernel is latency-bound: 1M x 128, 8 queries of 2 warps beat 7 of 3 and 5 of 4, measured); among equal
-  // residency the larger team wins (shorter issue phase).
+  TeamLayout lay{};
   bool auto_warps = false;
-  if (!warps) {
-    auto_warps = true;
-    warps = 4;
+  if (direct) {
+    lay = make_layout(dim, ds, ef, hash_bits, 0, 1, false, nn, filt, 0, 0, entries32);
+    while (lay.team_bytes > budget && hash_bits > 8) lay = make_layout(dim, ds, ef, --hash_bits, 0, 1, false, nn, filt, 0, 0, entries32);
+  } else {
+    uint32_t slots = ts, segs = tg;
+    if (sq8) {
+      // code rows are short (dim + 8 B) but cost ~10 instructions per element pair to decode with the reference's
+      // roundings: the reduce phase, not the gather, bounds a hop -> one gather round (32 slots) and the full team
+      // (measured at 1M x 384: 4 warps x 32 slots 7.97 ms, 2 x 16 8.92 ms)
+      if (!slots) slots = 32;
+      segs = 1;
+      if (!warps) warps = 4;
+    }
+    if (!slots || !segs) {
+      // Measured at 1M x 384 (tools/sweep.py): whole vectors (1 piece) through 16 slots with 5 resident queries
+      // per SM beat every split; pieces only pay when a whole vector leaves fewer than 4 queries resident
+      // (large dim / large ef).  Within a piece count: resident queries x min(slots, 16) — beyond 16 slots the
+      // lost residency costs more than the saved second gather round (measured) —, ties to the deeper staging.
+      const uint32_t sm_bytes = budget + 1024;
+      double best = -1.0;
+      uint32_t bs = 8, bg = 1;
+      for (uint32_t cg = tg ? tg : 1; cg <= (tg ? tg : 8); ++cg) {
+        uint32_t best_occ = 0;
+        for (uint32_t cs = ts ? ts : 8; cs <= (ts ? ts : 32); cs += 8) {
+          TeamLayout L = make_layout(dim, ds, ef, hash_bits, cs, cg, false, nn, filt, rb8, g4w, entries32);
+          if (L.n_segs != cg || L.team_bytes > budget) continue;
+          if (cg > 1 && L.seg_steps * 32 < 512) continue;
+          const uint32_t occ = std::min(8u, sm_bytes / (L.team_bytes + 1024));
+          const double score = (double)occ * std::min(cs, 16u) / cg + 1e-6 * cs;
+          if (score > best) {
+            best = score;
+            bs = cs;
+            bg = cg;
+          }
+          best_occ = std::max(best_occ, occ);
+        }
+        if (best_occ >= 4) break;  // enough resident queries without (further) splitting
+      }
+      slots = bs;
+      segs = bg;
+    }
+    lay = make_layout(dim, ds, ef, hash_bits, slots, segs, false, nn, filt, rb8, g4w, entries32);
+    // Team size: warp 0 leads (control flow + speculative preparation of the next hop), the others gather and
+    // reduce; every warp takes a share of a hop's bulk-copy issue.  Resident queries per SM come first (the
+    // kernel is latency-bound); among equal residency the larger team wins (shorter issue phase).
+    if (!warps) {
+      auto_warps = true;
+      warps = 4;
+    }
+    while (lay.team_bytes > budget && lay.n_segs < 16 && lay.seg_steps > 8)
+      lay = make_layout(dim, ds, ef, hash_bits, lay.n_groups * 8, lay.n_segs + 1, false, nn, filt, rb8, g4w, entries32);
+    while (lay.team_bytes > budget && lay.n_groups > 1)
+      lay = make_layout(dim, ds, ef, hash_bits, lay.n_groups * 8 - 8, lay.n_segs, false, nn, filt, rb8, g4w, entries32);
+    while (lay.team_bytes > budget && hash_bits > 8)
+      lay = make_layout(dim, ds, ef, --hash_bits, lay.n_groups * 8, lay.n_segs, false, nn, filt, rb8, g4w, entries32);
   }
-  while (lay.team_bytes > budget && lay.n_segs < 16 && lay.seg_steps > 8)
-    lay = make_layout(dim, ds, ef, hash_bits, lay.n_groups * 8, lay.n_segs + 1, false, nn, filt, rb8, g4w);
-  while (lay.team_bytes > budget && lay.n_groups > 1)
-    lay = make_layout(dim, ds, ef, hash_bits, lay.n_groups * 8 - 8, lay.n_segs, false, nn, filt, rb8, g4w);
-  while (lay.team_bytes > budget && hash_bits > 8)
-    lay = make_layout(dim, ds, ef, --hash_bits, lay.n_groups * 8, lay.n_segs, false, nn, filt, rb8, g4w);
   if (lay.team_bytes > budget)
     return fail(TURDB_ERR_UNSUPPORTED, "dim %u / ef %u need %u B of shared memory per query (> %u)", idx->ix.dim, ef, lay.team_bytes, budget);
 
+  SearchKernelFn kern = get_search_kernel(metric, false, filt, sq8, direct);
+  int occ = 0;
+  cudaError_t e = cudaSuccess;
+  if (auto_warps) {
+    int best_occ = 0;
+    for (uint32_t w = 4; w >= 2; --w) {
+      int o = 0;
+      if ((e = kernel_prepare(kern, lay.team_bytes, 32 * w, &o)) != cudaSuccess) break;
+      if (o > best_occ) {
+        best_occ = o;
+        warps = w;
+      }
+    }
+    occ = best_occ;
+  } else {
+    e = kernel_prepare(kern, lay.team_bytes, 32 * warps, &occ);
+  }
+  if (e != cudaSuccess || occ < 1)
+    return fail(TURDB_ERR_CUDA, "traversal kernel does not fit an SM (%u B, %u threads): %s", lay.team_bytes, 32 * warps,
+                cudaGetErrorString(e));
+  const uint32_t grid = std::max(1u, std::min<uint32_t>(nq, (uint32_t)occ * (uint32_t)idx->num_sms));
+
+  // fallback pass geometry (queries whose visited table or filtered-candidate buffer filled): same form, one bit
+  // per node in global memory; its filtered-candidate buffer holds every node, so it cannot fail
+  TeamLayout glay = direct ? make_layout(dim, ds, ef, 8, 0, 1, true, nn, filt, 0, 0)
+                           : make_layout(dim, ds, ef, 8, lay.n_groups * 8, lay.n_segs, true, nn, filt, rb8, g4w);
+  const uint32_t vis_words = (uint32_t)(((nn + 31) / 32 + 3) & ~3ull);
+  uint32_t fb_ctas = (uint32_t)std::min<uint32_t>((uint32_t)idx->num_sms, nq);
+  const uint32_t f_ocap_main = filt ? (uint32_t)std::min<uint64_t>(nn, 32768) : 0u;
+  const uint32_t f_ocap_fb = filt ? (uint32_t)nn : 0u;
+  if (filt) {  // bound the fallback's scratch to ~1 GiB
+    const uint64_t per_cta = (uint64_t)f_ocap_fb * sizeof(uint2) + (uint64_t)vis_words * 4;
+    fb_ctas = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(fb_ctas, (1ull << 30) / std::max<uint64_t>(per_cta, 1)));
+  }
+
   uint32_t* d_scratch = nullptr;  // [0] work counter, [1] overflow count, [2] fallback work counter, [4..] overflow list
-  CUDA_TRY(cudaMallocFromPoolAsync(&d_scratch, (size_t)(4 + nq) * 4, idx->pool, stream));
-  CUDA_TRY(cudaMemsetAsync(d_scratch, 0, 16, stream));
+  uint2* d_fovf = nullptr;
+  uint32_t* d_gv = nullptr;
+  uint2* d_fovf_fb = nullptr;
+  auto release = [&]() {
+    if (d_fovf_fb) cudaFreeAsync(d_fovf_fb, stream);
+    if (d_gv) cudaFreeAsync(d_gv, stream);
+    if (d_fovf) cudaFreeAsync(d_fovf, stream);
+    if (d_scratch) cudaFreeAsync(d_scratch, stream);
+  };
+  e = cudaMallocFromPoolAsync(&d_scratch, (size_t)(4 + nq) * 4, idx->pool, stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_scratch, 0, 16, stream);
+  if (e == cudaSuccess && filt) e = cudaMallocFromPoolAsync(&d_fovf, (size_t)grid * f_ocap_main * sizeof(uint2), idx->pool, stream);
+  if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&d_gv, (size_t)fb_ctas * vis_words * 4, idx->pool, stream);
+  if (e == cudaSuccess && filt) e = cudaMallocFromPoolAsync(&d_fovf_fb, (size_t)fb_ctas * f_ocap_fb * sizeof(uint2), idx->pool, stream);
+  if (e != cudaSuccess) {
+    release();
+    return fail(e == cudaErrorMemoryAllocation ? TURDB_ERR_OUT_OF_MEMORY : TURDB_ERR_CUDA, "traversal scratch: %s", cudaGetErrorString(e));
+  }
 
   SearchArgs a{};
   a.ix = idx->ix;
@@ -713,68 +784,48 @@ static int32_t search_batch_device_impl(turdb_cuda_index* idx, const float* d_qu
   a.rows = sq8 ? idx->d_arena_sq8 : reinterpret_cast<const uint8_t*>(idx->d_arena);
   a.row_bytes = lay.vec_bytes;
   if (sq8) a.ix.norm2 = idx->d_norm2_sq8;  // cosine's norm_b chain runs over the decoded row
-  a.f_ovf = nullptr;
-  a.f_ocap = 0;
-  uint2* d_fovf = nullptr;
-  if (filt) {
-    // candidate overflow of search_filtered: one buffer per resident CTA (at most 8 per SM at any layout)
-    a.f_ocap = (uint32_t)std::min<uint64_t>(idx->ix.n, 262144);
-    const size_t ctas = (size_t)idx->num_sms * 8;
-    cudaError_t fe = cudaMallocFromPoolAsync(&d_fovf, ctas * a.f_ocap * sizeof(uint2), idx->pool, stream);
-    if (fe != cudaSuccess) {
-      cudaFreeAsync(d_scratch, stream);
-      return fail(TURDB_ERR_OUT_OF_MEMORY, "filtered-search scratch: %s", cudaGetErrorString(fe));
-    }
-    a.f_ovf = d_fovf;
-  }
+  a.f_ovf = d_fovf;
+  a.f_ocap = f_ocap_main;
+  a.vis_max = idx->d_vis_max + ef_bucket;
+
   cudaEvent_t* pev = nullptr;
   {
     std::lock_guard<std::mutex> lk(idx->mu);
     if (idx->prof_used < idx->prof_capacity) pev = &idx->prof_events[3 * idx->prof_used++];
   }
-  if (auto_warps) {
-    int best_occ = 0;
-    for (uint32_t w = 4; w >= 2; --w) {
-      int occ = 0;
-      if (search_occupancy(metric, filt, w, lay.team_bytes, &occ) != cudaSuccess) break;
-      if (occ > best_occ) {
-        best_occ = occ;
-        warps = w;
-      }
-    }
-  }
   if (pev) cudaEventRecord(pev[0], stream);
-  cudaError_t e = launch_metric<false>(metric, a, warps, idx->num_sms, filt ? std::min<uint32_t>(nq, idx->num_sms * 8) : nq, stream, nullptr, sq8);
+  e = kernel_launch(kern, a, grid, 32 * warps, stream);
   if (pev) cudaEventRecord(pev[1], stream);
   if (e != cudaSuccess) {
-    cudaFreeAsync(d_scratch, stream);
+    release();
     return fail(TURDB_ERR_CUDA, "traversal kernel launch failed: %s", cudaGetErrorString(e));
   }
 
-  // exact fallback for queries whose shared visited table filled: same kernel, one bit per node in
-  // global memory.  Always enqueued (no host sync); exits immediately when the list is empty.
+  // exact fallback: always enqueued (no host sync); exits immediately when the list is empty
   {
-    TeamLayout glay = make_layout(dim, ds, ef, 8, lay.n_groups * 8, lay.n_segs, true, nn, filt, rb8, g4w);
-    SearchArgs b = a;
-    b.lay = glay;
-    b.work_counter = d_scratch + 2;
-    b.vis_words = (uint32_t)(((idx->ix.n + 31) / 32 + 3) & ~3ull);
-    const uint32_t fb_ctas = (uint32_t)std::min<uint32_t>((uint32_t)idx->num_sms, nq);
-    uint32_t* d_gv = nullptr;
-    e = cudaMallocFromPoolAsync(&d_gv, (size_t)fb_ctas * b.vis_words * 4, idx->pool, stream);
+    SearchKernelFn gkern = get_search_kernel(metric, true, filt, sq8, direct);
+    int gocc = 0;
+    e = kernel_prepare(gkern, glay.team_bytes, 32 * warps, &gocc);
+    if (e == cudaSuccess && gocc < 1) e = cudaErrorInvalidConfiguration;
     if (e == cudaSuccess) {
+      SearchArgs b = a;
+      b.lay = glay;
+      b.work_counter = d_scratch + 2;
+      b.vis_words = vis_words;
       b.global_visited = d_gv;
-      e = launch_metric<true>(metric, b, warps, idx->num_sms, fb_ctas, stream, nullptr, sq8);
-      if (pev) cudaEventRecord(pev[2], stream);
-      cudaFreeAsync(d_gv, stream);
+      b.f_ovf = d_fovf_fb;
+      b.f_ocap = f_ocap_fb;
+      e = kernel_launch(gkern, b, fb_ctas, 32 * warps, stream);
     }
+    if (pev) cudaEventRecord(pev[2], stream);
     if (e != cudaSuccess) {
-      cudaFreeAsync(d_scratch, stream);
+      release();
       return fail(TURDB_ERR_CUDA, "fallback traversal launch failed: %s", cudaGetErrorString(e));
     }
   }
-  if (d_fovf) cudaFreeAsync(d_fovf, stream);
-  CUDA_TRY(cudaFreeAsync(d_scratch, stream));
+  // refresh the host mirror of the visited-set statistics (read by the NEXT call; never waited for)
+  cudaMemcpyAsync(idx->h_vis_max, idx->d_vis_max, 16 * 4, cudaMemcpyDeviceToHost, stream);
+  release();
   return TURDB_OK;
 }
 
@@ -790,10 +841,10 @@ extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const f
 
 extern "C" int32_t turdb_cuda_search_batch_sq8_device(turdb_cuda_index* idx, const float* d_queries, uint32_t query_dim,
                                                       uint32_t nq, uint32_t k, uint32_t ef, uint8_t metric,
-                                                      uint64_t* d_out_row_ids, uint32_t* d_out_node_ids, float* d_out_dist,
-                                                      uint32_t* d_out_counts, turdb_cuda_search_stats* d_out_stats,
-                                                      void* stream_) {
-  return search_batch_device_impl(idx, d_queries, query_dim, nq, k, ef, metric, nullptr, d_out_row_ids, d_out_node_ids,
+                                                      const uint64_t* d_visible, uint64_t* d_out_row_ids,
+                                                      uint32_t* d_out_node_ids, float* d_out_dist, uint32_t* d_out_counts,
+                                                      turdb_cuda_search_stats* d_out_stats, void* stream_) {
+  return search_batch_device_impl(idx, d_queries, query_dim, nq, k, ef, metric, d_visible, d_out_row_ids, d_out_node_ids,
                                   d_out_dist, d_out_counts, d_out_stats, stream_, true);
 }
 
@@ -861,11 +912,6 @@ extern "C" int32_t turdb_cuda_search_batch(turdb_cuda_index* idx, const float* q
   cudaStreamSynchronize(stream);
   cudaStreamDestroy(stream);
   if (e != cudaSuccess) return fail(TURDB_ERR_CUDA, "search failed: %s", cudaGetErrorString(e));
-  if (visible)
-    for (uint32_t i = 0; i < nq; ++i)
-      if (out_counts[i] == 0xFFFFFFFEu)
-        return fail(TURDB_ERR_UNSUPPORTED, "search_filtered: candidate overflow buffer exhausted for query %u "
-                    "(filter leaves too few visible nodes); use bruteforce_topk", i);
   return TURDB_OK;
 }
 

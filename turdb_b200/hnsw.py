@@ -151,6 +151,10 @@ class CudaHnswIndex:
     def set_tuning(self, warps_per_cta: int = 0, staging_slots: int = 0, hash_bits: int = 0, segments: int = 0):
         _check(_lib.load().turdb_cuda_index_set_tuning(self._h, warps_per_cta, staging_slots, hash_bits, segments))
 
+    def set_traversal_form(self, form: int = 0):
+        """0 automatic, 1 staged (team + TMA staging), 2 direct (one warp per query); results are identical."""
+        _check(_lib.load().turdb_cuda_index_set_traversal_form(self._h, form))
+
     def debug_counters(self, enable: bool = True):
         """Diagnostics: returns the 16 per-phase cycle counters accumulated so far and (re)arms or disarms them."""
         out = np.zeros(16, np.uint64)
@@ -241,10 +245,10 @@ class CudaHnswIndex:
         return raw[:, :self.dim].copy(), ms[:, 0].copy(), ms[:, 1].copy()
 
     def search_batch_sq8_device(self, d_queries, nq: int, k: int, ef: int, metric, d_rows, d_dist, d_counts, d_nodes=0,
-                                d_stats=0, stream=0):
+                                d_stats=0, stream=0, d_visible=0):
         m = int(self._metric if metric is None else metric)
-        _check(_lib.load().turdb_cuda_search_batch_sq8_device(self._h, d_queries, self.dim, nq, k, ef, m, d_rows,
-                                                              d_nodes or None, d_dist, d_counts, d_stats or None,
+        _check(_lib.load().turdb_cuda_search_batch_sq8_device(self._h, d_queries, self.dim, nq, k, ef, m, d_visible or None,
+                                                              d_rows, d_nodes or None, d_dist, d_counts, d_stats or None,
                                                               stream or None))
 
     def bruteforce_topk(self, queries, k: int, metric: DistanceFunction | None = None, rerank_factor: int = 4):

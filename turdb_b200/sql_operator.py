@@ -35,15 +35,19 @@ def parse_vector_literal(text: str) -> np.ndarray:
 
 
 class VectorScanBatch:
-    """nq statements `ORDER BY vec <op> literal_i LIMIT limit OFFSET offset` against one table."""
+    """nq statements `SELECT [vec <proj_op> literal_i] ... ORDER BY vec <op> literal_i LIMIT limit OFFSET offset` against
+    one table.  `project` = the operator whose value the statement projects (predicate.rs:1634-1688), or None."""
 
     def __init__(self, index: CudaHnswIndex, op: VectorOp, limit: int, offset: int = 0, use_index: bool = False,
-                 ef_search: int = 0):
+                 ef_search: int = 0, project: VectorOp | None = None):
         self.index, self.op, self.limit, self.offset = index, VectorOp(op), int(limit), int(offset)
         self.use_index, self.ef_search = bool(use_index), int(ef_search)
+        self.project = None if project is None else VectorOp(project)
+        self.projected = None
 
     def execute(self, literals) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
-        """-> (row_ids u64 [nq, limit], keys f64 [nq, limit] (NaN = NULL), counts u32 [nq])."""
+        """-> (row_ids u64 [nq, limit], keys f64 [nq, limit] (NaN = NULL), counts u32 [nq]); the projected values, when
+        asked for, are left in `self.projected` (f64 [nq, limit], NaN = NULL)."""
         q = np.ascontiguousarray(literals, dtype=np.float32)
         if q.ndim == 1:
             q = q[None, :]
@@ -51,19 +55,23 @@ class VectorScanBatch:
         lim = max(self.limit, 1)
         rows = np.full((nq, lim), INVALID_ROW, np.uint64)
         keys = np.full((nq, lim), np.nan, np.float64)
+        proj = np.full((nq, lim), np.nan, np.float64) if self.project is not None else None
         counts = np.zeros(nq, np.uint32)
         _check(_lib.load().turdb_cuda_sql_topk_batch(self.index._h, _ptr(q, C.c_float), qd, nq, self.limit, self.offset,
-                                                     int(self.op), 1 if self.use_index else 0, self.ef_search,
-                                                     _ptr(rows, C.c_uint64), _ptr(keys, C.c_double), _ptr(counts, C.c_uint32)))
+                                                     int(self.op), int(self.project or 0), 1 if self.use_index else 0,
+                                                     self.ef_search, _ptr(rows, C.c_uint64), _ptr(keys, C.c_double),
+                                                     _ptr(proj, C.c_double) if proj is not None else None,
+                                                     _ptr(counts, C.c_uint32)))
+        self.projected = None if proj is None else proj[:, :self.limit]
         return rows[:, :self.limit], keys[:, :self.limit], counts
 
-
-    def execute_device(self, d_literals: int, nq: int, d_rows: int, d_keys: int, d_counts: int, stream: int = 0, margin: int = 0):
-        """Device-resident form: raw device addresses, enqueued on `stream` (no host synchronisation).
-        A statement the exact scan cannot certify at this margin has count 0xFFFFFFFD."""
+    def execute_device(self, d_literals: int, nq: int, d_rows: int, d_keys: int, d_counts: int, stream: int = 0,
+                       d_proj: int = 0):
+        """Device-resident form: raw device addresses, enqueued on `stream` (no host synchronisation)."""
         _check(_lib.load().turdb_cuda_sql_topk_batch_device(self.index._h, d_literals, self.index.dim, nq, self.limit, self.offset,
-                                                            int(self.op), margin, 1 if self.use_index else 0, self.ef_search,
-                                                            d_rows, d_keys, d_counts, stream or None))
+                                                            int(self.op), int(self.project or 0), 1 if self.use_index else 0,
+                                                            self.ef_search, d_rows, d_keys, d_proj or None, d_counts,
+                                                            stream or None))
 
 
 class VectorTopKExec:
