@@ -95,6 +95,38 @@ int32_t turdb_cuda_index_info(const turdb_cuda_index* idx, uint64_t* n, uint32_t
                               uint32_t* max_level, uint32_t* entry, uint64_t* device_bytes);
 
 /*
+ * ---- graph construction: PersistentHnswIndex::insert_with_callback (mod.rs:999-1084) on the device -------------
+ * Builds the index from `n` vectors by the reference's insert path: level = select_level(random_values[i], M)
+ * (operations.rs:76-83), greedy descent over the levels above it (operations.rs:111-133), one ef_construction beam per
+ * level target..0 seeded with the same, never refined entry (operations.rs:135-171), the beam's nearest 2M (level 0) /
+ * M results selected, the new node keeps the first 32 / 16 and every selected neighbour that has the level gets a
+ * back-link: appended while its list has room (mod.rs:275-301); when full, mode 0 (verbatim) drops it and mode 1
+ * (reference-intent) re-selects the list with select_neighbors_heuristic (operations.rs:181-233).  Distances are squared
+ * L2 whatever the metric (mod.rs:1031,1046).  Nodes are inserted in id order in steps of up to max_batch nodes (never
+ * more than 1/8 of the graph built so far) that search the same snapshot of the graph; max_batch == 1 is the reference's
+ * sequential procedure exactly (same graph as the CPU oracle, bit for bit), larger steps are the batched construction.
+ * Dense node id = position in `vectors`.
+ */
+typedef struct {
+  uint32_t dim;
+  uint32_t m;               /* HnswIndex::m (2..32); m0 = 2 m (mod.rs:628-641) */
+  uint32_t ef_construction; /* mod.rs:644 default 100 */
+  uint32_t mode;            /* 0 verbatim, 1 reference-intent */
+  uint32_t max_batch;       /* 1 .. 16384 */
+  uint32_t reserved;
+} turdb_cuda_build_params;
+
+int32_t turdb_cuda_index_build(const turdb_cuda_build_params* params, uint64_t n, const float* vectors,
+                               const uint64_t* row_ids, const double* random_values, int32_t device,
+                               turdb_cuda_index** out);
+
+/* The index's graph as flat host arrays (the turdb_cuda_graph layout; counts = valid ids per row); every pointer is
+ * nullable.  up_adj / up_cnt hold *n_up_slots rows (call once with only n_up_slots to size them). */
+int32_t turdb_cuda_index_export_graph(turdb_cuda_index* idx, float* vectors, uint64_t* row_ids, uint8_t* levels,
+                                      uint32_t* l0_adj, uint8_t* l0_cnt, uint32_t* up_base, uint32_t* up_adj,
+                                      uint8_t* up_cnt, uint32_t* entry, uint32_t* max_level, uint64_t* n_up_slots);
+
+/*
  * ---- search: PersistentHnswIndex::search (mod.rs:1092-1174) for a batch of queries ----------
  * For each query: greedy descent over levels max_level..1 (search.rs:283-309), level-0 beam search
  * with ef (search.rs:311-350), truncate to k (search.rs:245-252).  `ef` plays

@@ -36,6 +36,11 @@ class HnswFileInfo(C.Structure):
                 ("n_deleted_slots", C.c_uint64), ("n_unreadable_slots", C.c_uint64)]
 
 
+class BuildParams(C.Structure):
+    _fields_ = [("dim", C.c_uint32), ("m", C.c_uint32), ("ef_construction", C.c_uint32), ("mode", C.c_uint32),
+                ("max_batch", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 GET_VECTOR_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_uint64, C.POINTER(C.c_float))
 
 # every symbol include/turdb_cuda.h declares
@@ -49,6 +54,7 @@ EXPORTS = [
     "turdb_cuda_hnsw_file_get_info", "turdb_cuda_hnsw_file_nodes", "turdb_cuda_hnsw_file_graph",
     "turdb_cuda_hnsw_file_upload", "turdb_cuda_sql_topk_batch", "turdb_cuda_sql_topk_batch_device",
     "turdb_cuda_index_enable_sq8", "turdb_cuda_search_batch_sq8_device", "turdb_cuda_shards_search_batch",
+    "turdb_cuda_index_build", "turdb_cuda_index_export_graph",
 ]
 
 _lib = None
@@ -90,6 +96,8 @@ def load():
     L.turdb_cuda_index_enable_sq8.argtypes = [vp, pu8, u64, pu32]
     L.turdb_cuda_search_batch_sq8_device.argtypes = [vp, vp, u32, u32, u32, u32, u8, vp, vp, vp, vp, vp, vp, vp]
     L.turdb_cuda_shards_search_batch.argtypes = [C.POINTER(vp), u32, pf, u32, u32, u32, u32, u8, pu64, pf, pu32]
+    L.turdb_cuda_index_build.argtypes = [C.POINTER(BuildParams), u64, pf, pu64, C.POINTER(C.c_double), i32, C.POINTER(vp)]
+    L.turdb_cuda_index_export_graph.argtypes = [vp, pf, pu64, pu8, pu32, pu8, pu32, pu32, pu8, pu32, pu32, pu64]
     L.turdb_cuda_hnsw_file_open.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.turdb_cuda_hnsw_file_open_memory.argtypes = [pu8, u64, C.POINTER(vp)]
     L.turdb_cuda_hnsw_file_close.argtypes = [vp]

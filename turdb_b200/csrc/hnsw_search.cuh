@@ -67,6 +67,8 @@
 namespace turdb {
 
 constexpr uint32_t kDone = 0xFFFFFFFFu;
+constexpr uint32_t kInsLevels = 16;   // levels 0..15 (select_level caps at 15, operations.rs:76-79)
+constexpr uint32_t kInsSelMax = 64;   // m0 = 2 M <= 64
 #ifndef TURDB_MERGE_BATCH
 #define TURDB_MERGE_BATCH 4
 #endif
@@ -121,6 +123,12 @@ struct SearchArgs {
   uint2* f_ovf;              // [CTAs][f_ocap] (distance bits, id) overflow of the candidate window
   uint32_t f_ocap;
   uint32_t* vis_max;         // optional: running maximum of visited-set keys per query (sizes the next launch's table)
+  // INSERT kernels (graph_insert.inl): query q is node ins_first + q; per level l <= ins_levels[q] the beam's nearest
+  // ins_m0 (l == 0) / ins_m ids go to ins_sel[q][l][0..ins_cnt[q][l])
+  uint32_t ins_first, ins_m, ins_m0;
+  const uint8_t* ins_levels;  // [nq]
+  uint32_t* ins_sel;          // [nq][kInsLevels][kInsSelMax]
+  uint8_t* ins_cnt;           // [nq][kInsLevels]
 };
 
 // Per-team shared state handed to every warp.
@@ -815,7 +823,7 @@ __device__ __forceinline__ uint32_t rank_merge(const float* src_d, const uint32_
   return min(n_old + mp, cap);
 }
 
-template <int METRIC, bool GLOBAL_VISITED, bool FILTERED, bool SQ8, bool DIRECT>
+template <int METRIC, bool GLOBAL_VISITED, bool FILTERED, bool SQ8, bool DIRECT, bool INSERT = false>
 __device__ __forceinline__ void hnsw_search_body(const SearchArgs& a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const DeviceIndex& ix = a.ix;
@@ -885,7 +893,9 @@ __device__ __forceinline__ void hnsw_search_body(const SearchArgs& a) {
     const uint32_t qi = GLOBAL_VISITED ? a.overflow_list[wi] : wi;
 
     // ---- stage the query, clear the visited set (whole team) ----
-    const float* qg = a.queries + (size_t)qi * ix.dim;
+    // INSERT: the "query" is the new node's own vector (insert_with_callback, mod.rs:999-1084), already in the arena
+    const float* qg = INSERT ? ix.arena + (size_t)(a.ins_first + qi) * ix.ds : a.queries + (size_t)qi * ix.dim;
+    const uint32_t target = INSERT ? a.ins_levels[qi] : 0u;  // the new node's level (select_level, operations.rs:76-83)
     for (uint32_t i = tid; i < ix.ds; i += nthreads) qs[i] = i < ix.dim ? __ldg(qg + i) : 0.f;
     {
       uint4* v4 = reinterpret_cast<uint4*>(vis);
@@ -932,7 +942,8 @@ __device__ __forceinline__ void hnsw_search_body(const SearchArgs& a) {
       n_dist_upper = 1;
 
       // greedy descent over levels max_level..1 (mod.rs:1134-1145, search.rs:259-309)
-      for (uint32_t level = ix.max_level; level >= 1; --level) {
+      // INSERT: only the levels above the new node's (insert_descent_phase, operations.rs:111-133)
+      for (uint32_t level = ix.max_level; level >= (INSERT ? target + 1 : 1u); --level) {
         for (uint32_t it = 0; it < 1000; ++it) {
           const uint32_t lv = ix.levels[cur];
           const uint32_t ub = ix.up_base[cur];
@@ -1092,7 +1103,26 @@ __device__ __forceinline__ void hnsw_search_body(const SearchArgs& a) {
           else overflow = true;
         }
       } else {
-      // level-0 beam search (search.rs:311-350) on one sorted list
+      // adjacency row of node c at level lvl, one id per lane (INVALID padded)
+      auto adj_row = [&](uint32_t c, uint32_t lvl) -> uint32_t {
+        if (!INSERT || lvl == 0) return __ldg(ix.l0_adj + (size_t)c * kL0 + lane);
+        uint32_t nid = kInvalid;
+        if (lane < kUp && lvl <= ix.levels[c]) nid = __ldg(ix.up_adj + ((size_t)ix.up_base[c] + lvl - 1) * kUp + lane);
+        return nid;
+      };
+      // search(): one beam at level 0.  INSERT: insert_connection_phase (operations.rs:135-171) — one beam per level
+      // target..0 with ef_construction, every one seeded with the SAME (cur, cur_d): the reference's second
+      // finalize_results(1) drains an already empty heap, so the entry is never refined between levels; a level above
+      // the current max_level yields just the old entry (one-way link, operations.rs:147).
+      for (int32_t blevel = (int32_t)target; blevel >= 0 && !overflow; --blevel) {
+      if (INSERT && blevel != (int32_t)target) {  // ctx.reset(): a fresh visited set per level
+        uint4* v4 = reinterpret_cast<uint4*>(vis);
+        const uint32_t n16 = GLOBAL_VISITED ? (a.vis_words >> 2) : (a.lay.hash16 ? (hash_slots >> 3) : (hash_slots >> 2));
+        const uint32_t fill = (GLOBAL_VISITED || a.lay.hash16) ? 0u : kInvalid;
+        for (uint32_t i = lane; i < n16; i += 32) v4[i] = make_uint4(fill, fill, fill, fill);
+        __syncwarp();
+      }
+      // beam search (search.rs:311-350) on one sorted list
       if (lane == 0) {
         A_d[0] = cur_d;
         A_id[0] = cur;
@@ -1148,7 +1178,7 @@ __device__ __forceinline__ void hnsw_search_body(const SearchArgs& a) {
           if (lane < m) cand_ids[lane] = cand_next[lane];
           if (c2 != kInvalid) {
             row_node = c2;
-            row_nid = __ldg(ix.l0_adj + (size_t)c2 * kL0 + lane);
+            row_nid = adj_row(c2, (uint32_t)blevel);
           } else {
             row_node = kInvalid;
           }
@@ -1158,10 +1188,10 @@ __device__ __forceinline__ void hnsw_search_body(const SearchArgs& a) {
             overflow = true;
             break;
           }
-          const uint32_t nid = (c == row_node) ? row_nid : __ldg(ix.l0_adj + (size_t)c * kL0 + lane);
+          const uint32_t nid = (c == row_node) ? row_nid : adj_row(c, (uint32_t)blevel);
           if (c2 != kInvalid) {
             row_node = c2;
-            row_nid = __ldg(ix.l0_adj + (size_t)c2 * kL0 + lane);
+            row_nid = adj_row(c2, (uint32_t)blevel);
           } else {
             row_node = kInvalid;
           }
@@ -1309,6 +1339,15 @@ __device__ __forceinline__ void hnsw_search_body(const SearchArgs& a) {
         __syncwarp();
         if (t.dbg) c_mrg += (uint32_t)(clock64() - h3);
       }
+      if (INSERT && !overflow) {
+        // the level's selection: the beam's nearest m0 (level 0) / m results in ascending order (operations.rs:157-162)
+        const uint32_t cnt = min(len, blevel == 0 ? a.ins_m0 : a.ins_m);
+        uint32_t* os = a.ins_sel + ((size_t)qi * kInsLevels + (uint32_t)blevel) * kInsSelMax;
+        for (uint32_t i = lane; i < cnt; i += 32) os[i] = A_id[i] & ~kExpandedBit;
+        if (lane == 0) a.ins_cnt[(size_t)qi * kInsLevels + (uint32_t)blevel] = (uint8_t)cnt;
+        __syncwarp();
+      }
+      }  // levels
       }  // !FILTERED
     }
     if (t.dbg && lane == 0) {
@@ -1337,6 +1376,7 @@ __device__ __forceinline__ void hnsw_search_body(const SearchArgs& a) {
       if (lane == 0) a.overflow_list[atomicAdd(a.overflow_count, 1u)] = qi;
       continue;
     }
+    if (INSERT) continue;  // the per-level selections are the output
 
     // ---- finalize_results(k) (search.rs:245-252) + SearchResult mapping (mod.rs:1159-1171) ----
     const bool f_fail = FILTERED && len == 0xFFFFFFFEu;
@@ -1382,6 +1422,17 @@ __global__ void __launch_bounds__(128, TURDB_MIN_CTAS) hnsw_search_kernel(const 
 template <int METRIC, bool GLOBAL_VISITED, bool FILTERED>
 __global__ void __launch_bounds__(32, TURDB_WARP_MIN_CTAS) hnsw_search_warp_kernel(const SearchArgs a) {
   hnsw_search_body<METRIC, GLOBAL_VISITED, FILTERED, false, true>(a);
+}
+
+// The insert path's searches (insert_with_callback, mod.rs:999-1084: greedy descent, then one ef_construction beam per
+// level of the new node), always squared L2 (mod.rs:1031,1046), staged and direct form.
+template <bool GLOBAL_VISITED>
+__global__ void __launch_bounds__(128, TURDB_MIN_CTAS) hnsw_insert_search_kernel(const SearchArgs a) {
+  hnsw_search_body<kL2, GLOBAL_VISITED, false, false, false, true>(a);
+}
+template <bool GLOBAL_VISITED>
+__global__ void __launch_bounds__(32, TURDB_WARP_MIN_CTAS) hnsw_insert_search_warp_kernel(const SearchArgs a) {
+  hnsw_search_body<kL2, GLOBAL_VISITED, false, false, true, true>(a);
 }
 
 }  // namespace turdb

@@ -17,6 +17,9 @@ SearchKernelFn get_direct_kernel_l2(bool global_visited, bool filtered);
 SearchKernelFn get_direct_kernel_cosine(bool global_visited, bool filtered);
 SearchKernelFn get_direct_kernel_ip(bool global_visited, bool filtered);
 
+// the insert path's searches (squared L2 only): compiled with the L2 units
+SearchKernelFn get_insert_kernel(bool global_visited, bool direct);
+
 inline SearchKernelFn get_search_kernel(int metric, bool global_visited, bool filtered, bool sq8, bool direct) {
   if (direct) {
     switch (metric) {

@@ -22,4 +22,12 @@ SearchKernelFn TURDB_TU_GETTER(bool gv, bool filt) {
   return filt ? hnsw_search_warp_kernel<M, false, true> : hnsw_search_warp_kernel<M, false, false>;
 }
 
+#if TURDB_TU_METRIC == 0
+SearchKernelFn get_insert_kernel_staged(bool gv);
+SearchKernelFn get_insert_kernel(bool gv, bool direct) {
+  if (!direct) return get_insert_kernel_staged(gv);
+  return gv ? hnsw_insert_search_warp_kernel<true> : hnsw_insert_search_warp_kernel<false>;
+}
+#endif
+
 }  // namespace turdb

@@ -25,4 +25,8 @@ SearchKernelFn TURDB_TU_GETTER(bool gv, bool filt, bool sq8) {
   return filt ? hnsw_search_kernel<M, false, true, false> : hnsw_search_kernel<M, false, false, false>;
 }
 
+#if TURDB_TU_METRIC == 0
+SearchKernelFn get_insert_kernel_staged(bool gv) { return gv ? hnsw_insert_search_kernel<true> : hnsw_insert_search_kernel<false>; }
+#endif
+
 }  // namespace turdb

@@ -74,6 +74,7 @@ struct turdb_cuda_index {
   uint32_t* d_bf16_max2 = nullptr;         // [2 copies][2]: max |v - bf16(v)|_2, max |bf16(v)|_2 over rows (float bits)
   cudaMemPool_t pool = nullptr;            // per-index stream-ordered scratch pool (never trimmed)
   uint64_t device_bytes = 0;
+  uint64_t n_up_slots = 0;
   uint32_t tune_warps = 0, tune_slots = 0, tune_hash_bits = 0, tune_segs = 0;
   uint32_t tune_mode = 0;                  // 0 automatic, 1 staged (team + TMA staging), 2 direct (one warp per query)
   // visited-set sizing: running maximum of keys per query, one counter per ceil(log2(ef)) (device + pinned mirror
@@ -322,6 +323,7 @@ int32_t turdb_cuda_index_create(const turdb_cuda_graph* g, int32_t device, turdb
     IDX_TRY(cudaMalloc(&idx->d_up_adj, std::max<uint64_t>(slots, 1) * kUp * 4));
     if (slots) IDX_TRY(cudaMemcpy(idx->d_up_adj, g->up_adj, slots * kUp * 4, cudaMemcpyHostToDevice));
     idx->device_bytes = arena_bytes + n * 4 + n * kL0 * 4 + n * 4 + n * 8 + n + slots * kUp * 4;
+    idx->n_up_slots = slots;
 
     // counts -> INVALID padding, id range check
     uint8_t* d_cnt = nullptr;
@@ -568,11 +570,18 @@ __global__ void fill_empty_results_kernel(uint64_t* rows, uint32_t* nodes, float
 
 [[maybe_unused]] static int32_t ensure_row_map(turdb_cuda_index* idx);  // defined after the tensor-map helpers (exact_abi.inl)
 
+// the insert path's searches (graph_insert.inl): nodes [first, first + nq) against the graph built so far
+struct InsertSpec {
+  uint32_t first, m, m0;
+  uint32_t* sel;
+  uint8_t* cnt;
+};
+
 static int32_t search_batch_device_impl(turdb_cuda_index* idx, const float* d_queries, uint32_t query_dim, uint32_t nq,
                                         uint32_t k, uint32_t ef, uint8_t metric, const uint64_t* d_visible,
                                         uint64_t* d_out_row_ids, uint32_t* d_out_node_ids, float* d_out_dist,
                                         uint32_t* d_out_counts, turdb_cuda_search_stats* d_out_stats, void* stream_,
-                                        bool sq8) {
+                                        bool sq8, const InsertSpec* ins = nullptr) {
   if (!idx) return fail(TURDB_ERR_INVALID_ARGUMENT, "idx is null");
   if (sq8 && idx->ix.n && !idx->d_arena_sq8) return fail(TURDB_ERR_INVALID_ARGUMENT, "call turdb_cuda_index_enable_sq8 first");
   if (query_dim != idx->ix.dim)
@@ -581,13 +590,13 @@ static int32_t search_batch_device_impl(turdb_cuda_index* idx, const float* d_qu
   if (ef == 0) return fail(TURDB_ERR_INVALID_ARGUMENT, "ef_search must be >= 1");
   if (ef > 2048) return fail(TURDB_ERR_UNSUPPORTED, "ef_search %u > 2048", ef);
   if (nq == 0) return TURDB_OK;
-  if (!d_queries || !d_out_counts || (k && (!d_out_row_ids || !d_out_dist)))
+  if (!ins && (!d_queries || !d_out_counts || (k && (!d_out_row_ids || !d_out_dist))))
     return fail(TURDB_ERR_INVALID_ARGUMENT, "null query/output pointer");
   cudaStream_t stream = (cudaStream_t)stream_;
   DeviceGuard guard(idx->device);
   if (!guard.ok) return fail(TURDB_ERR_CUDA, "cudaSetDevice(%d) failed", idx->device);
 
-  if (idx->ix.n == 0 || idx->ix.entry == kInvalid || k == 0) {  // Ok(vec![]), mod.rs:1106-1109
+  if (!ins && (idx->ix.n == 0 || idx->ix.entry == kInvalid || k == 0)) {  // Ok(vec![]), mod.rs:1106-1109
     uint64_t total = std::max<uint64_t>((uint64_t)nq * std::max(k, 1u), (uint64_t)nq * 4);
     fill_empty_results_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
         d_out_row_ids, d_out_node_ids, d_out_dist, d_out_counts, (uint32_t*)d_out_stats, nq, k);
@@ -604,7 +613,7 @@ static int32_t search_batch_device_impl(turdb_cuda_index* idx, const float* d_qu
     th = idx->tune_hash_bits;
     tg = idx->tune_segs;
     tm = idx->tune_mode;
-    vis_seen = idx->h_vis_max[ef_bucket];  // pinned mirror; refreshed asynchronously after every launch
+    vis_seen = ins ? 0u : idx->h_vis_max[ef_bucket];  // pinned mirror; refreshed asynchronously after every launch
   }
   const uint32_t ds = idx->ix.ds, dim = idx->ix.dim;
   // Visited table: 2 << hash_bits bytes of shared memory per resident query — the item that decides how many
@@ -706,7 +715,7 @@ static int32_t search_batch_device_impl(turdb_cuda_index* idx, const float* d_qu
   if (lay.team_bytes > budget)
     return fail(TURDB_ERR_UNSUPPORTED, "dim %u / ef %u need %u B of shared memory per query (> %u)", idx->ix.dim, ef, lay.team_bytes, budget);
 
-  SearchKernelFn kern = get_search_kernel(metric, false, filt, sq8, direct);
+  SearchKernelFn kern = ins ? get_insert_kernel(false, direct) : get_search_kernel(metric, false, filt, sq8, direct);
   int occ = 0;
   cudaError_t e = cudaSuccess;
   if (auto_warps) {
@@ -786,7 +795,15 @@ static int32_t search_batch_device_impl(turdb_cuda_index* idx, const float* d_qu
   if (sq8) a.ix.norm2 = idx->d_norm2_sq8;  // cosine's norm_b chain runs over the decoded row
   a.f_ovf = d_fovf;
   a.f_ocap = f_ocap_main;
-  a.vis_max = idx->d_vis_max + ef_bucket;
+  a.vis_max = ins ? nullptr : idx->d_vis_max + ef_bucket;
+  if (ins) {
+    a.ins_first = ins->first;
+    a.ins_m = ins->m;
+    a.ins_m0 = ins->m0;
+    a.ins_levels = idx->d_levels + ins->first;
+    a.ins_sel = ins->sel;
+    a.ins_cnt = ins->cnt;
+  }
 
   cudaEvent_t* pev = nullptr;
   {
@@ -803,7 +820,7 @@ static int32_t search_batch_device_impl(turdb_cuda_index* idx, const float* d_qu
 
   // exact fallback: always enqueued (no host sync); exits immediately when the list is empty
   {
-    SearchKernelFn gkern = get_search_kernel(metric, true, filt, sq8, direct);
+    SearchKernelFn gkern = ins ? get_insert_kernel(true, direct) : get_search_kernel(metric, true, filt, sq8, direct);
     int gocc = 0;
     e = kernel_prepare(gkern, glay.team_bytes, 32 * warps, &gocc);
     if (e == cudaSuccess && gocc < 1) e = cudaErrorInvalidConfiguration;
@@ -824,9 +841,19 @@ static int32_t search_batch_device_impl(turdb_cuda_index* idx, const float* d_qu
     }
   }
   // refresh the host mirror of the visited-set statistics (read by the NEXT call; never waited for)
-  cudaMemcpyAsync(idx->h_vis_max, idx->d_vis_max, 16 * 4, cudaMemcpyDeviceToHost, stream);
+  if (!ins) cudaMemcpyAsync(idx->h_vis_max, idx->d_vis_max, 16 * 4, cudaMemcpyDeviceToHost, stream);
   release();
   return TURDB_OK;
+}
+
+// one step of the insert path: searches of nodes [first, first + count) (squared L2, ef_construction)
+static int32_t insert_search_step(turdb_cuda_index* idx, uint32_t first, uint32_t count, uint32_t ef, uint32_t m, uint32_t m0,
+                                  uint32_t* d_sel, uint8_t* d_cnt, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(d_cnt, 0, (size_t)count * kInsLevels, stream);
+  if (e != cudaSuccess) return fail(TURDB_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+  InsertSpec spec{first, m, m0, d_sel, d_cnt};
+  return search_batch_device_impl(idx, nullptr, idx->ix.dim, count, 0, ef, kL2, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                  nullptr, stream, false, &spec);
 }
 
 extern "C" int32_t turdb_cuda_search_batch_device(turdb_cuda_index* idx, const float* d_queries, uint32_t query_dim,
@@ -993,3 +1020,4 @@ extern "C" int32_t turdb_cuda_index_gather_probe(turdb_cuda_index* idx, uint32_t
 }
 #include "sql_topk.inl"
 #include "hnsw_file.inl"
+#include "graph_insert.inl"

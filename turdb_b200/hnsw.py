@@ -120,6 +120,42 @@ class CudaHnswIndex:
         _check(L.turdb_cuda_index_create(C.byref(g), device, C.byref(h)))
         return cls(h, dim, n, metric, device)
 
+    @classmethod
+    def build(cls, vectors, row_ids=None, random_values=None, m: int = 16, ef_construction: int = 100, mode: int = 1,
+              max_batch: int = 4096, device: int = 0, metric: DistanceFunction = DistanceFunction.L2, seed: int = 1234):
+        """Build the graph ON THE DEVICE by the reference's insert path (insert_with_callback, src/hnsw/mod.rs:999-1084;
+        turdb_cuda_index_build).  mode 0 verbatim / 1 reference-intent; max_batch = 1 is the reference's sequential
+        procedure exactly.  random_values: the (0, 1] stream select_level draws from (default: seeded like the oracle's)."""
+        vec = np.ascontiguousarray(vectors, dtype=np.float32)
+        n, dim = vec.shape
+        rid = np.arange(n, dtype=np.uint64) if row_ids is None else np.ascontiguousarray(row_ids, dtype=np.uint64)
+        rnd = (1.0 - np.random.default_rng(seed).random(n)) if random_values is None else np.ascontiguousarray(random_values, np.float64)
+        bp = _lib.BuildParams(dim, m, ef_construction, mode, max_batch, 0)
+        h = C.c_void_p()
+        _check(_lib.load().turdb_cuda_index_build(C.byref(bp), n, _ptr(vec, C.c_float), _ptr(rid, C.c_uint64),
+                                                  _ptr(rnd, C.c_double), device, C.byref(h)))
+        return cls(h, dim, n, metric, device)
+
+    def export_graph(self, with_vectors: bool = True) -> dict:
+        """The graph the device holds, as the flat arrays from_graph takes (turdb_cuda_index_export_graph)."""
+        L = _lib.load()
+        slots, entry, ml = C.c_uint64(0), C.c_uint32(0), C.c_uint32(0)
+        _check(L.turdb_cuda_index_export_graph(self._h, None, None, None, None, None, None, None, None, C.byref(entry),
+                                               C.byref(ml), C.byref(slots)))
+        n, ns = self.n, int(slots.value)
+        g = dict(vectors=np.zeros((n, self.dim), np.float32) if with_vectors else None, row_ids=np.zeros(n, np.uint64),
+                 levels=np.zeros(n, np.uint8), l0_adj=np.zeros((n, 32), np.uint32), l0_cnt=np.zeros(n, np.uint8),
+                 up_base=np.zeros(n, np.uint32), up_adj=np.zeros((ns, 16), np.uint32), up_cnt=np.zeros(ns, np.uint8))
+        _check(L.turdb_cuda_index_export_graph(self._h, _ptr(g["vectors"], C.c_float), _ptr(g["row_ids"], C.c_uint64),
+                                               _ptr(g["levels"], C.c_uint8), _ptr(g["l0_adj"], C.c_uint32),
+                                               _ptr(g["l0_cnt"], C.c_uint8), _ptr(g["up_base"], C.c_uint32),
+                                               _ptr(g["up_adj"], C.c_uint32) if ns else None,
+                                               _ptr(g["up_cnt"], C.c_uint8) if ns else None, C.byref(entry), C.byref(ml),
+                                               C.byref(slots)))
+        g["entry"] = int(entry.value)
+        g["max_level"] = int(ml.value)
+        return g
+
     def close(self):
         if getattr(self, "_h", None):
             _lib.load().turdb_cuda_index_destroy(self._h)
