@@ -12,14 +12,33 @@ from turdb_b200.hnsw import CudaHnswIndex, DistanceFunction
 pytestmark = pytest.mark.gpu
 
 
-def graphs_equal(a, b):
+def lists_equal_up_to_ties(x, owner_rows, la, lb, what):
+    """Two adjacency tables must agree entry for entry, except that two neighbours at EXACTLY the same distance from the
+    owner may swap places: Candidate's order is distance-only (search.rs:94-115), so which of two equidistant results the
+    reference's heaps emit first follows std BinaryHeap internals.  Returns the number of such lists."""
+    swapped = 0
+    for r in np.where((la != lb).any(axis=1))[0]:
+        o = int(owner_rows[r])
+        pos = np.where(la[r] != lb[r])[0]
+        assert sorted(la[r].tolist()) == sorted(lb[r].tolist()), f"{what} of node {o}: {la[r]} vs {lb[r]}"
+        for p_ in pos:
+            da, db = ob.distance(ob.L2, x[o], x[int(la[r][p_])]), ob.distance(ob.L2, x[o], x[int(lb[r][p_])])
+            assert np.float32(da).view(np.uint32) == np.float32(db).view(np.uint32), \
+                f"{what} of node {o} differs at {p_} without a distance tie: {la[r]} vs {lb[r]}"
+        swapped += 1
+    return swapped
+
+
+def graphs_equal(a, b, x):
     assert a["entry"] == b["entry"] and a["max_level"] == b["max_level"]
     assert np.array_equal(a["levels"], b["levels"]) and np.array_equal(a["up_base"], b["up_base"])
     assert np.array_equal(a["l0_cnt"], b["l0_cnt"]), np.where(a["l0_cnt"] != b["l0_cnt"])[0][:10]
     assert np.array_equal(a["up_cnt"], b["up_cnt"])
-    for i in np.where((a["l0_adj"] != b["l0_adj"]).any(axis=1))[0][:5]:
-        raise AssertionError(f"level-0 list of node {i}: {a['l0_adj'][i][:a['l0_cnt'][i]]} vs {b['l0_adj'][i][:b['l0_cnt'][i]]}")
-    assert np.array_equal(a["up_adj"], b["up_adj"])
+    n = len(a["levels"])
+    tied = lists_equal_up_to_ties(x, np.arange(n), a["l0_adj"], b["l0_adj"], "level-0 list")
+    owner = np.repeat(np.arange(n), a["levels"])  # upper slot -> owning node
+    tied += lists_equal_up_to_ties(x, owner, a["up_adj"], b["up_adj"], "upper list")
+    assert tied <= max(1, n // 500), f"{tied} lists differ by tie order"
     assert np.array_equal(a["row_ids"], b["row_ids"])
 
 
@@ -32,11 +51,11 @@ def test_sequential_build_equals_the_oracle_graph(gpu_required, n, dim, mode):
     og = ob.OracleGraph.new(dim, 16, 100, mode)
     og.insert_batch(rid, x, rnd)
     idx = CudaHnswIndex.build(x, rid, rnd, m=16, ef_construction=100, mode=mode, max_batch=1)
-    graphs_equal(idx.export_graph(), og.export())
+    graphs_equal(idx.export_graph(), og.export(), x)
     # and the built index searches like any uploaded one
     q = ds.gaussian_latent(50, dim, seed=5)
     gpu = idx.search_batch(q, 10, 64, DistanceFunction.L2)
-    cpu = og.search(q, 10, 64, ob.L2)
+    cpu = ob.OracleGraph.from_arrays(idx.export_graph()).search(q, 10, 64, ob.L2)
     assert np.array_equal(gpu[1], cpu[1]) and np.array_equal(gpu[2].view(np.uint32), cpu[2].view(np.uint32))
     idx.close()
 
@@ -51,7 +70,7 @@ def test_level_above_max_level_links_one_way(gpu_required):
     og.insert_batch(np.arange(30, dtype=np.uint64), x, rnd)
     idx = CudaHnswIndex.build(x, None, rnd, max_batch=1)
     g, o = idx.export_graph(), og.export()
-    graphs_equal(g, o)
+    graphs_equal(g, o, x)
     assert g["entry"] == 20 and g["max_level"] == 3
     idx.close()
 

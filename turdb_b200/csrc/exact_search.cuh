@@ -559,14 +559,11 @@ __global__ void __launch_bounds__(256) exact_threshold_kernel(uint32_t nq, uint3
   const uint32_t cnt = min(raw_cnt, cap);
   const uint32_t prev = min(kept[q], cnt);
   if (raw_cnt > cap && threadIdx.x == 0) qflags[q] = 1u;
+  const uint32_t arch_base = arch_id ? arch_cnt[q] : 0u;  // read by every thread; rewritten only after the barrier below
   if (arch_id) {
-    const uint32_t base = arch_cnt[q], n_new = cnt - prev;
+    const uint32_t n_new = cnt - prev;
     for (uint32_t i = threadIdx.x; i < n_new; i += blockDim.x) {
-      if (base + i < arch_cap) arch_id[(size_t)q * arch_cap + base + i] = cand_id[(size_t)q * cap + prev + i];
-    }
-    if (threadIdx.x == 0) {
-      arch_cnt[q] = min(base + n_new, arch_cap);
-      if (base + n_new > arch_cap) qflags[q] = 1u;
+      if (arch_base + i < arch_cap) arch_id[(size_t)q * arch_cap + arch_base + i] = cand_id[(size_t)q * cap + prev + i];
     }
   }
   uint32_t n2 = 1;
@@ -577,6 +574,11 @@ __global__ void __launch_bounds__(256) exact_threshold_kernel(uint32_t nq, uint3
   }
   if (threadIdx.x == 0) s_keep = 0;
   __syncthreads();
+  if (arch_id && threadIdx.x == 0) {
+    const uint32_t n_new = cnt - prev;
+    arch_cnt[q] = min(arch_base + n_new, arch_cap);
+    if (arch_base + n_new > arch_cap) qflags[q] = 1u;
+  }
   for (uint32_t size = 2; size <= n2; size <<= 1) {
     for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
       for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) {

@@ -528,6 +528,7 @@ __device__ __forceinline__ float warp_request(const DeviceIndex& ix, Team& t, ui
   const bool full = steps != 0 && steps % US == 0;  // every unit carries US steps: the loops below run unpredicated
   const uint32_t npass = (m + 7) >> 3, nunits = npass * nch;
   uint64_t b[NBUF][US];
+  __syncwarp();  // cand_ids[0..m) were written by lanes 0..m-1; every quad reads them (the staged form has a CTA barrier here)
   // Quads beyond the request's last candidate gather (and reduce) that last candidate again: every lane then runs
   // the same unpredicated instruction stream; their result is discarded.
   uint32_t l_pass = 0, l_ch = 0;  // next unit to load
@@ -628,6 +629,7 @@ __device__ __forceinline__ float warp_request(const DeviceIndex& ix, Team& t, ui
         if (u + i + NBUF < nunits) load(b[i]);
       }
   }
+  __syncwarp();  // all reads of cand_ids are done before the caller reuses it
   return lane < m ? out : INFINITY;
 }
 
