@@ -9,7 +9,9 @@ M=16, ef_search=128, k=10, batch 10k queries.  A "step" = one batch through
 turdb_cuda_search_batch_device (value; inputs resident in HBM) or through turdb_cuda_search_batch with
 pinned host buffers (e2e; H2D + D2H inside the timed region).  N>1: one process per GPU, one 1M x 384
 sub-index per rank (weak scaling), queries replicated, per-shard top-k all-gathered over NCCL and merged
-on every rank; value = sub-index searches per second summed over ranks (= N x global QPS).
+on every rank; value = sub-index searches per second summed over ranks (= N x global QPS; unit says so at N>1).
+The graph is built on the device by the reference's insert path (turdb_cuda_index_build, --graph insert); --graph knn
+selects round 1's exact-kNN stand-in builder for comparison.
 
 Only the cpu_baseline leg and --impl reference execute oracle/ (as the CPU baseline being timed, and as
 the parity checker); the measured GPU path never touches it.
@@ -49,6 +51,10 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tuning", default="", help="warps,slots,hash_bits override")
+    ap.add_argument("--graph", default="insert", choices=["insert", "knn"],
+                    help="insert: the reference's insert path on the device (turdb_cuda_index_build); knn: exact-kNN stand-in")
+    ap.add_argument("--ef-construction", type=int, default=100)
+    ap.add_argument("--build-batch", type=int, default=4096, help="insert path: nodes per step (1 = sequential)")
     ap.add_argument("--out", default="")
     return ap.parse_args()
 
@@ -118,6 +124,32 @@ def make_data(args, rank: int):
     return x, q.reshape(nb, args.nq, args.dim)
 
 
+def workload_string(args) -> str:
+    """Identical in both arms (the driver compares them)."""
+    return f"{args.n}x{args.dim} cosine per GPU, M={args.m}, ef={args.ef}, k={args.k}, batch {args.nq}"
+
+
+def unit_string(world: int) -> str:
+    return "queries/s" if world == 1 else "sub-index searches/s (N x global queries/s)"
+
+
+def build_index(args, x, row_ids, device_index: int):
+    """-> (CudaHnswIndex, graph arrays for the oracle, provenance string)."""
+    from turdb_b200.hnsw import CudaHnswIndex, DistanceFunction
+    if args.graph == "insert":
+        idx = CudaHnswIndex.build(x, row_ids, None, m=args.m, ef_construction=args.ef_construction, mode=1,
+                                  max_batch=args.build_batch, device=device_index, metric=DistanceFunction.Cosine, seed=args.seed)
+        prov = (f"device insert path (insert_with_callback semantics, reference-intent back-links, efC={args.ef_construction}, "
+                f"steps of <= {args.build_batch} nodes)")
+        return idx, None, prov
+    import torch
+    from turdb_b200.graph_build import build_graph
+    arrays = build_graph(x, m=args.m, seed=args.seed, device=torch.device("cuda", device_index))
+    arrays["row_ids"] = row_ids
+    idx = CudaHnswIndex.from_graph(arrays, device=device_index, metric=DistanceFunction.Cosine)
+    return idx, arrays, arrays["provenance"]
+
+
 def algorithmic_bytes(stats: np.ndarray, dim: int, k: int) -> int:
     """n_dist*dim*4 + n_expanded*(32*4+1) + n_upper_hops*(16*4+1) + dim*4 + k*12 per query."""
     s = stats.astype(np.int64)
@@ -149,10 +181,18 @@ def run_reference(args, rank, world):
         return
     import torch
     from oracle import binding as ob
-    from turdb_b200.graph_build import build_graph
     x, qb = make_data(args, 0)
-    dev = "cuda:0" if torch.cuda.is_available() else "cpu"
-    arrays = build_graph(x, m=args.m, seed=args.seed, device=dev)
+    # the SAME graph as the GPU arm's rank 0 (same data, same seed, same builder); building it is not the timed path
+    if torch.cuda.is_available():
+        bidx, arrays, prov = build_index(args, x, np.arange(args.n, dtype=np.uint64), 0)
+        if arrays is None:
+            arrays = bidx.export_graph()
+        bidx.close()
+    else:
+        from turdb_b200.graph_build import build_graph
+        arrays = build_graph(x, m=args.m, seed=args.seed, device="cpu")
+        prov = arrays["provenance"]
+    arrays["vectors"] = x
     g = ob.OracleGraph.from_arrays(arrays)
     cores = os.cpu_count() or 1
     sample = args.cpu_sample or min(args.nq, max(256, 125 * cores))
@@ -167,15 +207,15 @@ def run_reference(args, rank, world):
     ms = float(np.mean(times) * 1e3)
     qps = sample / (ms / 1e3)
     line = {
-        "impl": "reference", "metric": METRIC_NAME, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC_NAME, "value": qps, "unit": unit_string(world), "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.n}x{args.dim} cosine, M={args.m}, ef={args.ef}, k={args.k}, batch {args.nq}",
+        "config": {"workload": workload_string(args),
                    "generator": f"gaussian_latent(latent={args.latent}, normalised)", "seed": args.seed,
-                   "graph": arrays["provenance"]},
+                   "graph": prov},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
                          "sample": f"{sample} of the {args.nq}-query batch per step, oracle C++ port (AVX2+FMA), {cores} threads"},
-        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": qps, "unit": unit_string(world), "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -193,8 +233,7 @@ def main():
     import torch
     import torch.distributed as dist
     from turdb_b200 import _lib
-    from turdb_b200.graph_build import build_graph
-    from turdb_b200.hnsw import CudaHnswIndex, DistanceFunction, merge_topk_device
+    from turdb_b200.hnsw import DistanceFunction, merge_topk_packed_device
     from turdb_b200.sharding import ShardedSearch
 
     _lib.load()  # fail loudly if the CUDA library is missing
@@ -209,21 +248,17 @@ def main():
     x, qb = make_data(args, rank)
     t_data = time.time() - t0
     t0 = time.time()
-    arrays = build_graph(x, m=args.m, seed=args.seed, device=dev)
+    # shard-local row ids are offset so the merged result names global rows
+    row_ids = np.arange(args.n, dtype=np.uint64) + np.uint64(rank) * np.uint64(args.n)
+    idx, arrays, provenance = build_index(args, x, row_ids, local_rank)
     torch.cuda.synchronize()
     t_build = time.time() - t0
-    # shard-local row ids are offset so the merged result names global rows
-    arrays["row_ids"] = (np.arange(args.n, dtype=np.uint64) + np.uint64(rank) * np.uint64(args.n))
-    idx = CudaHnswIndex.from_graph(arrays, device=local_rank, metric=DistanceFunction.Cosine)
     if args.tuning:
         idx.set_tuning(*[int(v) for v in args.tuning.split(",")])
 
     nb, nq, k, ef = qb.shape[0], args.nq, args.k, args.ef
     dq = torch.from_numpy(qb).to(dev)  # [nb][nq][dim] resident in HBM
-    rows = torch.empty((nq, k), dtype=torch.int64, device=dev)
-    dd = torch.empty((nq, k), dtype=torch.float32, device=dev)
     nodes = torch.empty((nq, k), dtype=torch.int32, device=dev)
-    cnt = torch.empty(nq, dtype=torch.int32, device=dev)
     stats = torch.empty((nq, 4), dtype=torch.int32, device=dev)
     m_rows = torch.empty((nq, k), dtype=torch.int64, device=dev)
     m_dd = torch.empty((nq, k), dtype=torch.float32, device=dev)
@@ -231,17 +266,19 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     launches_per_step = 2 + (1 if world > 1 else 0)  # traversal + overflow pass (+ merge)
 
-    def local_search(dq_batch):
-        idx.search_batch_device(dq_batch.data_ptr(), nq, k, ef, DistanceFunction.Cosine, rows.data_ptr(),
-                                dd.data_ptr(), cnt.data_ptr(), nodes.data_ptr(), stats.data_ptr(), 0, stream)
-        return rows, dd, cnt
+    def local_search(dq_batch, o_rows=None, o_dd=None, o_cnt=None):
+        o_rows, o_dd, o_cnt = (rows, dd, cnt) if o_rows is None else (o_rows, o_dd, o_cnt)
+        idx.search_batch_device(dq_batch.data_ptr(), nq, k, ef, DistanceFunction.Cosine, o_rows.data_ptr(),
+                                o_dd.data_ptr(), o_cnt.data_ptr(), nodes.data_ptr(), stats.data_ptr(), 0,
+                                torch.cuda.current_stream().cuda_stream)
 
-    def merge(g_rows, g_dd, g_cnt):
-        merge_topk_device(local_rank, g_rows.data_ptr(), g_dd.data_ptr(), g_cnt.data_ptr(), world, nq, k,
-                          m_rows.data_ptr(), m_dd.data_ptr(), m_cnt.data_ptr(), stream)
+    def merge(gathered, block_bytes):  # ONE all-gather delivered [world][rows | distances | counts]
+        merge_topk_packed_device(local_rank, gathered.data_ptr(), block_bytes, world, nq, k, m_rows.data_ptr(),
+                                 m_dd.data_ptr(), m_cnt.data_ptr(), torch.cuda.current_stream().cuda_stream)
         return m_rows, m_dd, m_cnt
 
-    sharded = ShardedSearch(dist, world, local_search, merge)
+    sharded = ShardedSearch(dist, world, local_search, merge, nq, k, dev)
+    rows, dd, cnt = sharded.rows, sharded.dd, sharded.cnt  # the rank's own top-k lives inside its packed block
 
     def step(i):
         sharded.search_batch(dq[i % nb])
@@ -322,15 +359,41 @@ def main():
     L = _lib.load()
     import ctypes as C
 
-    # N>1: the step is H2D of the query batch -> per-shard search -> NCCL all-gather -> merge -> D2H of the merged top-k
-    dq_e2e = torch.empty((nq, args.dim), dtype=torch.float32, device=dev)
+    # N>1: the step is H2D of the query batch -> per-shard search -> ONE NCCL all-gather -> merge -> D2H of the merged
+    # top-k.  One caller per rank (the collective must be issued in one order on all ranks), but the copies run on a
+    # copy stream, double-buffered: batch i+1 goes up and result i-1 comes down while batch i is searched.
+    copy_stream = torch.cuda.Stream(device=dev)
+    dq_e2e = [torch.empty((nq, args.dim), dtype=torch.float32, device=dev) for _ in range(2)]
+    res_dev = [(torch.empty_like(m_rows), torch.empty_like(m_dd), torch.empty_like(m_cnt)) for _ in range(2)]
+    res_host = [(torch.empty((nq, k), dtype=torch.int64).pin_memory(), torch.empty((nq, k), dtype=torch.float32).pin_memory(),
+                 torch.empty(nq, dtype=torch.int32).pin_memory()) for _ in range(2)]
 
-    def e2e_step_sharded(i):
-        dq_e2e.copy_(hq[i % nb], non_blocking=True)
-        sharded.search_batch(dq_e2e)
-        h_rows.copy_(m_rows, non_blocking=True)
-        h_dd.copy_(m_dd, non_blocking=True)
-        h_cnt.copy_(m_cnt, non_blocking=True)
+    def e2e_pipeline(first, count):
+        main = torch.cuda.current_stream()
+        up = [torch.cuda.Event() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+        down = [torch.cuda.Event() for _ in range(2)]
+        with torch.cuda.stream(copy_stream):
+            dq_e2e[0].copy_(hq[first % nb], non_blocking=True)
+            up[0].record(copy_stream)
+        for j in range(count):
+            b = j & 1
+            if j + 1 < count:  # next batch goes up while this one is searched
+                with torch.cuda.stream(copy_stream):
+                    dq_e2e[b ^ 1].copy_(hq[(first + j + 1) % nb], non_blocking=True)
+                    up[b ^ 1].record(copy_stream)
+            main.wait_event(up[b])
+            if j >= 2:
+                main.wait_event(down[b])  # result buffer b has been read back
+            sharded.search_batch(dq_e2e[b])
+            for dst, src in zip(res_dev[b], (m_rows, m_dd, m_cnt)):
+                dst.copy_(src, non_blocking=True)
+            done[b].record(main)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done[b])
+                for dst, src in zip(res_host[b], res_dev[b]):
+                    dst.copy_(src, non_blocking=True)
+                down[b].record(copy_stream)
         torch.cuda.synchronize()
 
     # N=1: two host threads issue alternate batches through the same call.  The ABI is re-entrant (every call owns a
@@ -352,8 +415,7 @@ def main():
 
     def e2e_run(first, count):
         if e2e_callers == 1:
-            for i in range(first, first + count):
-                e2e_step_sharded(i)
+            e2e_pipeline(first, count)
             return
         def worker(b):
             for i in range(first + b, first + count, e2e_callers):
@@ -411,6 +473,9 @@ def main():
     parity = None
     if rank == 0 and not args.no_cpu_baseline:
         from oracle import binding as ob
+        if arrays is None:
+            arrays = idx.export_graph()
+        arrays["vectors"] = x
         g = ob.OracleGraph.from_arrays(arrays)
         cores = os.cpu_count() or 1
         sample = args.cpu_sample or min(nq, max(256, 125 * cores))
@@ -437,18 +502,19 @@ def main():
 
     if rank == 0:
         line = {
-            "metric": METRIC_NAME, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC_NAME, "value": value, "unit": unit_string(world), "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": f"{args.n}x{args.dim} cosine per GPU, M={args.m}, ef={ef}, k={k}, batch {nq}",
+                "workload": workload_string(args),
                 "generator": f"gaussian_latent(latent={args.latent}, normalised)", "seed": args.seed,
-                "graph": arrays["provenance"], "graph_build_s": round(t_build, 1), "data_gen_s": round(t_data, 1),
+                "graph": provenance, "graph_build_s": round(t_build, 1), "data_gen_s": round(t_data, 1),
                 "l2_policy": "inputs larger than L2 (1.5 GB arena, 4 rotating query batches)",
-                "sharding": "one sub-index per GPU, queries replicated, NCCL all-gather + merge" if world > 1 else "single index",
+                "sharding": "one sub-index per GPU, queries replicated, ONE NCCL all-gather of the packed top-k + merge" if world > 1 else "single index",
                 "global_qps": value / world,
             },
             "recall_at_10": recall,
+            "recall_ok": bool(recall >= 0.95),  # the metric is QPS AT recall@10 >= 0.95: a record below it is not a result
             "exact_path": exact_info,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
@@ -457,8 +523,10 @@ def main():
                          "algorithmic_bytes_per_launch": float(np.mean(step_bytes))},
             "cpu_baseline": cpu_baseline,
             "parity": parity,
-            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "host_callers": e2e_callers},
+            "e2e": {"value": e2e_value, "unit": unit_string(world), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "host_callers": e2e_callers,
+                    "how": "two host threads through turdb_cuda_search_batch (pinned host buffers)" if world == 1 else
+                           "one caller per rank; copies double-buffered on a copy stream around search + all-gather + merge"},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }

@@ -279,6 +279,13 @@ int32_t turdb_cuda_shards_search_batch(turdb_cuda_index* const* shards, uint32_t
                                        uint32_t ef, uint8_t metric, uint64_t* out_row_ids,
                                        float* out_dist, uint32_t* out_counts);
 
+/* The same merge over ONE packed block per shard — row ids [nq][k] u64 | distances [nq][k] f32 | counts [nq] u32 —,
+ * blocks shard_stride_bytes apart (a multiple of 8): the output of a single all-gather of every rank's block. */
+int32_t turdb_cuda_merge_topk_packed_device(int32_t device, const void* d_gathered,
+                                            uint64_t shard_stride_bytes, uint32_t n_shards, uint32_t nq,
+                                            uint32_t k, uint64_t* d_out_row_ids, float* d_out_dist,
+                                            uint32_t* d_out_counts, void* stream);
+
 int32_t turdb_cuda_merge_topk_device(int32_t device, const uint64_t* d_gathered_row_ids,
                                      const float* d_gathered_dist, const uint32_t* d_gathered_counts,
                                      uint32_t n_shards, uint32_t nq, uint32_t k,

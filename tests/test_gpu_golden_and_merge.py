@@ -49,6 +49,23 @@ def test_merge_kernel_matches_host_spec(gpu_required):
         assert np.array_equal(o_cnt.cpu().numpy().view(np.uint32), c)
         assert np.array_equal(o_dist.cpu().numpy(), d)
         assert np.array_equal(o_rows.cpu().numpy().view(np.uint64), r)
+        # the packed form: one block per shard (rows | distances | counts), as a single all-gather delivers them
+        from turdb_b200.hnsw import merge_topk_packed_device
+        from turdb_b200.sharding import pack_layout
+        o_r, o_d, o_c, size = pack_layout(nq, k)
+        blocks = np.zeros((n_shards, size), np.uint8)
+        for s_ in range(n_shards):
+            blocks[s_, o_r:o_d] = rows[s_].view(np.uint8).ravel()
+            blocks[s_, o_d:o_c] = dist[s_].view(np.uint8).ravel()
+            blocks[s_, o_c:o_c + nq * 4] = cnt[s_].view(np.uint8).ravel()
+        d_blocks = torch.from_numpy(blocks).to(dev)
+        o_rows.zero_(); o_dist.zero_(); o_cnt.zero_()
+        merge_topk_packed_device(0, d_blocks.data_ptr(), size, n_shards, nq, k, o_rows.data_ptr(), o_dist.data_ptr(),
+                                 o_cnt.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(o_cnt.cpu().numpy().view(np.uint32), c)
+        assert np.array_equal(o_dist.cpu().numpy(), d)
+        assert np.array_equal(o_rows.cpu().numpy().view(np.uint64), r)
 
 
 def test_single_process_sharded_search_matches_per_shard_oracle_merge(gpu_required):

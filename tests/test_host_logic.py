@@ -100,16 +100,19 @@ def _sharded_worker(rank, world, port, out_dir):
     lo, hi = shard_bounds(n_total, world, rank)
     g = ob.OracleGraph.build(x[lo:hi], seed=30 + rank, row_ids=np.arange(lo, hi, dtype=np.uint64))
 
-    def local_search(queries):
+    def local_search(queries, o_rows, o_dd, o_cnt):  # the rank's top-k goes straight into its packed block
         rows, _, dd, cnt, _ = g.search(queries, k, ef)
-        return (torch.from_numpy(rows.astype(np.int64)), torch.from_numpy(dd.copy()),
-                torch.from_numpy(cnt.astype(np.int32)))
+        o_rows.copy_(torch.from_numpy(rows.astype(np.int64)))
+        o_dd.copy_(torch.from_numpy(dd.copy()))
+        o_cnt.copy_(torch.from_numpy(cnt.astype(np.int32)))
 
-    def merge(g_rows, g_dd, g_cnt):
+    def merge(gathered, block_bytes):  # ONE all-gather delivered [world, block]; the host specification merges it
+        assert gathered.numel() == world * block_bytes
+        g_rows, g_dd, g_cnt = s.unpack(gathered)
         r, d, c = merge_topk_host(g_rows.numpy().astype(np.uint64), g_dd.numpy(), g_cnt.numpy().astype(np.uint32), k)
         return torch.from_numpy(r.astype(np.int64)), torch.from_numpy(d), torch.from_numpy(c.astype(np.int32))
 
-    s = ShardedSearch(dist, world, local_search, merge)
+    s = ShardedSearch(dist, world, local_search, merge, nq, k, "cpu")
     rows, dd, cnt = s.search_batch(q)
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), rows=rows.numpy(), dist=dd.numpy(), cnt=cnt.numpy())
     dist.destroy_process_group()

@@ -49,7 +49,7 @@ EXPORTS = [
     "turdb_cuda_index_destroy", "turdb_cuda_index_info", "turdb_cuda_search_batch", "turdb_cuda_search_batch_device",
     "turdb_cuda_index_set_tuning", "turdb_cuda_index_set_traversal_form", "turdb_cuda_index_profile_begin", "turdb_cuda_index_profile_read",
     "turdb_cuda_index_debug_counters", "turdb_cuda_bruteforce_topk", "turdb_cuda_bruteforce_topk_device",
-    "turdb_cuda_merge_topk_device", "turdb_cuda_index_gather_probe",
+    "turdb_cuda_merge_topk_device", "turdb_cuda_merge_topk_packed_device", "turdb_cuda_index_gather_probe",
     "turdb_cuda_hnsw_file_open", "turdb_cuda_hnsw_file_open_memory", "turdb_cuda_hnsw_file_close",
     "turdb_cuda_hnsw_file_get_info", "turdb_cuda_hnsw_file_nodes", "turdb_cuda_hnsw_file_graph",
     "turdb_cuda_hnsw_file_upload", "turdb_cuda_sql_topk_batch", "turdb_cuda_sql_topk_batch_device",
@@ -90,6 +90,7 @@ def load():
     L.turdb_cuda_bruteforce_topk.argtypes = [vp, pf, u32, u32, u32, u8, u32, pu64, pu32, pf, pu32]
     L.turdb_cuda_bruteforce_topk_device.argtypes = [vp, vp, u32, u32, u32, u8, u32, vp, vp, vp, vp, vp]
     L.turdb_cuda_merge_topk_device.argtypes = [i32, vp, vp, vp, u32, u32, u32, vp, vp, vp, vp]
+    L.turdb_cuda_merge_topk_packed_device.argtypes = [i32, vp, u64, u32, u32, u32, vp, vp, vp, vp]
     L.turdb_cuda_sql_topk_batch.argtypes = [vp, pf, u32, u32, u32, u32, u8, u8, i32, u32, pu64, C.POINTER(C.c_double),
                                             C.POINTER(C.c_double), pu32]
     L.turdb_cuda_sql_topk_batch_device.argtypes = [vp, vp, u32, u32, u32, u32, u8, u8, i32, u32, vp, vp, vp, vp, vp]

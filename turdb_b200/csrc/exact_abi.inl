@@ -13,8 +13,32 @@ extern "C" int32_t turdb_cuda_merge_topk_device(int32_t device, const uint64_t* 
   cudaStream_t stream = (cudaStream_t)stream_;
   const uint32_t threads = 128;
   const uint32_t blocks = (uint32_t)(((uint64_t)nq * 32 + threads - 1) / threads);
-  merge_topk_kernel<<<blocks, threads, 0, stream>>>(d_gathered_row_ids, d_gathered_dist, d_gathered_counts, n_shards,
-                                                    nq, k, d_out_row_ids, d_out_dist, d_out_counts);
+  merge_topk_kernel<<<blocks, threads, 0, stream>>>((const uint8_t*)d_gathered_row_ids, (const uint8_t*)d_gathered_dist,
+                                                    (const uint8_t*)d_gathered_counts, (size_t)nq * k * 8, (size_t)nq * k * 4,
+                                                    (size_t)nq * 4, n_shards, nq, k, d_out_row_ids, d_out_dist, d_out_counts);
+  CUDA_TRY(cudaGetLastError());
+  return TURDB_OK;
+}
+
+// The same merge over ONE packed block per shard — row ids [nq][k] u64 | distances [nq][k] f32 | counts [nq] u32, blocks
+// shard_stride_bytes apart (a multiple of 8) — i.e. over the output of a single all-gather of each rank's block.
+extern "C" int32_t turdb_cuda_merge_topk_packed_device(int32_t device, const void* d_gathered, uint64_t shard_stride_bytes,
+                                                       uint32_t n_shards, uint32_t nq, uint32_t k, uint64_t* d_out_row_ids,
+                                                       float* d_out_dist, uint32_t* d_out_counts, void* stream_) {
+  if (n_shards == 0 || n_shards > 32) return fail(TURDB_ERR_INVALID_ARGUMENT, "n_shards must be 1..32");
+  if (nq == 0) return TURDB_OK;
+  const uint64_t need = (uint64_t)nq * k * 12 + (uint64_t)nq * 4;
+  if (!d_gathered || !d_out_counts || (k && (!d_out_row_ids || !d_out_dist))) return fail(TURDB_ERR_INVALID_ARGUMENT, "null pointer");
+  if (shard_stride_bytes < need || (shard_stride_bytes & 7)) return fail(TURDB_ERR_INVALID_ARGUMENT, "shard stride %llu: need a multiple of 8, >= %llu", (unsigned long long)shard_stride_bytes, (unsigned long long)need);
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(TURDB_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const uint32_t threads = 128;
+  const uint32_t blocks = (uint32_t)(((uint64_t)nq * 32 + threads - 1) / threads);
+  const uint8_t* b = (const uint8_t*)d_gathered;
+  merge_topk_kernel<<<blocks, threads, 0, stream>>>(b, b + (size_t)nq * k * 8, b + (size_t)nq * k * 12, shard_stride_bytes,
+                                                    shard_stride_bytes, shard_stride_bytes, n_shards, nq, k, d_out_row_ids,
+                                                    d_out_dist, d_out_counts);
   CUDA_TRY(cudaGetLastError());
   return TURDB_OK;
 }

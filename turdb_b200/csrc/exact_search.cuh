@@ -23,18 +23,24 @@ namespace turdb {
 // ------------------------------------------------------------------------------------------------
 // One warp per query: k-way merge of n_shards ascending lists; at every step the head with the smallest
 // (distance, row_id, shard) wins.  gathered_* are [n_shards][nq][k]; lane s walks shard s (n_shards <= 32).
-__global__ void merge_topk_kernel(const uint64_t* __restrict__ g_rows, const float* __restrict__ g_dist,
-                                  const uint32_t* __restrict__ g_counts, uint32_t n_shards, uint32_t nq,
+// Shard s's arrays start s * stride bytes after the base pointers (dense [n_shards][nq][k] arrays: stride = the array's
+// size; one packed block per shard, as a single all-gather delivers it: stride = the block's size for all three).
+__global__ void merge_topk_kernel(const uint8_t* __restrict__ g_rows_b, const uint8_t* __restrict__ g_dist_b,
+                                  const uint8_t* __restrict__ g_counts_b, size_t rows_stride, size_t dist_stride,
+                                  size_t cnt_stride, uint32_t n_shards, uint32_t nq,
                                   uint32_t k, uint64_t* __restrict__ out_rows, float* __restrict__ out_dist,
                                   uint32_t* __restrict__ out_counts) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (q >= nq) return;
   uint32_t head = 0, cnt = 0;
-  size_t base = 0;
+  const size_t base = (size_t)q * k;
+  const uint64_t* g_rows = nullptr;
+  const float* g_dist = nullptr;
   if (lane < n_shards) {
-    cnt = min(g_counts[(size_t)lane * nq + q], k);
-    base = ((size_t)lane * nq + q) * k;
+    g_rows = reinterpret_cast<const uint64_t*>(g_rows_b + lane * rows_stride);
+    g_dist = reinterpret_cast<const float*>(g_dist_b + lane * dist_stride);
+    cnt = min(reinterpret_cast<const uint32_t*>(g_counts_b + lane * cnt_stride)[q], k);
   }
   uint32_t produced = 0;
   for (; produced < k; ++produced) {

@@ -63,6 +63,9 @@
 #ifndef TURDB_DIRECT_MAX_ROW_BYTES
 #define TURDB_DIRECT_MAX_ROW_BYTES 1024
 #endif
+#ifndef TURDB_DIRECT_MAX_ROWS_PER_HOP
+#define TURDB_DIRECT_MAX_ROWS_PER_HOP 10.0
+#endif
 
 namespace turdb {
 
@@ -98,6 +101,13 @@ struct TeamLayout {
   uint32_t key_bits;   // ceil(log2(n)), >= hash_bits
 };
 
+// Feedback from past launches, one record per ceil(log2(ef)) class: the largest visited set any query produced (sizes
+// the shared-memory table) and the level-0 totals whose ratio is the new rows gathered per expansion (picks the form).
+struct TraversalStats {
+  uint32_t vis_max, pad;
+  unsigned long long sum_dist, sum_exp;
+};
+
 struct SearchArgs {
   DeviceIndex ix;
   TeamLayout lay;
@@ -122,7 +132,7 @@ struct SearchArgs {
   const uint64_t* visible;   // null => unfiltered search
   uint2* f_ovf;              // [CTAs][f_ocap] (distance bits, id) overflow of the candidate window
   uint32_t f_ocap;
-  uint32_t* vis_max;         // optional: running maximum of visited-set keys per query (sizes the next launch's table)
+  TraversalStats* tstats;    // optional: what this ef class's queries looked like (sizes and shapes the next launch)
   // INSERT kernels (graph_insert.inl): query q is node ins_first + q; per level l <= ins_levels[q] the beam's nearest
   // ins_m0 (l == 0) / ins_m ids go to ins_sel[q][l][0..ins_cnt[q][l])
   uint32_t ins_first, ins_m, ins_m0;
@@ -503,6 +513,13 @@ struct LoadSteps<US, US> {
 };
 
 // steps (of 8 floats) per unit and units in flight per warp: registers for the landing zone = 2 * US * NBUF
+// 1: rows of the speculated next hop are prefetched into L2 during the current hop (rows up to ..._MAX_ROW bytes)
+#ifndef TURDB_SPEC_PREFETCH
+#define TURDB_SPEC_PREFETCH 1
+#endif
+#ifndef TURDB_SPEC_PREFETCH_MAX_ROW
+#define TURDB_SPEC_PREFETCH_MAX_ROW 1024
+#endif
 #ifndef TURDB_DIRECT_DBG
 #define TURDB_DIRECT_DBG 0
 #endif
@@ -1228,6 +1245,17 @@ __device__ __forceinline__ void hnsw_search_body(const SearchArgs& a) {
           const uint32_t nm = __ballot_sync(kFullMask, sp_inserted);
           sp_m = __popc(nm);
           if (sp_inserted) cand_next[__popc(nm & ((1u << lane) - 1))] = row_nid;
+#if TURDB_SPEC_PREFETCH
+          // short rows: the kernel is latency-bound, so the rows hop h+1 will most likely gather (the speculation holds
+          // ~85 % of the time) are pulled into L2 now, one 128 B line per instruction and lane — hop h+1's loads then pay
+          // an L2 hit.  A wrong guess costs the DRAM bytes of those rows (counted in roofline.traffic, not in the
+          // algorithmic bytes).
+          if (sp_inserted && t.vec_bytes <= TURDB_SPEC_PREFETCH_MAX_ROW) {
+            const uintptr_t r0 = reinterpret_cast<uintptr_t>(t.rows + (size_t)row_nid * t.vec_bytes);
+            for (uintptr_t pa = r0 & ~(uintptr_t)127; pa < r0 + t.vec_bytes; pa += 128)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+          }
+#endif
           sp_node = row_node;
           sp_valid = true;
         });
@@ -1398,7 +1426,11 @@ __device__ __forceinline__ void hnsw_search_body(const SearchArgs& a) {
       }
     }
     if (lane == 0) {
-      if (a.vis_max) atomicMax(a.vis_max, n_dist - n_dist_upper + 1);
+      if (a.tstats) {
+        atomicMax(&a.tstats->vis_max, n_dist - n_dist_upper + 1);
+        atomicAdd(&a.tstats->sum_dist, (unsigned long long)(n_dist - n_dist_upper));
+        atomicAdd(&a.tstats->sum_exp, (unsigned long long)n_expanded);
+      }
       a.out_counts[qi] = f_fail ? 0xFFFFFFFEu : count;
       if (a.out_stats) {
         uint32_t* s = a.out_stats + (size_t)qi * 4;

@@ -79,8 +79,8 @@ struct turdb_cuda_index {
   uint32_t tune_mode = 0;                  // 0 automatic, 1 staged (team + TMA staging), 2 direct (one warp per query)
   // visited-set sizing: running maximum of keys per query, one counter per ceil(log2(ef)) (device + pinned mirror
   // refreshed by an async copy after every launch; the next launch sizes its shared-memory table from it)
-  uint32_t* d_vis_max = nullptr;
-  uint32_t* h_vis_max = nullptr;
+  TraversalStats* d_tstats = nullptr;
+  TraversalStats* h_tstats = nullptr;
   // profiling ring: 3 events per call (before main, after main, after overflow pass)
   std::vector<cudaEvent_t> prof_events;
   uint32_t prof_capacity = 0, prof_used = 0;
@@ -214,8 +214,8 @@ int32_t turdb_cuda_index_destroy(turdb_cuda_index* idx) {
     cudaFree(idx->d_bf16_max2);
     for (cudaEvent_t ev : idx->prof_events) cudaEventDestroy(ev);
     cudaFree(idx->d_dbg);
-    cudaFree(idx->d_vis_max);
-    if (idx->h_vis_max) cudaFreeHost(idx->h_vis_max);
+    cudaFree(idx->d_tstats);
+    if (idx->h_tstats) cudaFreeHost(idx->h_tstats);
     if (idx->pool) cudaMemPoolDestroy(idx->pool);
   }
   delete idx;
@@ -275,12 +275,13 @@ int32_t turdb_cuda_index_create(const turdb_cuda_graph* g, int32_t device, turdb
     uint64_t keep = ~0ull;  // keep freed scratch cached across synchronisations
     cudaMemPoolSetAttribute(idx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
   }
-  if (cudaMalloc(&idx->d_vis_max, 16 * 4) != cudaSuccess || cudaMemset(idx->d_vis_max, 0, 16 * 4) != cudaSuccess ||
-      cudaMallocHost(&idx->h_vis_max, 16 * 4) != cudaSuccess) {
+  if (cudaMalloc(&idx->d_tstats, 16 * sizeof(TraversalStats)) != cudaSuccess ||
+      cudaMemset(idx->d_tstats, 0, 16 * sizeof(TraversalStats)) != cudaSuccess ||
+      cudaMallocHost(&idx->h_tstats, 16 * sizeof(TraversalStats)) != cudaSuccess) {
     turdb_cuda_index_destroy(idx);
-    return fail(TURDB_ERR_OUT_OF_MEMORY, "visited-set statistics allocation failed");
+    return fail(TURDB_ERR_OUT_OF_MEMORY, "traversal statistics allocation failed");
   }
-  memset(idx->h_vis_max, 0, 16 * 4);
+  memset(idx->h_tstats, 0, 16 * sizeof(TraversalStats));
   const uint64_t n = g->n;
   const uint32_t dim = g->dim, ds = (dim + 3) & ~3u;
   idx->ix.n = n;
@@ -605,6 +606,7 @@ static int32_t search_batch_device_impl(turdb_cuda_index* idx, const float* d_qu
   }
 
   uint32_t tw, ts, th, tg, tm, vis_seen;
+  double rows_per_hop = 0.0;  // level-0 distance evaluations per expansion seen so far in this ef class (0: nothing seen)
   const uint32_t ef_bucket = std::min(15u, ceil_log2(ef));
   {
     std::lock_guard<std::mutex> lk(idx->mu);
@@ -613,7 +615,9 @@ static int32_t search_batch_device_impl(turdb_cuda_index* idx, const float* d_qu
     th = idx->tune_hash_bits;
     tg = idx->tune_segs;
     tm = idx->tune_mode;
-    vis_seen = ins ? 0u : idx->h_vis_max[ef_bucket];  // pinned mirror; refreshed asynchronously after every launch
+    const TraversalStats hs = idx->h_tstats[ef_bucket];  // pinned mirror; refreshed asynchronously after every launch
+    vis_seen = ins ? 0u : hs.vis_max;
+    if (!ins && hs.sum_exp) rows_per_hop = (double)hs.sum_dist / (double)hs.sum_exp;
   }
   const uint32_t ds = idx->ix.ds, dim = idx->ix.dim;
   // Visited table: 2 << hash_bits bytes of shared memory per resident query — the item that decides how many
@@ -644,7 +648,11 @@ static int32_t search_batch_device_impl(turdb_cuda_index* idx, const float* d_qu
   const uint64_t nn = idx->ix.n;
   const bool filt = d_visible != nullptr;
   // form: short FP32 rows -> one warp per query, registers as the landing zone; long rows -> team + TMA staging
-  const bool direct = !sq8 && (tm == 2 || (tm == 0 && ds * 4 <= TURDB_DIRECT_MAX_ROW_BYTES));
+  // (measured, r02: 2M x 128 clustered, 4 new rows per hop: direct 2.64 ms, staged 3.00; 1M x 128 SIFT-like, 24 new rows
+  // per hop: direct 7.9 ms, staged 4.9) — so the direct form needs short rows AND few of them per hop; until a launch
+  // has reported what the corpus looks like the staged form runs.
+  const bool direct = !sq8 && (tm == 2 || (tm == 0 && ds * 4 <= TURDB_DIRECT_MAX_ROW_BYTES && rows_per_hop > 0.0 &&
+                                           rows_per_hop <= TURDB_DIRECT_MAX_ROWS_PER_HOP));
   uint32_t warps = direct ? 1u : (tw ? std::min(tw, 4u) : 0u);  // staged team size (0: chosen below)
   uint32_t g4w = 0;
 #if TURDB_GATHER4
@@ -795,7 +803,7 @@ static int32_t search_batch_device_impl(turdb_cuda_index* idx, const float* d_qu
   if (sq8) a.ix.norm2 = idx->d_norm2_sq8;  // cosine's norm_b chain runs over the decoded row
   a.f_ovf = d_fovf;
   a.f_ocap = f_ocap_main;
-  a.vis_max = ins ? nullptr : idx->d_vis_max + ef_bucket;
+  a.tstats = ins ? nullptr : idx->d_tstats + ef_bucket;
   if (ins) {
     a.ins_first = ins->first;
     a.ins_m = ins->m;
@@ -841,7 +849,7 @@ static int32_t search_batch_device_impl(turdb_cuda_index* idx, const float* d_qu
     }
   }
   // refresh the host mirror of the visited-set statistics (read by the NEXT call; never waited for)
-  if (!ins) cudaMemcpyAsync(idx->h_vis_max, idx->d_vis_max, 16 * 4, cudaMemcpyDeviceToHost, stream);
+  if (!ins) cudaMemcpyAsync(idx->h_tstats, idx->d_tstats, 16 * sizeof(TraversalStats), cudaMemcpyDeviceToHost, stream);
   release();
   return TURDB_OK;
 }

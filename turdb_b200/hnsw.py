@@ -338,6 +338,13 @@ def visibility_bitmap(visible_mask) -> np.ndarray:
     return np.packbits(padded.reshape(words, 64), axis=1, bitorder="little").view(np.uint64).reshape(words)
 
 
+def merge_topk_packed_device(device: int, d_gathered, shard_stride_bytes: int, n_shards: int, nq: int, k: int, d_out_rows,
+                             d_out_dist, d_out_counts, stream=0):
+    """Merge over one packed block per shard (rows | distances | counts): the output of a single all-gather."""
+    _check(_lib.load().turdb_cuda_merge_topk_packed_device(device, d_gathered, shard_stride_bytes, n_shards, nq, k, d_out_rows,
+                                                           d_out_dist, d_out_counts, stream or None))
+
+
 def merge_topk_device(device: int, d_rows, d_dist, d_counts, n_shards: int, nq: int, k: int, d_out_rows, d_out_dist,
                       d_out_counts, stream=0):
     """Per-shard top-k lists [n_shards][nq][k] (the all-gather output) -> global top-k."""
