@@ -513,9 +513,11 @@ struct LoadSteps<US, US> {
 };
 
 // steps (of 8 floats) per unit and units in flight per warp: registers for the landing zone = 2 * US * NBUF
-// 1: rows of the speculated next hop are prefetched into L2 during the current hop (rows up to ..._MAX_ROW bytes)
+// 1: rows of the speculated next hop are prefetched into L2 during the current hop (rows up to ..._MAX_ROW bytes).
+// Measured on B200 (r02, 2M x 128 clustered / 1M x 128 SIFT-like): no gain in the direct form (2.648 vs 2.647 ms), 5 %
+// slower in the staged form (3.16 vs 3.00 ms) — the 128-d kernel waits on dependent instructions, not on the rows.  Off.
 #ifndef TURDB_SPEC_PREFETCH
-#define TURDB_SPEC_PREFETCH 1
+#define TURDB_SPEC_PREFETCH 0
 #endif
 #ifndef TURDB_SPEC_PREFETCH_MAX_ROW
 #define TURDB_SPEC_PREFETCH_MAX_ROW 1024
