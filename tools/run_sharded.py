@@ -52,7 +52,7 @@ if args.config == 5:
     n = args.rows_per_rank or 12_500_000
     total = n * world
     nq = args.nq or 10_000
-    efs = [int(e) for e in (args.efs or "64,128,256").split(",")]
+    efs = [int(e) for e in (args.efs or "16,32,64,128").split(",")]
     gen_kw = dict(sigma=args.sigma, centre_latent=args.centre_latent, corpus_n=total)
     # the corpus is one clustered set of `total` rows; rank r holds rows [r n, (r+1) n): same centres, disjoint draws
     x = ds.clustered(n, dim, seed=1000 + rank, **gen_kw)
@@ -190,10 +190,22 @@ if args.config == 5:
     sms = allmax(e0.elapsed_time(e1) / 5)
     sql = dict(ef=ef_sql, per_rank_ms=sms, statements_per_s_per_rank=nq / sms * 1e3)
 
+def host_mem_available_gb():
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable"):
+                return int(ln.split()[1]) / 1e6
+    except OSError:
+        pass
+    return 0.0
+
+
 parity = None
-if rank == 0 and args.parity:
+if rank == 0 and args.parity and host_mem_available_gb() < 2.5 * x.nbytes / 1e9 + 8:
+    parity = dict(skipped=f"host MemAvailable {host_mem_available_gb():.0f} GB: the oracle copies the {x.nbytes / 1e9:.0f} GB arena")
+elif rank == 0 and args.parity:
     from oracle import binding as ob
-    cur_ef[0] = efs[min(1, len(efs) - 1)]
+    cur_ef[0] = efs[-1]
     local_search(dq, sharded.rows, sharded.dd, sharded.cnt)
     torch.cuda.synchronize()
     g_nodes = nodes.cpu().numpy().view(np.uint32)

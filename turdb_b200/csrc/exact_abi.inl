@@ -106,11 +106,20 @@ extern "C" int32_t turdb_cuda_shards_search_batch(turdb_cuda_index* const* shard
     g_last_error = err;
     return rc;
   }
-  // gather into shard 0 (peer copies ordered after each shard's search), then merge on shard 0's stream
+  // gather into shard 0 (peer copies ordered after each shard's search AND after shard 0's slab exists: it is a
+  // stream-ordered allocation on lanes[0].stream), then merge on shard 0's stream
   cudaError_t e = cudaSuccess;
+  cudaEvent_t slab0_ready = nullptr;
+  {
+    DeviceGuard g(shards[0]->device);
+    e = cudaEventCreateWithFlags(&slab0_ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(slab0_ready, lanes[0].stream);
+  }
   for (uint32_t s = 0; s < n_shards && e == cudaSuccess; ++s) {
     DeviceGuard g(shards[s]->device);
     uint8_t* dst = lanes[0].slab;
+    if (s != 0) e = cudaStreamWaitEvent(lanes[s].stream, slab0_ready, 0);
+    if (e != cudaSuccess) break;
     e = cudaMemcpyPeerAsync(dst + g_rows + (size_t)s * nq * k * 8, shards[0]->device, lanes[s].slab + off_rows, shards[s]->device,
                             (size_t)nq * k * 8, lanes[s].stream);
     if (e == cudaSuccess)
@@ -139,6 +148,11 @@ extern "C" int32_t turdb_cuda_shards_search_batch(turdb_cuda_index* const* shard
   }
   if (rc == TURDB_OK && e != cudaSuccess) rc = fail(TURDB_ERR_CUDA, "sharded search failed: %s", cudaGetErrorString(e));
   err = g_last_error;
+  if (slab0_ready) {
+    DeviceGuard g(shards[0]->device);
+    cudaStreamSynchronize(lanes[0].stream);
+    cudaEventDestroy(slab0_ready);
+  }
   cleanup();
   g_last_error = err;
   return rc;

@@ -224,8 +224,21 @@ static int32_t hnsw_file_parse(const uint8_t* data, uint64_t len, turdb_cuda_hns
 
 extern "C" {
 
+// no exception crosses the ABI: the parser's containers may throw bad_alloc on a huge (or hostile) file
+static int32_t hnsw_file_parse_noexcept(const uint8_t* bytes, uint64_t len, turdb_cuda_hnsw_file** out) {
+  try {
+    return hnsw_file_parse(bytes, len, out);
+  } catch (const std::bad_alloc&) {
+    if (out) *out = nullptr;
+    return fail(TURDB_ERR_OUT_OF_MEMORY, "out of host memory while parsing a %llu-byte .hnsw file", (unsigned long long)len);
+  } catch (...) {
+    if (out) *out = nullptr;
+    return fail(TURDB_ERR_INVALID_ARGUMENT, "unexpected failure while parsing the .hnsw file");
+  }
+}
+
 int32_t turdb_cuda_hnsw_file_open_memory(const uint8_t* bytes, uint64_t len, turdb_cuda_hnsw_file** out) {
-  return hnsw_file_parse(bytes, len, out);
+  return hnsw_file_parse_noexcept(bytes, len, out);
 }
 
 int32_t turdb_cuda_hnsw_file_open(const char* path, turdb_cuda_hnsw_file** out) {
@@ -248,7 +261,7 @@ int32_t turdb_cuda_hnsw_file_open(const char* path, turdb_cuda_hnsw_file** out) 
   const size_t got = buf.empty() ? 0 : fread(buf.data(), 1, buf.size(), fp);
   fclose(fp);
   if (got != buf.size()) return fail(TURDB_ERR_INVALID_ARGUMENT, "short read on '%s'", path);
-  return hnsw_file_parse(buf.data(), buf.size(), out);
+  return hnsw_file_parse_noexcept(buf.data(), buf.size(), out);
 }
 
 int32_t turdb_cuda_hnsw_file_close(turdb_cuda_hnsw_file* f) {
