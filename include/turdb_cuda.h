@@ -132,7 +132,7 @@ int32_t turdb_cuda_index_export_graph(turdb_cuda_index* idx, float* vectors, uin
  * with ef (search.rs:311-350), truncate to k (search.rs:245-252).  `ef` plays
  * HnswSearchContext::ef_search (search.rs:202-225).  visible == NULL -> search(); otherwise
  * search_filtered (mod.rs:1176-1273, search.rs:352-398) with one bit per NODE id
- * (bit i of word i/64 = is_visible(row_id of node i)).
+ * (bit i of word i/64 = is_visible(row_id of node i); the array holds ceil(n / 64) words).
  *
  * Outputs are [nq][k]; out_counts[q] results are valid (<= min(k, ef)), the rest are filled with
  * TURDB_INVALID_ROW / TURDB_INVALID_NODE / +inf.  Results ascend by distance.  out_node_ids,
@@ -302,9 +302,8 @@ int32_t turdb_cuda_merge_topk_device(int32_t device, const uint64_t* d_gathered_
  *
  * Dense ids: readable active slots in (page, slot) order, then "tombstones" — NodeIds that are referenced
  * but unreadable (deleted / missing / damaged); they keep the reference's behaviour for such nodes
- * (distance +inf under L2, no neighbours, row_id 0; mod.rs:1111-1127, 1159-1171).  With cosine / inner
- * product their distance is NaN (unspecified, like NaN elsewhere); the exact path must not be used on an
- * index that holds tombstones or absent vectors.
+ * (distance +inf whatever the metric, no neighbours, row_id 0; mod.rs:1111-1127, 1159-1171): an absent vector is
+ * uploaded as a row of +inf, and every kernel evaluates a row whose first element is +inf to distance +inf.
  */
 typedef struct turdb_cuda_hnsw_file turdb_cuda_hnsw_file; /* opaque, host memory only */
 

@@ -98,3 +98,27 @@ def test_batched_build_matches_sequential_quality(gpu_required, gen, kw, dim):
     cpu = ob.OracleGraph.from_arrays(g).search(q, 10, 64, ob.L2, n_threads=8)
     assert np.array_equal(bat[1], cpu[1]) and np.array_equal(bat[2].view(np.uint32), cpu[2].view(np.uint32))
     idx.close()
+
+
+def test_capacity_caps_on_the_device(gpu_required):
+    """The reference's node capacity tests (tests/hnsw_integration.rs:79-112: MAX + 5 additions leave MAX = 32 / 16) through
+    the device insert path (verbatim mode, sequential) and through index_create's clamp of an over-long count."""
+    n = 38
+    x = np.zeros((n, 4), np.float32)
+    x[:, 0] = np.arange(n) * 1e-3
+    rnd = np.full(n, 0.05)  # level 1 for every node (select_level, M = 16)
+    og = ob.OracleGraph.new(4, 16, 100, ob.BUILD_VERBATIM)
+    og.insert_batch(np.arange(n, dtype=np.uint64), x, rnd)
+    idx = CudaHnswIndex.build(x, None, rnd, mode=ob.BUILD_VERBATIM, max_batch=1)
+    g = idx.export_graph()
+    graphs_equal(g, og.export(), x)
+    assert g["l0_cnt"][0] == 32 and g["l0_adj"][0].tolist() == list(range(1, 33))
+    assert g["up_cnt"][g["up_base"][0]] == 16 and g["up_adj"][g["up_base"][0]].tolist() == list(range(1, 17))
+    idx.close()
+    # an uploaded row whose count claims more than the row holds is clamped to 32 entries
+    a = og.export()
+    a["l0_cnt"] = a["l0_cnt"].copy()
+    a["l0_cnt"][0] = 37
+    up = CudaHnswIndex.from_graph(a)
+    assert up.export_graph(with_vectors=False)["l0_cnt"][0] == 32
+    up.close()

@@ -7,6 +7,7 @@ import pytest
 from oracle import binding as ob
 
 INV = ob.INVALID
+TD_L0, TD_UP = 32, 16  # MAX_L0_NEIGHBORS, MAX_LEVEL_NEIGHBORS (src/hnsw/mod.rs:126-127)
 
 
 def graph_from_lists(vectors, l0, upper=None, entry=0, max_level=0, levels=None):
@@ -256,3 +257,21 @@ def test_sq8_from_f32_hand_computed():
     v = np.array([[-2.0, -1.0, 0.0, 2.0]], np.float32)
     codes, mn, sc = ob.sq8_encode(v)
     assert mn[0] == -2.0 and codes[0, 0] == 0 and codes[0, 3] == 255 and codes[0, 1] == 64 and codes[0, 2] == 127
+
+
+# ---- capacity caps: the reference's own unit tests (tests/hnsw_integration.rs:79-112) --------------------------
+def test_capacity_caps_like_the_reference_node_tests():
+    """add_level0_neighbor_respects_max_capacity / higher_level_respects_max_capacity: MAX + 5 additions leave MAX (32 at
+    level 0, 16 above); add_higher_level_neighbor_stores_correctly: the first addition lands in slot 0.  Here through the
+    insert path in verbatim mode, where every new node back-links into node 0's lists in arrival order."""
+    n = TD_L0 + 6  # node 0 + 37 more
+    x = np.zeros((n, 4), np.float32)
+    x[:, 0] = np.arange(n) * 1e-3  # distinct points, node 0 nearest to all in insertion order
+    rs = np.full(n, r_for_level(1))  # every node has level 1
+    g = ob.OracleGraph.new(4, mode=ob.BUILD_VERBATIM)
+    g.insert_batch(np.arange(n, dtype=np.uint64), x, rs)
+    a = g.export()
+    assert a["l0_cnt"][0] == TD_L0 and a["l0_adj"][0][:TD_L0].tolist() == list(range(1, TD_L0 + 1))
+    base = a["up_base"][0]
+    assert a["up_cnt"][base] == TD_UP and a["up_adj"][base][:TD_UP].tolist() == list(range(1, TD_UP + 1))
+    assert (a["l0_cnt"] <= TD_L0).all() and (a["up_cnt"] <= TD_UP).all()

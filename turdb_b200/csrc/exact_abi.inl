@@ -176,13 +176,14 @@ static EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
-// rows x kp BF16, row-major; box = 64 (K) x 128 (rows), 128-byte swizzle, out-of-range rows read as zero
-static bool make_bf16_map(CUtensorMap* map, const void* base, uint64_t rows, uint32_t kp) {
+// rows x kp BF16, row-major; box = 64 (K) x box_rows (128 queries / kTileN vectors), 128-byte swizzle, out-of-range rows
+// read as zero
+static bool make_bf16_map(CUtensorMap* map, const void* base, uint64_t rows, uint32_t kp, uint32_t box_rows) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return false;
   cuuint64_t dims[2] = {kp, rows};
   cuuint64_t strides[1] = {(cuuint64_t)kp * 2};
-  cuuint32_t box[2] = {kChunkK, kTileM};
+  cuuint32_t box[2] = {kChunkK, box_rows};
   cuuint32_t estr[2] = {1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -284,11 +285,11 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
                                                                                          idx->d_bf16_max2 + 2 * copy, metric, d_slack);
   }
   CUtensorMap map_q, map_x;
-  if (!make_bf16_map(&map_q, d_qb, nq, kp) || !make_bf16_map(&map_x, d_xb, n, kp))
+  if (!make_bf16_map(&map_q, d_qb, nq, kp, kTileM) || !make_bf16_map(&map_x, d_xb, n, kp, kTileN))
     return bail(fail(TURDB_ERR_CUDA, "cuTensorMapEncodeTiled failed"));
 
-  const size_t stage_bytes = stream_a ? 2 * (size_t)kChunkBytes : (size_t)kChunkBytes;
-  const size_t fixed_smem = (stream_a ? 0 : (size_t)k_chunks * kChunkBytes) + 4 * kTileN * 4 + 4 * kRing * kTileM * 4 + 24 * 8 + 16;
+  const size_t stage_bytes = (stream_a ? (size_t)kChunkBytes : 0) + (size_t)kBChunkBytes;
+  const size_t fixed_smem = (stream_a ? 0 : (size_t)k_chunks * kChunkBytes) + 4 * kTileN * 4 + 4 * kRing * kEpiThreads * 4 + 24 * 8 + 16;
   const uint32_t n_stages = (uint32_t)std::min<size_t>(kMaxStages, ((size_t)idx->max_smem_optin - fixed_smem) / stage_bytes);
   if (n_stages < 2) return bail(fail(TURDB_ERR_UNSUPPORTED, "not enough shared memory for the exact path at dim %u", dim));
   const size_t gemm_smem = fixed_smem + (size_t)n_stages * stage_bytes;

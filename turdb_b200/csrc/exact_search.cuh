@@ -241,13 +241,24 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32_nowait(uint32_t taddr, uint32
 // ------------------------------------------------------------------------------------------------
 // pass (1): GEMM + threshold filter
 // ------------------------------------------------------------------------------------------------
+// (r02) 256-column tiles: one MMA instruction covers N = 256, which halves the A bytes read from shared memory per flop —
+// the 1-CTA SS form is shared-memory-port bound (A + B reads + TMA writes: 288 KB per 128x128x384 tile through a
+// 128 B/clk port = 2250 cycles against 1632 cycles of MMAs; 480 KB per 128x256x384 tile = 3750 against 3264) — and eight
+// epilogue warps (two per TMEM lane quarter, 128 columns each) so that the epilogue keeps up with the wider tile.
+#ifndef TURDB_EXACT_TILE_N
+#define TURDB_EXACT_TILE_N 256
+#endif
 constexpr uint32_t kTileM = 128;   // queries per CTA tile (UMMA M)
-constexpr uint32_t kTileN = 128;   // vectors per MMA tile (UMMA N)
+constexpr uint32_t kTileN = TURDB_EXACT_TILE_N;   // vectors per MMA tile (UMMA N): 128 or 256
 constexpr uint32_t kChunkK = 64;   // BF16 elements per 128 B swizzle row
-constexpr uint32_t kChunkBytes = kTileM * kChunkK * 2;  // 16 KB per operand chunk
-constexpr uint32_t kMaxStages = 8; // B pipeline depth is chosen at launch (as many 16 KB stages as fit)
-constexpr uint32_t kRing = 8;       // candidates a thread parks in shared memory before one atomic reserves their slots
-constexpr uint32_t kExactThreads = 192;  // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
+constexpr uint32_t kChunkBytes = kTileM * kChunkK * 2;   // 16 KB per A (query) chunk
+constexpr uint32_t kBChunkBytes = kTileN * kChunkK * 2;  // 16 / 32 KB per B (vector) chunk
+constexpr uint32_t kMaxStages = 8; // B pipeline depth is chosen at launch (as many stages as fit)
+constexpr uint32_t kRing = 4;       // candidates a thread parks in shared memory before one atomic reserves their slots
+constexpr uint32_t kEpiWarps = 4 * (kTileN / 128);       // epilogue warps: one per (TMEM lane quarter, 128-column half)
+constexpr uint32_t kEpiThreads = 32 * kEpiWarps;
+constexpr uint32_t kExactThreads = 64 + kEpiThreads;  // warp 0 TMA, warp 1 MMA + TMEM alloc, then the epilogue warps
+static_assert(kTileN == 128 || kTileN == 256, "UMMA N");
 
 struct ExactArgs {
   uint32_t n_vec, nq, k_chunks;
@@ -277,12 +288,12 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
   uint8_t* sA = smem;
   uint8_t* sB = sA + (STREAM_A ? 0 : (size_t)a.k_chunks * kChunkBytes);
   const uint32_t kStages = a.n_stages;
-  const uint32_t stage_bytes = STREAM_A ? 2 * kChunkBytes : kChunkBytes;  // [A chunk |] B chunk
+  const uint32_t stage_bytes = (STREAM_A ? kChunkBytes : 0) + kBChunkBytes;  // [A chunk |] B chunk
   const uint32_t b_in_stage = STREAM_A ? kChunkBytes : 0;
-  float* s_bias = reinterpret_cast<float*>(sB + (size_t)kStages * stage_bytes);  // [2][128] (+ pad to 2 KB)
-  float* ring_key = s_bias + 4 * kTileN;                                              // [2][kRing][128] pending candidates
-  uint32_t* ring_col = reinterpret_cast<uint32_t*>(ring_key + 2 * kRing * kTileM);    // [2][kRing][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_col + 2 * kRing * kTileM);
+  float* s_bias = reinterpret_cast<float*>(sB + (size_t)kStages * stage_bytes);  // [2][kTileN] (+ pad)
+  float* ring_key = s_bias + 4 * kTileN;                                              // [2][kRing][epilogue threads] pending candidates
+  uint32_t* ring_col = reinterpret_cast<uint32_t*>(ring_key + 2 * kRing * kEpiThreads);  // [2][kRing][epilogue threads]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_col + 2 * kRing * kEpiThreads);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
   const uint32_t bar_a_full = smem_u32(bars + 0), bar_a_empty = smem_u32(bars + 1);
   const uint32_t bar_b_full = smem_u32(bars + 2), bar_b_empty = smem_u32(bars + 2 + kMaxStages);
@@ -297,12 +308,12 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
     }
     for (uint32_t s = 0; s < 2; ++s) {
       mbar_init(bar_t_full + 8 * s, 1);
-      mbar_init(bar_t_empty + 8 * s, 4);  // one arrive per epilogue warp
+      mbar_init(bar_t_empty + 8 * s, kEpiWarps);  // one arrive per epilogue warp
     }
     mbar_fence_init();
   }
-  if (warp == 1) {  // 2 accumulator buffers x 128 FP32 columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u)
+  if (warp == 1) {  // 2 accumulator buffers x kTileN FP32 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2u * kTileN)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -398,7 +409,7 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
       }
     }
   } else {
-    // ===== epilogue: 4 warps, thread = one query row, 128 scores per tile =====
+    // ===== epilogue: kEpiWarps warps, thread = one query row x 128 of the tile's columns =====
     // ncu (round 1, source counters): a third of all samples sat in the MMA issuer's wait for a drained accumulator
     // and 17 % in the candidate flush (an atomicAdd round trip with the accumulator still held).  Hence:
     //  * the whole 128-column row is read into registers at once (4 x tcgen05.ld, one wait) and the accumulator is
@@ -407,7 +418,8 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
     //    its result is consumed one flush later (double-buffered ring), so nobody waits for the round trip.
     const uint32_t quarter = warp & 3;               // TMEM lane quarter this warp may read
     const uint32_t row = quarter * 32 + lane;
-    const uint32_t et = threadIdx.x - 64;            // 0..127 among epilogue threads
+    const uint32_t et = threadIdx.x - 64;            // index among the epilogue threads
+    const uint32_t chalf = (warp - 2) >> 2;          // which 128 columns of the tile this warp reads (0 when kTileN == 128)
     uint32_t acc = 0, acc_phase = 0;
     uint32_t half = 0, n_pend = 0;                   // ring half being filled, entries in it
     uint32_t p_pos = 0, p_n = 0, p_q = 0;            // reserved-but-unwritten flush of the other half
@@ -415,8 +427,8 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
       const uint32_t base = (half ^ 1) * kRing;
       for (uint32_t i = 0; i < p_n; ++i) {
         if (p_pos + i < a.cap) {
-          a.cand_id[(size_t)p_q * a.cap + p_pos + i] = ring_col[(base + i) * kTileM + et];
-          a.cand_key[(size_t)p_q * a.cap + p_pos + i] = ring_key[(base + i) * kTileM + et];
+          a.cand_id[(size_t)p_q * a.cap + p_pos + i] = ring_col[(base + i) * kEpiThreads + et];
+          a.cand_key[(size_t)p_q * a.cap + p_pos + i] = ring_key[(base + i) * kEpiThreads + et];
         } else {
           a.qflags[p_q] = 1u;
         }
@@ -439,10 +451,10 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
         n_pend = 0;
       };
       for (uint32_t t = t0; t < t1; ++t) {
-        if (BIAS) {  // stage this tile's per-column bias (L2: -|x|^2/2)
+        if (BIAS) {  // stage this tile's per-column bias (L2: -|x|^2/2): kEpiThreads == kTileN, one column each
           const uint64_t col = (uint64_t)t * kTileN + et;
           s_bias[acc * kTileN + et] = col < a.n_vec ? a.col_bias[col] : 0.f;
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         }
         long long c6 = (a.dbg && et == 0) ? clock64() : 0;
         mbar_wait(bar_t_full + 8 * acc, acc_phase);
@@ -450,14 +462,14 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
         tc_fence_after();
         const uint32_t n_valid = min(kTileN, a.n_vec - t * kTileN);  // columns past the corpus are zero rows
         uint32_t v[4][32];
-        const uint32_t tcol = tmem_base + ((quarter * 32) << 16) + acc * kTileN;
+        const uint32_t tcol = tmem_base + ((quarter * 32) << 16) + acc * kTileN + chalf * 128;
 #pragma unroll
         for (uint32_t cb = 0; cb < 4; ++cb) tmem_ld_32x32b_x32_nowait(tcol + cb * 32, v[cb]);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_t_empty + 8 * acc);  // the tensor pipe may refill this accumulator now
-        const uint32_t bias_buf = acc * kTileN;
+        const uint32_t bias_buf = acc * kTileN + chalf * 128;
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -487,7 +499,8 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
           if (mx[0] >= tau) {
             // rare: count first, make room once, then predicated pushes — no call inside the unrolled loop, so
             // the hot path (above) stays a few hundred instructions
-            const uint32_t lim = n_valid > cb * 32 ? min(32u, n_valid - cb * 32) : 0u;
+            const uint32_t c0 = chalf * 128 + cb * 32;  // first tile column of this 32-column block
+            const uint32_t lim = n_valid > c0 ? min(32u, n_valid - c0) : 0u;
             uint32_t cnt = 0;
 #pragma unroll
             for (uint32_t j = 0; j < 32; ++j) cnt += (__uint_as_float(v[cb][j]) >= tau && j < lim) ? 1u : 0u;
@@ -501,7 +514,7 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
                 const float key = __uint_as_float(v[cb][j]);
                 if (key >= tau && j < lim) {
                   if (o < a.cap) {
-                    a.cand_id[(size_t)q * a.cap + o] = t * kTileN + cb * 32 + j;
+                    a.cand_id[(size_t)q * a.cap + o] = t * kTileN + c0 + j;
                     a.cand_key[(size_t)q * a.cap + o] = key;
                   } else {
                     a.qflags[q] = 1u;
@@ -515,8 +528,8 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
               for (uint32_t j = 0; j < 32; ++j) {
                 const float key = __uint_as_float(v[cb][j]);
                 if (key >= tau && j < lim) {
-                  ring_key[(half * kRing + n_pend) * kTileM + et] = key;
-                  ring_col[(half * kRing + n_pend) * kTileM + et] = t * kTileN + cb * 32 + j;
+                  ring_key[(half * kRing + n_pend) * kEpiThreads + et] = key;
+                  ring_col[(half * kRing + n_pend) * kEpiThreads + et] = t * kTileN + c0 + j;
                   ++n_pend;
                 }
               }
@@ -538,7 +551,7 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * kTileN) : "memory");
   }
 }
 
