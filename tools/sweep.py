@@ -29,6 +29,7 @@ ap.add_argument("--libs", default="", help="A/B: comma-separated library files; 
 ap.add_argument("--graph", default="", help="(internal) npz with a prebuilt graph")
 ap.add_argument("--sq8", action="store_true", help="traverse the SQ8 arena (enable_sq8 + search_batch_sq8_device)")
 ap.add_argument("--genkw", default="{}", help="JSON keyword arguments of the generator (clustered: corpus_n defaults to --n)")
+ap.add_argument("--builder", default="knn", choices=["knn", "insert"], help="graph source: exact-kNN stand-in or the device insert path")
 ap.add_argument("--probe", default="", help="gather-ceiling probe settings: ctas_per_sm,slots,cta_smem_bytes;...")
 args = ap.parse_args()
 
@@ -47,6 +48,11 @@ if args.graph:
     z = np.load(args.graph)
     arrays = {k: (z[k] if z[k].ndim else z[k].item()) for k in z.files}
     arrays["vectors"] = x
+elif args.builder == "insert":
+    b = CudaHnswIndex.build(x, None, None, max_batch=8192, seed=42)
+    arrays = b.export_graph(with_vectors=False)
+    arrays["vectors"] = x
+    b.close()
 else:
     arrays = build_graph(x, seed=42)
     torch.cuda.synchronize()
