@@ -178,14 +178,14 @@ static EncodeTiledFn get_encode_tiled() {
 
 // rows x kp BF16, row-major; box = 64 (K) x box_rows (128 queries / kTileN vectors), 128-byte swizzle, out-of-range rows
 // read as zero
-static bool make_bf16_map(CUtensorMap* map, const void* base, uint64_t rows, uint32_t kp, uint32_t box_rows) {
+static bool make_bf16_map(CUtensorMap* map, const void* base, uint64_t rows, uint32_t kp, uint32_t box_rows, int fp16) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return false;
   cuuint64_t dims[2] = {kp, rows};
   cuuint64_t strides[1] = {(cuuint64_t)kp * 2};
   cuuint32_t box[2] = {kChunkK, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  return enc(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -231,25 +231,37 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
   const int copy = metric == kCosine ? 1 : 0;
   {
     std::lock_guard<std::mutex> lk(idx->mu);
-    __nv_bfloat16*& dst = copy ? idx->d_arena_bf16n : idx->d_arena_bf16;
+    uint16_t*& dst = copy ? idx->d_arena_bf16n : idx->d_arena_bf16;
     if (!dst) {
       if (!idx->d_bf16_max2) {
-        CUDA_TRY(cudaMalloc(&idx->d_bf16_max2, 4 * 4));
-        CUDA_TRY(cudaMemsetAsync(idx->d_bf16_max2, 0, 4 * 4, stream));
+        CUDA_TRY(cudaMalloc(&idx->d_bf16_max2, 5 * 4));  // [2 copies][2 maxima] + max |value| of the arena
+        CUDA_TRY(cudaMemsetAsync(idx->d_bf16_max2, 0, 5 * 4, stream));
+      }
+      if (!copy) {  // raw rows: FP16 only if every value fits comfortably (the cosine copy is unit-length rows: always FP16)
+        max_abs_kernel<<<(unsigned)((n * dim + 255) / 256), 256, 0, stream>>>(idx->d_arena, dim, ds, n, idx->d_bf16_max2 + 4);
+        uint32_t mbits = 0;
+        CUDA_TRY(cudaMemcpyAsync(&mbits, idx->d_bf16_max2 + 4, 4, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        float mabs;
+        memcpy(&mabs, &mbits, 4);
+        idx->half_fp16[0] = (mabs <= 16384.0f && getenv("TURDB_EXACT_FORCE_BF16") == nullptr) ? 1 : 0;
+      } else if (getenv("TURDB_EXACT_FORCE_BF16")) {
+        idx->half_fp16[1] = 0;
       }
       CUDA_TRY(cudaMalloc(&dst, (size_t)n * kp * 2));
       const uint64_t total = n * kp;
-      to_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(idx->d_arena, dim, ds, kp, n,
-                                                                            copy ? idx->d_norm2 : nullptr, dst);
+      to_half_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(idx->d_arena, dim, ds, kp, n,
+                                                                            copy ? idx->d_norm2 : nullptr, idx->half_fp16[copy], dst);
       bf16_rowerr_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(idx->d_arena, dim, ds, kp, n,
                                                                                  copy ? idx->d_norm2 : nullptr, dst,
-                                                                                 idx->d_bf16_max2 + 2 * copy);
+                                                                                 idx->half_fp16[copy], idx->d_bf16_max2 + 2 * copy);
       CUDA_TRY(cudaGetLastError());
       CUDA_TRY(cudaStreamSynchronize(stream));
       idx->device_bytes += (size_t)n * kp * 2;
     }
   }
-  const __nv_bfloat16* d_xb = copy ? idx->d_arena_bf16n : idx->d_arena_bf16;
+  const uint16_t* d_xb = copy ? idx->d_arena_bf16n : idx->d_arena_bf16;
+  const int fp16 = idx->half_fp16[copy];
 
   // scratch: Qb | col bias | thresh | cand_cnt | kept | slack | cand_id | cand_key
   size_t off = 0;
@@ -263,7 +275,7 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
                o_id = take((size_t)nq * cap * 4), o_key = take((size_t)nq * cap * 4);
   uint8_t* scr = nullptr;
   CUDA_TRY(cudaMallocFromPoolAsync(&scr, off, idx->pool, stream));
-  __nv_bfloat16* d_qb = (__nv_bfloat16*)(scr + o_qb);
+  uint16_t* d_qb = (uint16_t*)(scr + o_qb);
   float* d_bias = (float*)(scr + o_ab);
   float* d_th = (float*)(scr + o_th);
   uint32_t* d_cnt = (uint32_t*)(scr + o_cnt);
@@ -278,14 +290,19 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
 
   {
     const uint64_t total = (uint64_t)nq * kp;
-    to_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_queries, dim, dim, kp, nq, nullptr, d_qb);
+    to_half_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_queries, dim, dim, kp, nq, nullptr, fp16, d_qb);
     if (metric == kL2) col_bias_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(idx->d_norm2, n, d_bias);
     exact_init_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(d_th, d_cnt, d_kept, d_qflags, d_arch_cnt, nq);
-    query_slack_kernel<<<(unsigned)(((uint64_t)nq * 32 + 255) / 256), 256, 0, stream>>>(d_queries, dim, kp, nq, d_qb,
-                                                                                         idx->d_bf16_max2 + 2 * copy, metric, d_slack);
+    // diagnostic only (measuring what the certificate costs): TURDB_EXACT_SLACK_SCALE=0 turns the slack band off, which
+    // makes the filter the uncertified heuristic of round 1
+    float slack_scale = 1.0f;
+    if (const char* ev = getenv("TURDB_EXACT_SLACK_SCALE")) slack_scale = (float)atof(ev);
+    query_slack_kernel<<<(unsigned)(((uint64_t)nq * 32 + 255) / 256), 256, 0, stream>>>(d_queries, dim, kp, nq, d_qb, fp16,
+                                                                                         idx->d_bf16_max2 + 2 * copy, metric,
+                                                                                         slack_scale, d_slack);
   }
   CUtensorMap map_q, map_x;
-  if (!make_bf16_map(&map_q, d_qb, nq, kp, kTileM) || !make_bf16_map(&map_x, d_xb, n, kp, kTileN))
+  if (!make_bf16_map(&map_q, d_qb, nq, kp, kTileM, fp16) || !make_bf16_map(&map_x, d_xb, n, kp, kTileN, fp16))
     return bail(fail(TURDB_ERR_CUDA, "cuTensorMapEncodeTiled failed"));
 
   const size_t stage_bytes = (stream_a ? (size_t)kChunkBytes : 0) + (size_t)kBChunkBytes;
@@ -320,6 +337,7 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
     a.k_chunks = k_chunks;
     a.n_stages = n_stages;
     a.stream_a = stream_a;
+    a.fp16 = (uint32_t)fp16;
     a.tile_lo = lo;
     a.tile_hi = hi;
     const uint32_t tiles = hi - lo;

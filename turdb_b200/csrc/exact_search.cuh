@@ -13,6 +13,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -84,10 +85,22 @@ __global__ void merge_topk_kernel(const uint8_t* __restrict__ g_rows_b, const ui
 // ------------------------------------------------------------------------------------------------
 // operand preparation
 // ------------------------------------------------------------------------------------------------
-// FP32 rows [rows][ds] -> BF16 rows [rows][kp] (kp = dim rounded up to 64, zero padded).  With `norm2` the row is
+// 16-bit operand formats of the filter (tcgen05 kind::f16 takes either): BF16 (8-bit mantissa, FP32 range) or FP16 (11-bit
+// mantissa — an 8x smaller rounding error, hence an 8x narrower slack band and far fewer rows to rerank — but values
+// beyond +-65504 overflow).  The arena copy is FP16 whenever its largest |value| allows (always for the cosine copy, whose
+// rows are pre-scaled to unit length), else BF16; queries are converted to the arena copy's format per call, and a
+// query that overflows it gets an infinite error bound and is served by the streaming scan.
+__device__ __forceinline__ uint16_t to_half_bits(float v, int fp16) {
+  return fp16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+__device__ __forceinline__ float from_half_bits(uint16_t b, int fp16) {
+  return fp16 ? __half2float(__ushort_as_half(b)) : __bfloat162float(__ushort_as_bfloat16(b));
+}
+
+// FP32 rows [rows][ds] -> 16-bit rows [rows][kp] (kp = dim rounded up to 64, zero padded).  With `norm2` the row is
 // scaled by 1/|x| first, so that the cosine pass's score q.x/|x| is already its ranking key.
-__global__ void to_bf16_kernel(const float* __restrict__ src, uint32_t dim, uint32_t ds, uint32_t kp,
-                               uint64_t rows, const float* __restrict__ norm2, __nv_bfloat16* __restrict__ dst) {
+__global__ void to_half_kernel(const float* __restrict__ src, uint32_t dim, uint32_t ds, uint32_t kp,
+                               uint64_t rows, const float* __restrict__ norm2, int fp16, uint16_t* __restrict__ dst) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * kp) return;
   const uint64_t r = i / kp;
@@ -97,7 +110,16 @@ __global__ void to_bf16_kernel(const float* __restrict__ src, uint32_t dim, uint
     const float n2 = norm2[r];
     v = n2 > 0.f ? v * rsqrtf(n2) : 0.f;
   }
-  dst[i] = __float2bfloat16_rn(v);
+  dst[i] = to_half_bits(v, fp16);
+}
+
+// largest |value| of the arena (picks the copy's format)
+__global__ void max_abs_kernel(const float* __restrict__ src, uint32_t dim, uint32_t ds, uint64_t rows, uint32_t* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float m = 0.f;
+  if (i < rows * dim) m = fabsf(src[(i / dim) * ds + (i % dim)]);
+  for (uint32_t off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(kFullMask, m, off));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
 }
 
 // What the BF16 rounding cost, per operand set: max over rows of |v - bf16(v)|_2 and of |bf16(v)|_2 (v = the FP32 row
@@ -105,7 +127,7 @@ __global__ void to_bf16_kernel(const float* __restrict__ src, uint32_t dim, uint
 // patterns of non-negative floats (atomicMax on uint32).  They bound the filter's score error (query_slack_kernel), so
 // that the tensor-core pass is a CERTIFIED filter: it never drops a row the exact ranking would keep.
 __global__ void bf16_rowerr_kernel(const float* __restrict__ src, uint32_t dim, uint32_t ds, uint32_t kp, uint64_t rows,
-                                   const float* __restrict__ norm2, const __nv_bfloat16* __restrict__ conv,
+                                   const float* __restrict__ norm2, const uint16_t* __restrict__ conv, int fp16,
                                    uint32_t* __restrict__ out_max2) {
   const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -117,7 +139,7 @@ __global__ void bf16_rowerr_kernel(const float* __restrict__ src, uint32_t dim, 
   }
   float e2 = 0.f, n2b = 0.f;
   for (uint32_t c = lane; c < dim; c += 32) {
-    const float v = src[r * ds + c] * sc, b = __bfloat162float(conv[r * kp + c]);
+    const float v = src[r * ds + c] * sc, b = from_half_bits(conv[r * kp + c], fp16);
     e2 = fmaf(v - b, v - b, e2);
     n2b = fmaf(b, b, n2b);
   }
@@ -140,13 +162,13 @@ __global__ void bf16_rowerr_kernel(const float* __restrict__ src, uint32_t dim, 
 // The filter admits a key >= tau - 2 e(q) where tau is the kprime-th best FILTER key seen so far; a rejected row then
 // has an exact key below the exact keys of kprime admitted rows.
 __global__ void query_slack_kernel(const float* __restrict__ queries, uint32_t dim, uint32_t kp, uint32_t nq,
-                                   const __nv_bfloat16* __restrict__ qconv, const uint32_t* __restrict__ arena_max2,
-                                   int metric, float* __restrict__ slack) {
+                                   const uint16_t* __restrict__ qconv, int fp16, const uint32_t* __restrict__ arena_max2,
+                                   int metric, float scale, float* __restrict__ slack) {
   const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (q >= nq) return;
   float e2 = 0.f, n2 = 0.f;
   for (uint32_t c = lane; c < dim; c += 32) {
-    const float v = queries[(size_t)q * dim + c], b = __bfloat162float(qconv[(size_t)q * kp + c]);
+    const float v = queries[(size_t)q * dim + c], b = from_half_bits(qconv[(size_t)q * kp + c], fp16);
     e2 = fmaf(v - b, v - b, e2);
     n2 = fmaf(v, v, n2);
   }
@@ -166,7 +188,7 @@ __global__ void query_slack_kernel(const float* __restrict__ queries, uint32_t d
     } else {
       e += 2.3841858e-7f * (float)(dim / 8 + 8) * qn * (Xn + Dx);
     }
-    slack[q] = 2.02f * e;
+    slack[q] = 2.02f * e * scale;  // scale == 1 always, except under the TURDB_EXACT_SLACK_SCALE diagnostic (uncertified)
   }
 }
 
@@ -263,6 +285,7 @@ static_assert(kTileN == 128 || kTileN == 256, "UMMA N");
 struct ExactArgs {
   uint32_t n_vec, nq, k_chunks;
   uint32_t n_stages;              // B pipeline stages (2..kMaxStages)
+  uint32_t fp16;                  // operand format: 1 FP16, 0 BF16 (instruction descriptor a_format / b_format)
   uint32_t stream_a;              // 1: A (the query block) is not resident; its K chunk travels in every stage, ahead
                                   //    of the B chunk (dims above 512: 128 x K BF16 no longer fits beside the pipeline)
   uint32_t tile_lo, tile_hi;      // vector tiles of this pass
@@ -363,7 +386,8 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
     // ===== MMA issuer (one elected lane) =====
     if (lane == 0) {
       // instruction descriptor: D=F32, A=B=BF16, both K-major, N=128, M=128 (cute::UMMA::InstrDescriptor)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((kTileN >> 3) << 17) | ((kTileM >> 4) << 24);
+      const uint32_t fmt = a.fp16 ? 0u : 1u;  // a_format (bits 7-9) / b_format (bits 10-12): 0 = F16, 1 = BF16
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((kTileN >> 3) << 17) | ((kTileM >> 4) << 24);
       uint32_t stage = 0, phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
       for (uint32_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
         const uint32_t t0 = a.tile_lo + (item / a.n_qblocks) * a.tiles_per_item;

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -69,8 +70,9 @@ struct turdb_cuda_index {
   uint8_t* d_arena_sq8 = nullptr;          // SQ8 rows: dim codes | pad | min | scale, sq8_row_bytes apart (enable_sq8)
   float* d_norm2_sq8 = nullptr;            // dot(decode(x), decode(x)) per row, AVX2 lane order
   uint32_t sq8_row_bytes = 0;
-  __nv_bfloat16* d_arena_bf16 = nullptr;   // exact path operand (raw rows: L2, IP), built lazily
-  __nv_bfloat16* d_arena_bf16n = nullptr;  // exact path operand (rows scaled by 1/|x|: cosine), built lazily
+  uint16_t* d_arena_bf16 = nullptr;        // exact path operand (raw rows: L2, IP), 16-bit (FP16 or BF16), built lazily
+  uint16_t* d_arena_bf16n = nullptr;       // exact path operand (rows scaled by 1/|x|: cosine), FP16, built lazily
+  int half_fp16[2] = {0, 1};               // format of the two copies: 1 FP16, 0 BF16
   uint32_t* d_bf16_max2 = nullptr;         // [2 copies][2]: max |v - bf16(v)|_2, max |bf16(v)|_2 over rows (float bits)
   cudaMemPool_t pool = nullptr;            // per-index stream-ordered scratch pool (never trimmed)
   uint64_t device_bytes = 0;
