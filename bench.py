@@ -55,6 +55,7 @@ def parse():
                     help="insert: the reference's insert path on the device (turdb_cuda_index_build); knn: exact-kNN stand-in")
     ap.add_argument("--ef-construction", type=int, default=100)
     ap.add_argument("--build-batch", type=int, default=4096, help="insert path: nodes per step (1 = sequential)")
+    ap.add_argument("--build-graph-only", default="", help="(internal) build rank 0's graph, save it as .npz, exit")
     ap.add_argument("--out", default="")
     return ap.parse_args()
 
@@ -179,21 +180,29 @@ def run_reference(args, rank, world):
     """The reference algorithm (oracle port, AVX2+FMA, all host threads) on the same config."""
     if rank != 0:
         return
-    import torch
     from oracle import binding as ob
     x, qb = make_data(args, 0)
-    # the SAME graph as the GPU arm's rank 0 (same data, same seed, same builder); building it is not the timed path
-    if torch.cuda.is_available():
-        bidx, arrays, prov = build_index(args, x, np.arange(args.n, dtype=np.uint64), 0)
-        if arrays is None:
-            arrays = bidx.export_graph()
-        bidx.close()
+    # The SAME graph as the GPU arm's rank 0 (same data, same seed, same builder).  Building it is not the timed path and
+    # happens in a CHILD process (bench.py --build-graph-only), so that this process — the one being timed — loads the
+    # oracle library and nothing of this repo's CUDA code.
+    import tempfile
+    path = os.path.join(tempfile.gettempdir(), f"turdb_ref_graph_{os.getpid()}.npz")
+    child = [sys.executable, os.path.abspath(__file__), "--build-graph-only", path] + [a for a in sys.argv[1:] if a not in ("--impl", "reference")]
+    rc = subprocess.run(child, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if rc.returncode == 0 and os.path.exists(path):
+        z = np.load(path, allow_pickle=False)
+        arrays = {k: z[k] for k in ("row_ids", "levels", "l0_adj", "l0_cnt", "up_base", "up_adj", "up_cnt")}
+        arrays["entry"], arrays["max_level"] = int(z["entry"]), int(z["max_level"])
+        prov = str(z["provenance"])
+        os.remove(path)
+        arrays["vectors"] = x
+        g = ob.OracleGraph.from_arrays(arrays)
+    elif args.n <= 50_000:  # no device to build on: the oracle's own sequential insert path (small corpora only)
+        g = ob.OracleGraph.build(x, m=args.m, ef_construction=args.ef_construction, mode=ob.BUILD_INTENT, seed=args.seed)
+        prov = "oracle sequential insert path (reference-intent)"
     else:
-        from turdb_b200.graph_build import build_graph
-        arrays = build_graph(x, m=args.m, seed=args.seed, device="cpu")
-        prov = arrays["provenance"]
-    arrays["vectors"] = x
-    g = ob.OracleGraph.from_arrays(arrays)
+        print(json.dumps({"impl": "reference", "unavailable": "graph build child failed: " + rc.stdout[-300:].replace("\n", " ")}), flush=True)
+        return
     cores = os.cpu_count() or 1
     sample = args.cpu_sample or min(args.nq, max(256, 125 * cores))
     times = []
@@ -226,6 +235,15 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.build_graph_only:  # child of the reference arm: rank 0's graph -> .npz
+        x, _ = make_data(args, 0)
+        bidx, arrays, prov = build_index(args, x, np.arange(args.n, dtype=np.uint64), 0)
+        if arrays is None:
+            arrays = bidx.export_graph(with_vectors=False)
+        bidx.close()
+        np.savez(args.build_graph_only, provenance=np.array(prov), entry=np.array(arrays["entry"]), max_level=np.array(arrays["max_level"]),
+                 **{k: arrays[k] for k in ("row_ids", "levels", "l0_adj", "l0_cnt", "up_base", "up_adj", "up_cnt")})
+        return
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
