@@ -58,4 +58,7 @@ def test_sass_shows_the_blackwell_native_paths():
     assert "sm_100a" in out
     for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UBLKCP", "UBLKPF", "FFMA2"):
         assert mnemonic in out, f"{mnemonic} missing from the SASS of libturdb_cuda.so"
-    assert "HGMMA" not in out and "HMMA." not in out  # no Hopper wgmma, no legacy mma.sync tensor path
+    import re
+    # no Hopper wgmma, no legacy mma.sync tensor path (UTCHMMA[.2CTA] is the tcgen05 instruction, not HMMA)
+    assert "HGMMA" not in out and not re.search(r"(?<![A-Z])HMMA\.", out)
+    assert "UTCHMMA.2CTA" in out and "UTMALDG.2D.2CTA" in out  # the exact path's two-CTA (cta_group::2) form

@@ -158,6 +158,10 @@ extern "C" int32_t turdb_cuda_shards_search_batch(turdb_cuda_index* const* shard
   return rc;
 }
 
+#ifndef TURDB_EXACT_PAIR_DEFAULT
+#define TURDB_EXACT_PAIR_DEFAULT 0
+#endif
+
 // ---- TMA descriptors: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -301,14 +305,20 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
                                                                                          idx->d_bf16_max2 + 2 * copy, metric,
                                                                                          slack_scale, d_slack);
   }
+  // Two-CTA form (tcgen05 cta_group::2, clusters of 2): each CTA of a pair stages half of every vector tile, so the L2 -> SM
+  // traffic and the shared-memory fill per flop halve (exact_search.cuh).  TURDB_EXACT_PAIR=0/1 overrides the default.
+  int pair = TURDB_EXACT_PAIR_DEFAULT;
+  if (const char* ev = getenv("TURDB_EXACT_PAIR")) pair = atoi(ev) != 0;
+  if (idx->num_sms < 2) pair = 0;
   CUtensorMap map_q, map_x;
-  if (!make_bf16_map(&map_q, d_qb, nq, kp, kTileM, fp16) || !make_bf16_map(&map_x, d_xb, n, kp, kTileN, fp16))
+  if (!make_bf16_map(&map_q, d_qb, nq, kp, kTileM, fp16) || !make_bf16_map(&map_x, d_xb, n, kp, pair ? kTileN / 2 : kTileN, fp16))
     return bail(fail(TURDB_ERR_CUDA, "cuTensorMapEncodeTiled failed"));
 
-  const size_t stage_bytes = (stream_a ? (size_t)kChunkBytes : 0) + (size_t)kBChunkBytes;
-  const size_t fixed_smem = (stream_a ? 0 : (size_t)k_chunks * kChunkBytes) + 4 * kTileN * 4 + 4 * kRing * kEpiThreads * 4 + 24 * 8 + 16;
+  const size_t stage_bytes = exact_stage_bytes(stream_a != 0, pair != 0);
+  const size_t fixed_smem = exact_fixed_smem(k_chunks, stream_a != 0);
+  if ((size_t)idx->max_smem_optin < fixed_smem + 2 * stage_bytes)
+    return bail(fail(TURDB_ERR_UNSUPPORTED, "not enough shared memory for the exact path at dim %u", dim));
   const uint32_t n_stages = (uint32_t)std::min<size_t>(kMaxStages, ((size_t)idx->max_smem_optin - fixed_smem) / stage_bytes);
-  if (n_stages < 2) return bail(fail(TURDB_ERR_UNSUPPORTED, "not enough shared memory for the exact path at dim %u", dim));
   const size_t gemm_smem = fixed_smem + (size_t)n_stages * stage_bytes;
   cudaError_t e = cudaSuccess;
   {
@@ -321,12 +331,43 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
     set_smem(exact_gemm_filter_kernel<false, false>, (size_t)idx->max_smem_optin);
     set_smem(exact_gemm_filter_kernel<true, true>, (size_t)idx->max_smem_optin);
     set_smem(exact_gemm_filter_kernel<false, true>, (size_t)idx->max_smem_optin);
+    set_smem(exact_gemm_filter_pair_kernel<true, false>, (size_t)idx->max_smem_optin);
+    set_smem(exact_gemm_filter_pair_kernel<false, false>, (size_t)idx->max_smem_optin);
+    set_smem(exact_gemm_filter_pair_kernel<true, true>, (size_t)idx->max_smem_optin);
+    set_smem(exact_gemm_filter_pair_kernel<false, true>, (size_t)idx->max_smem_optin);
     set_smem(exact_threshold_kernel, (size_t)16384 * 8);
   }
   if (e != cudaSuccess) return bail(fail(TURDB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)));
 
+  // workers: CTAs, or CTA pairs (as many clusters of 2 as the device keeps resident at this shared-memory size)
+  uint32_t n_workers = (uint32_t)idx->num_sms;
+  if (pair) {
+    int max_clusters = 0;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(idx->num_sms & ~1), 1, 1);
+    cfg.blockDim = dim3(kExactThreads, 1, 1);
+    cfg.dynamicSmemBytes = gemm_smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t oe = metric == kL2 ? (stream_a ? cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<true, true>, &cfg)
+                                               : cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<true, false>, &cfg))
+                                   : (stream_a ? cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<false, true>, &cfg)
+                                               : cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<false, false>, &cfg));
+    if (oe != cudaSuccess || max_clusters <= 0) {
+      cudaGetLastError();
+      max_clusters = idx->num_sms / 2;
+    }
+    n_workers = (uint32_t)std::min<int>(max_clusters, idx->num_sms / 2);
+  }
+
   const uint32_t n_tiles = (uint32_t)((n + kTileN - 1) / kTileN);
-  const uint32_t n_qblocks = (nq + kTileM - 1) / kTileM;
+  const uint32_t q_rows = pair ? 2 * kTileM : kTileM;  // queries per work item
+  const uint32_t n_qblocks = (nq + q_rows - 1) / q_rows;
   // first slice: every column becomes a candidate (threshold -inf), so it must fit the buffer
   uint32_t lo = 0, span = std::max(1u, std::min(first_rows, cap / 2) / kTileN);
   while (lo < n_tiles) {
@@ -341,7 +382,7 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
     a.tile_lo = lo;
     a.tile_hi = hi;
     const uint32_t tiles = hi - lo;
-    uint32_t tpi = (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(1, ((uint64_t)tiles * n_qblocks) / (4ull * idx->num_sms)));
+    uint32_t tpi = (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(1, ((uint64_t)tiles * n_qblocks) / (4ull * n_workers)));
     a.tiles_per_item = tpi;
     a.n_qblocks = n_qblocks;
     a.n_items = n_qblocks * ((tiles + tpi - 1) / tpi);
@@ -353,8 +394,16 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
     a.cap = cap;
     a.qflags = d_qflags;
     a.dbg = idx->d_dbg;
-    const uint32_t grid = std::min<uint32_t>(a.n_items, (uint32_t)idx->num_sms);
-    if (metric == kL2) {
+    const uint32_t grid = std::min<uint32_t>(a.n_items, n_workers) * (pair ? 2u : 1u);
+    if (pair) {  // __cluster_dims__(2, 1, 1) on the kernel: the grid is a multiple of 2
+      if (metric == kL2) {
+        if (stream_a) exact_gemm_filter_pair_kernel<true, true><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
+        else exact_gemm_filter_pair_kernel<true, false><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
+      } else {
+        if (stream_a) exact_gemm_filter_pair_kernel<false, true><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
+        else exact_gemm_filter_pair_kernel<false, false><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
+      }
+    } else if (metric == kL2) {
       if (stream_a) exact_gemm_filter_kernel<true, true><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
       else exact_gemm_filter_kernel<true, false><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
     } else {

@@ -263,24 +263,60 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32_nowait(uint32_t taddr, uint32
 // ------------------------------------------------------------------------------------------------
 // pass (1): GEMM + threshold filter
 // ------------------------------------------------------------------------------------------------
-// (r02) 256-column tiles: one MMA instruction covers N = 256, which halves the A bytes read from shared memory per flop —
-// the 1-CTA SS form is shared-memory-port bound (A + B reads + TMA writes: 288 KB per 128x128x384 tile through a
-// 128 B/clk port = 2250 cycles against 1632 cycles of MMAs; 480 KB per 128x256x384 tile = 3750 against 3264) — and eight
-// epilogue warps (two per TMEM lane quarter, 128 columns each) so that the epilogue keeps up with the wider tile.
+// 256-column tiles: one MMA instruction covers N = 256, which halves the A bytes read from shared memory per flop.
+//
+// (r02, second half) What bounded this kernel was never the tensor pipe: 10k x 1M took 14 ms at 128-d, 13.5 ms at 384-d
+// and 16.3 ms at 768-d, i.e. the time followed the number of SCORES, not the flops — the MMA issuer sat waiting for a
+// drained accumulator (7.2k cycles per 128-d tile in the per-role cycle counters).  The epilogue is therefore built for
+// latency, not for instruction count:
+//  * sixteen epilogue warps (one per TMEM lane quarter x 64-column slice; TURDB_EXACT_EPI_COLS) so that four warps per
+//    scheduler hide each other's dependent chains;
+//  * per 32-column block: four 8-column group maxima and their maximum (3-input FMNMX), ONE warp vote; a block nobody's
+//    threshold reaches costs ~25 instructions;
+//  * a block that is reached looks only at the 8-column groups that are (one vote each), column by column with a ballot:
+//    control flow stays warp-uniform, and the rare survivors go to a per-WARP queue in shared memory
+//    (slot = running count + popc(ballot below me));
+//  * when the queue passes 32 entries the whole warp flushes it: lane i reserves a slot in entry i's query buffer with
+//    its own atomicAdd — one round trip for up to 64 candidates instead of one per thread.
+//
+// Two-CTA form (`PAIR`, tcgen05 cta_group::2): at K >= 384 the next bound is L2 -> SM bandwidth — 148 CTAs each streaming
+// the whole slice need 148 x 192 KB per 256-column tile against ~6.3 KB/clk of L2 throughput = 4.6k cycles, above the
+// 3.1k cycles of its MMAs.  A CTA pair (cluster of 2 on one TPC) shares every vector tile: each CTA stages HALF of the
+// tile's rows (128 x 64 elements = 16 KB per stage) plus its own 128 queries, the leader issues M = 256 x N = 256 MMAs
+// that read A from both CTAs and B halves from both, and each CTA's TMEM receives its own 128 query rows x 256 columns.
+// L2 traffic and shared-memory fill per flop halve, and the B pipeline is twice as deep in time at the same bytes.
+// Barriers: TMA of both CTAs completes on the LEADER's full barriers (.cta_group::2 form, leader arms 2x the bytes);
+// tcgen05.commit multicasts "stage free" / "accumulator full" to both CTAs; both CTAs' epilogue warps arrive remotely on
+// the leader's "accumulator drained" barrier.
 #ifndef TURDB_EXACT_TILE_N
 #define TURDB_EXACT_TILE_N 256
 #endif
-constexpr uint32_t kTileM = 128;   // queries per CTA tile (UMMA M)
+#ifndef TURDB_EXACT_EPI_COLS
+#define TURDB_EXACT_EPI_COLS 64
+#endif
+constexpr uint32_t kTileM = 128;   // queries per CTA tile (UMMA M per CTA)
 constexpr uint32_t kTileN = TURDB_EXACT_TILE_N;   // vectors per MMA tile (UMMA N): 128 or 256
-constexpr uint32_t kChunkK = 64;   // BF16 elements per 128 B swizzle row
+constexpr uint32_t kChunkK = 64;   // 16-bit elements per 128 B swizzle row
 constexpr uint32_t kChunkBytes = kTileM * kChunkK * 2;   // 16 KB per A (query) chunk
-constexpr uint32_t kBChunkBytes = kTileN * kChunkK * 2;  // 16 / 32 KB per B (vector) chunk
 constexpr uint32_t kMaxStages = 8; // B pipeline depth is chosen at launch (as many stages as fit)
-constexpr uint32_t kRing = 4;       // candidates a thread parks in shared memory before one atomic reserves their slots
-constexpr uint32_t kEpiWarps = 4 * (kTileN / 128);       // epilogue warps: one per (TMEM lane quarter, 128-column half)
+constexpr uint32_t kEpiCols = TURDB_EXACT_EPI_COLS;      // tile columns one epilogue warp owns
+constexpr uint32_t kEpiWarps = 4 * (kTileN / kEpiCols);  // one per (TMEM lane quarter, column slice)
 constexpr uint32_t kEpiThreads = 32 * kEpiWarps;
 constexpr uint32_t kExactThreads = 64 + kEpiThreads;  // warp 0 TMA, warp 1 MMA + TMEM alloc, then the epilogue warps
+constexpr uint32_t kWq = 64;       // entries of a warp's candidate queue (flushed when more than 32 are pending)
 static_assert(kTileN == 128 || kTileN == 256, "UMMA N");
+static_assert(kEpiCols == 32 || kEpiCols == 64 || kEpiCols == 128, "epilogue slice");
+static_assert(kExactThreads <= 1024, "CTA size");
+
+// bytes of one B (vector) chunk a CTA stages: the whole tile's rows, or half of them in the two-CTA form
+__host__ __device__ constexpr uint32_t exact_b_chunk_bytes(bool pair) { return (pair ? kTileN / 2 : kTileN) * kChunkK * 2; }
+__host__ __device__ constexpr uint32_t exact_stage_bytes(bool stream_a, bool pair) {
+  return (stream_a ? kChunkBytes : 0u) + exact_b_chunk_bytes(pair);
+}
+// everything in dynamic shared memory except the pipeline stages (kernel and host compute the layout from this)
+__host__ __device__ constexpr uint32_t exact_fixed_smem(uint32_t k_chunks, bool stream_a) {
+  return (stream_a ? 0u : k_chunks * kChunkBytes) + 2 * kTileN * 4 + kEpiWarps * kWq * 12 + 32 * 8 + 16;
+}
 
 struct ExactArgs {
   uint32_t n_vec, nq, k_chunks;
@@ -289,8 +325,8 @@ struct ExactArgs {
   uint32_t stream_a;              // 1: A (the query block) is not resident; its K chunk travels in every stage, ahead
                                   //    of the B chunk (dims above 512: 128 x K BF16 no longer fits beside the pipeline)
   uint32_t tile_lo, tile_hi;      // vector tiles of this pass
-  uint32_t tiles_per_item;        // consecutive tiles one CTA handles for one query block
-  uint32_t n_qblocks, n_items;
+  uint32_t tiles_per_item;        // consecutive tiles one CTA (pair) handles for one query block
+  uint32_t n_qblocks, n_items;    // query blocks: 128 queries each, 256 (two CTAs x 128) in the two-CTA form
   const float* col_bias;          // [n_vec] (L2 only)
   const float* thresh;            // [nq] keep keys >= thresh
   uint32_t* cand_cnt;             // [nq]
@@ -301,23 +337,104 @@ struct ExactArgs {
   unsigned long long* dbg;  // optional [16] cycle counters (diagnostics)
 };
 
-// smem: [A: k_chunks x 16 KB][B: n_stages x 16 KB][col bias: 2 x 128 float + pad][barriers][tmem ptr]
-template <bool BIAS, bool STREAM_A>
-__global__ void __launch_bounds__(kExactThreads, 1)
-exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
-                         const ExactArgs a) {
+// ---- two-CTA (cta_group::2) helpers ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {  // same offset in CTA `rank` of the cluster
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion is counted on a barrier of EITHER CTA of the pair (`bar` is a shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {  // arrives on `bar`'s offset in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // acquires arrivals made by the peer CTA
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+
+__device__ __forceinline__ float max8(const uint32_t* v) {
+  const float a = fmaxf(fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])), __uint_as_float(v[2]));
+  const float b = fmaxf(fmaxf(__uint_as_float(v[3]), __uint_as_float(v[4])), __uint_as_float(v[5]));
+  return fmaxf(fmaxf(a, b), fmaxf(__uint_as_float(v[6]), __uint_as_float(v[7])));
+}
+
+// Flush of a warp's candidate queue (rare path, kept out of line): entry i belongs to query q_base + q_lane[i]; lane i
+// reserves a slot in that query's buffer with its own atomicAdd, so up to 64 candidates cost one round trip.
+__device__ __noinline__ void exact_wq_flush(uint32_t* cand_cnt, uint32_t* cand_id, float* cand_key, uint32_t* qflags, uint32_t cap,
+                                            const float* q_key, const uint32_t* q_id, const uint32_t* q_lane, uint32_t q_base,
+                                            uint32_t n) {
+  const uint32_t lane = threadIdx.x & 31;
+  __syncwarp();
+  for (uint32_t i = lane; i < n; i += 32) {
+    const uint32_t q = q_base + q_lane[i];
+    const uint32_t pos = atomicAdd(cand_cnt + q, 1u);
+    if (pos < cap) {
+      cand_id[(size_t)q * cap + pos] = q_id[i];
+      cand_key[(size_t)q * cap + pos] = q_key[i];
+    } else {
+      qflags[q] = 1u;
+    }
+  }
+  __syncwarp();
+}
+
+// smem: [A: k_chunks x 16 KB (resident form)][stages: n_stages x ([A chunk] B chunk)][col bias: 2 x kTileN float]
+//       [warp queues: key | id | lane][barriers][tmem ptr]
+template <bool BIAS, bool STREAM_A, bool PAIR>
+__device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q, const CUtensorMap* map_x, const ExactArgs& a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;   // CTA within the pair; rank 0 (the leader) issues the MMAs
+  const uint32_t n_workers = PAIR ? gridDim.x >> 1 : gridDim.x, worker = PAIR ? blockIdx.x >> 1 : blockIdx.x;
+  constexpr uint32_t kBRows = PAIR ? kTileN / 2 : kTileN;          // vector rows this CTA stages per tile
+  constexpr uint32_t stage_bytes = exact_stage_bytes(STREAM_A, PAIR);  // [A chunk |] B chunk
+  constexpr uint32_t b_in_stage = STREAM_A ? kChunkBytes : 0;
+  constexpr uint32_t kQRows = PAIR ? 2 * kTileM : kTileM;          // queries per work item
   uint8_t* sA = smem;
   uint8_t* sB = sA + (STREAM_A ? 0 : (size_t)a.k_chunks * kChunkBytes);
   const uint32_t kStages = a.n_stages;
-  const uint32_t stage_bytes = (STREAM_A ? kChunkBytes : 0) + kBChunkBytes;  // [A chunk |] B chunk
-  const uint32_t b_in_stage = STREAM_A ? kChunkBytes : 0;
-  float* s_bias = reinterpret_cast<float*>(sB + (size_t)kStages * stage_bytes);  // [2][kTileN] (+ pad)
-  float* ring_key = s_bias + 4 * kTileN;                                              // [2][kRing][epilogue threads] pending candidates
-  uint32_t* ring_col = reinterpret_cast<uint32_t*>(ring_key + 2 * kRing * kEpiThreads);  // [2][kRing][epilogue threads]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_col + 2 * kRing * kEpiThreads);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  float* s_bias = reinterpret_cast<float*>(sB + (size_t)kStages * stage_bytes);  // [2][kTileN]
+  float* wq_key = s_bias + 2 * kTileN;                                            // [kEpiWarps][kWq]
+  uint32_t* wq_id = reinterpret_cast<uint32_t*>(wq_key + kEpiWarps * kWq);
+  uint32_t* wq_lane = wq_id + kEpiWarps * kWq;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wq_lane + kEpiWarps * kWq);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
   const uint32_t bar_a_full = smem_u32(bars + 0), bar_a_empty = smem_u32(bars + 1);
   const uint32_t bar_b_full = smem_u32(bars + 2), bar_b_empty = smem_u32(bars + 2 + kMaxStages);
   const uint32_t bar_t_full = smem_u32(bars + 2 + 2 * kMaxStages), bar_t_empty = smem_u32(bars + 4 + 2 * kMaxStages);
@@ -331,49 +448,68 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
     }
     for (uint32_t s = 0; s < 2; ++s) {
       mbar_init(bar_t_full + 8 * s, 1);
-      mbar_init(bar_t_empty + 8 * s, kEpiWarps);  // one arrive per epilogue warp
+      mbar_init(bar_t_empty + 8 * s, (PAIR ? 2 : 1) * kEpiWarps);  // one arrive per epilogue warp (of both CTAs)
     }
     mbar_fence_init();
   }
-  if (warp == 1) {  // 2 accumulator buffers x kTileN FP32 columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2u * kTileN)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 1) {  // 2 accumulator buffers x kTileN FP32 columns (in each CTA of a pair)
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2u * kTileN)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2u * kTileN)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers exist before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const unsigned long long k_t0 = a.dbg ? (unsigned long long)clock64() : 0ull;
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer (in BOTH CTAs of a pair: own queries, own half of the vector tile) =====
     if (lane == 0) {
+      // completions are counted on the leader's barriers; only the leader arms them (with both CTAs' bytes)
+      const uint32_t full_a = PAIR ? mapa_u32(bar_a_full, 0) : bar_a_full;
+      const uint32_t full_b = PAIR ? mapa_u32(bar_b_full, 0) : bar_b_full;
+      const uint32_t n_arm = PAIR ? 2u : 1u;
       uint32_t stage = 0, phase = 0, a_phase = 0;
-      for (uint32_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+      for (uint32_t item = worker; item < a.n_items; item += n_workers) {
         const uint32_t qb = item % a.n_qblocks;
+        const int32_t q_row0 = (int32_t)(qb * kQRows + rank * kTileM);
         const uint32_t t0 = a.tile_lo + (item / a.n_qblocks) * a.tiles_per_item;
         const uint32_t t1 = min(a.tile_hi, t0 + a.tiles_per_item);
         if (!STREAM_A) {
           long long c0 = a.dbg ? clock64() : 0;
           mbar_wait(bar_a_empty, a_phase ^ 1);  // previous item's MMAs have drained A
           if (a.dbg) atomicAdd(a.dbg + 0, (unsigned long long)(clock64() - c0));
-          mbar_expect_tx(bar_a_full, a.k_chunks * kChunkBytes);
-          for (uint32_t kc = 0; kc < a.k_chunks; ++kc)
-            tma_load_2d(smem_u32(sA + (size_t)kc * kChunkBytes), &map_q, (int32_t)(kc * kChunkK), (int32_t)(qb * kTileM), bar_a_full);
+          if (rank == 0) mbar_expect_tx(bar_a_full, n_arm * a.k_chunks * kChunkBytes);
+          for (uint32_t kc = 0; kc < a.k_chunks; ++kc) {
+            if (PAIR) tma_load_2d_pair(smem_u32(sA + (size_t)kc * kChunkBytes), map_q, (int32_t)(kc * kChunkK), q_row0, full_a);
+            else tma_load_2d(smem_u32(sA + (size_t)kc * kChunkBytes), map_q, (int32_t)(kc * kChunkK), q_row0, full_a);
+          }
           a_phase ^= 1;
         }
         for (uint32_t t = t0; t < t1; ++t) {
+          const int32_t x_row0 = (int32_t)(t * kTileN + rank * kBRows);
           for (uint32_t kc = 0; kc < a.k_chunks; ++kc) {
             long long c1 = a.dbg ? clock64() : 0;
             mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
             if (a.dbg) atomicAdd(a.dbg + 1, (unsigned long long)(clock64() - c1));
-            mbar_expect_tx(bar_b_full + 8 * stage, stage_bytes);
-            if (STREAM_A)  // the query block's chunk comes from L2 (it is 128 x K BF16, re-read once per vector tile)
-              tma_load_2d(smem_u32(sB + (size_t)stage * stage_bytes), &map_q, (int32_t)(kc * kChunkK), (int32_t)(qb * kTileM),
-                          bar_b_full + 8 * stage);
-            tma_load_2d(smem_u32(sB + (size_t)stage * stage_bytes + b_in_stage), &map_x, (int32_t)(kc * kChunkK),
-                        (int32_t)(t * kTileN), bar_b_full + 8 * stage);
+            if (rank == 0) mbar_expect_tx(bar_b_full + 8 * stage, n_arm * stage_bytes);
+            const uint32_t dst = smem_u32(sB + (size_t)stage * stage_bytes);
+            if (PAIR) {
+              if (STREAM_A) tma_load_2d_pair(dst, map_q, (int32_t)(kc * kChunkK), q_row0, full_b + 8 * stage);
+              tma_load_2d_pair(dst + b_in_stage, map_x, (int32_t)(kc * kChunkK), x_row0, full_b + 8 * stage);
+            } else {
+              if (STREAM_A)  // the query block's chunk comes from L2 (it is 128 x K, re-read once per vector tile)
+                tma_load_2d(dst, map_q, (int32_t)(kc * kChunkK), q_row0, full_b + 8 * stage);
+              tma_load_2d(dst + b_in_stage, map_x, (int32_t)(kc * kChunkK), x_row0, full_b + 8 * stage);
+            }
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
@@ -381,15 +517,25 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
           }
         }
       }
+      // drain: every stage (and A) has been released, i.e. every commit aimed at this CTA's barriers has landed —
+      // a CTA of a pair must not exit while its peer's tensor pipe can still signal it
+      for (uint32_t s = 0; s < kStages; ++s) {
+        mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (!STREAM_A) mbar_wait(bar_a_empty, a_phase ^ 1);
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one elected lane) =====
-    if (lane == 0) {
-      // instruction descriptor: D=F32, A=B=BF16, both K-major, N=128, M=128 (cute::UMMA::InstrDescriptor)
+    // ===== MMA issuer (one elected lane; in a pair only the leader CTA's) =====
+    if (lane == 0 && rank == 0) {
+      // instruction descriptor: D=F32, A=B=F16/BF16, both K-major, N, M (cute::UMMA::InstrDescriptor); M = 256 across a pair
       const uint32_t fmt = a.fp16 ? 0u : 1u;  // a_format (bits 7-9) / b_format (bits 10-12): 0 = F16, 1 = BF16
-      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((kTileN >> 3) << 17) | ((kTileM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((kTileN >> 3) << 17) | (((PAIR ? 2 * kTileM : kTileM) >> 4) << 24);
       uint32_t stage = 0, phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
-      for (uint32_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+      for (uint32_t item = worker; item < a.n_items; item += n_workers) {
         const uint32_t t0 = a.tile_lo + (item / a.n_qblocks) * a.tiles_per_item;
         const uint32_t t1 = min(a.tile_hi, t0 + a.tiles_per_item);
         if (!STREAM_A) {
@@ -401,7 +547,8 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
         tc_fence_after();
         for (uint32_t t = t0; t < t1; ++t) {
           long long c3 = a.dbg ? clock64() : 0;
-          mbar_wait(bar_t_empty + 8 * acc, acc_phase ^ 1);  // epilogue has drained this accumulator
+          if (PAIR) mbar_wait_cluster(bar_t_empty + 8 * acc, acc_phase ^ 1);  // both CTAs' epilogues have drained it
+          else mbar_wait(bar_t_empty + 8 * acc, acc_phase ^ 1);              // epilogue has drained this accumulator
           if (a.dbg) atomicAdd(a.dbg + 3, (unsigned long long)(clock64() - c3));
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * kTileN;
@@ -414,70 +561,63 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
                                                            : smem_u32(sA + (size_t)kc * kChunkBytes));
             const uint64_t db = umma_desc_sw128(smem_u32(sB + (size_t)stage * stage_bytes + b_in_stage));
 #pragma unroll
-            for (uint32_t k4 = 0; k4 < kChunkK / 16; ++k4)  // UMMA_K = 16 BF16 = 32 B inside the swizzle row
-              tc_mma_bf16(d_tmem, da + 2 * k4, db + 2 * k4, idesc, (kc | k4) != 0 ? 1u : 0u);
-            tc_commit(bar_b_empty + 8 * stage);  // frees the B stage when these MMAs retire
+            for (uint32_t k4 = 0; k4 < kChunkK / 16; ++k4) {  // UMMA_K = 16 elements = 32 B inside the swizzle row
+              if (PAIR) tc_mma_pair(d_tmem, da + 2 * k4, db + 2 * k4, idesc, (kc | k4) != 0 ? 1u : 0u);
+              else tc_mma_bf16(d_tmem, da + 2 * k4, db + 2 * k4, idesc, (kc | k4) != 0 ? 1u : 0u);
+            }
+            if (PAIR) tc_commit_pair(bar_b_empty + 8 * stage);  // frees the stage (in both CTAs) when these MMAs retire
+            else tc_commit(bar_b_empty + 8 * stage);
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
             }
           }
-          tc_commit(bar_t_full + 8 * acc);
+          if (PAIR) tc_commit_pair(bar_t_full + 8 * acc);
+          else tc_commit(bar_t_full + 8 * acc);
           if (a.dbg) atomicAdd(a.dbg + 5, 1ull);  // tiles
           if (++acc == 2) {
             acc = 0;
             acc_phase ^= 1;
           }
         }
-        if (!STREAM_A) tc_commit(bar_a_empty);
+        if (!STREAM_A) {
+          if (PAIR) tc_commit_pair(bar_a_empty);
+          else tc_commit(bar_a_empty);
+        }
       }
     }
   } else {
-    // ===== epilogue: kEpiWarps warps, thread = one query row x 128 of the tile's columns =====
-    // ncu (round 1, source counters): a third of all samples sat in the MMA issuer's wait for a drained accumulator
-    // and 17 % in the candidate flush (an atomicAdd round trip with the accumulator still held).  Hence:
-    //  * the whole 128-column row is read into registers at once (4 x tcgen05.ld, one wait) and the accumulator is
-    //    handed back to the tensor pipe BEFORE any key is looked at;
-    //  * a flush is split: the atomicAdd that reserves the slots is issued when a ring half fills or the item ends,
-    //    its result is consumed one flush later (double-buffered ring), so nobody waits for the round trip.
-    const uint32_t quarter = warp & 3;               // TMEM lane quarter this warp may read
+    // ===== epilogue: kEpiWarps warps; warp = one TMEM lane quarter (32 query rows) x kEpiCols of the tile's columns =====
+    const uint32_t ew = warp - 2;                    // index among the epilogue warps
+    const uint32_t quarter = warp & 3;               // TMEM lane quarter this warp may read (= warp id % 4)
     const uint32_t row = quarter * 32 + lane;
+    const uint32_t cslice = (ew >> 2) * kEpiCols;    // first tile column of this warp's slice
     const uint32_t et = threadIdx.x - 64;            // index among the epilogue threads
-    const uint32_t chalf = (warp - 2) >> 2;          // which 128 columns of the tile this warp reads (0 when kTileN == 128)
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    float* my_key = wq_key + ew * kWq;
+    uint32_t* my_id = wq_id + ew * kWq;
+    uint32_t* my_lane = wq_lane + ew * kWq;
+    const uint32_t t_empty_dst = PAIR ? mapa_u32(bar_t_empty, 0) : bar_t_empty;  // the leader's barrier
     uint32_t acc = 0, acc_phase = 0;
-    uint32_t half = 0, n_pend = 0;                   // ring half being filled, entries in it
-    uint32_t p_pos = 0, p_n = 0, p_q = 0;            // reserved-but-unwritten flush of the other half
-    auto flush_end = [&]() {                         // write the other half out (its reservation has long arrived)
-      const uint32_t base = (half ^ 1) * kRing;
-      for (uint32_t i = 0; i < p_n; ++i) {
-        if (p_pos + i < a.cap) {
-          a.cand_id[(size_t)p_q * a.cap + p_pos + i] = ring_col[(base + i) * kEpiThreads + et];
-          a.cand_key[(size_t)p_q * a.cap + p_pos + i] = ring_key[(base + i) * kEpiThreads + et];
-        } else {
-          a.qflags[p_q] = 1u;
-        }
-      }
-      p_n = 0;
+    uint32_t wq_n = 0;                               // entries in the warp's queue (warp-uniform)
+    uint32_t q_base = 0;                             // query of queue entry i = q_base + my_lane[i]
+    auto flush = [&]() {                             // whole warp: entry i is written out by lane i (and i + 32)
+      exact_wq_flush(a.cand_cnt, a.cand_id, a.cand_key, a.qflags, a.cap, my_key, my_id, my_lane, q_base, wq_n);
+      wq_n = 0;
     };
-    for (uint32_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+    for (uint32_t item = worker; item < a.n_items; item += n_workers) {
       const uint32_t qb = item % a.n_qblocks;
       const uint32_t t0 = a.tile_lo + (item / a.n_qblocks) * a.tiles_per_item;
       const uint32_t t1 = min(a.tile_hi, t0 + a.tiles_per_item);
-      const uint32_t q = qb * kTileM + row;
-      const bool q_ok = q < a.nq;
-      const float tau = q_ok ? a.thresh[q] : INFINITY;
-      auto flush_begin = [&]() {                     // reserve slots for the half just filled, switch halves
-        flush_end();
-        p_n = n_pend;
-        p_q = q;
-        p_pos = atomicAdd(a.cand_cnt + q, n_pend);
-        half ^= 1;
-        n_pend = 0;
-      };
+      q_base = qb * kQRows + rank * kTileM + quarter * 32;
+      const uint32_t q = q_base + lane;
+      const float tau = q < a.nq ? a.thresh[q] : INFINITY;  // rows past the batch never keep anything
       for (uint32_t t = t0; t < t1; ++t) {
-        if (BIAS) {  // stage this tile's per-column bias (L2: -|x|^2/2): kEpiThreads == kTileN, one column each
-          const uint64_t col = (uint64_t)t * kTileN + et;
-          s_bias[acc * kTileN + et] = col < a.n_vec ? a.col_bias[col] : 0.f;
+        if (BIAS) {  // stage this tile's per-column bias (L2: -|x|^2/2)
+          if (et < kTileN) {
+            const uint64_t col = (uint64_t)t * kTileN + et;
+            s_bias[acc * kTileN + et] = col < a.n_vec ? a.col_bias[col] : 0.f;
+          }
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         }
         long long c6 = (a.dbg && et == 0) ? clock64() : 0;
@@ -485,21 +625,24 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
         long long c7 = (a.dbg && et == 0) ? clock64() : 0;
         tc_fence_after();
         const uint32_t n_valid = min(kTileN, a.n_vec - t * kTileN);  // columns past the corpus are zero rows
-        uint32_t v[4][32];
-        const uint32_t tcol = tmem_base + ((quarter * 32) << 16) + acc * kTileN + chalf * 128;
+        uint32_t v[kEpiCols / 32][32];
+        const uint32_t tcol = tmem_base + ((quarter * 32) << 16) + acc * kTileN + cslice;
 #pragma unroll
-        for (uint32_t cb = 0; cb < 4; ++cb) tmem_ld_32x32b_x32_nowait(tcol + cb * 32, v[cb]);
+        for (uint32_t cb = 0; cb < kEpiCols / 32; ++cb) tmem_ld_32x32b_x32_nowait(tcol + cb * 32, v[cb]);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_t_empty + 8 * acc);  // the tensor pipe may refill this accumulator now
-        const uint32_t bias_buf = acc * kTileN + chalf * 128;
+        if (lane == 0) {  // the tensor pipe may refill this accumulator now
+          if (PAIR) mbar_arrive_cluster(t_empty_dst + 8 * acc);
+          else mbar_arrive(t_empty_dst + 8 * acc);
+        }
+        const uint32_t bias_buf = acc * kTileN + cslice;
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
         }
 #pragma unroll
-        for (uint32_t cb = 0; cb < 4; ++cb) {
+        for (uint32_t cb = 0; cb < kEpiCols / 32; ++cb) {
           if (BIAS) {
             const float4* b4 = reinterpret_cast<const float4*>(s_bias + bias_buf + cb * 32);
 #pragma unroll
@@ -511,50 +654,31 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
               v[cb][j + 3] = __float_as_uint(__uint_as_float(v[cb][j + 3]) + b.w);
             }
           }
-          // a key that reaches the running threshold is rare once the first slices have been seen: one
-          // max-tree over the 32 keys, then the per-key test only when something can pass
-          float mx[16];
+          // a key that reaches the running threshold is rare once the first slices have been seen
+          float g[4];
 #pragma unroll
-          for (uint32_t j = 0; j < 16; ++j) mx[j] = fmaxf(__uint_as_float(v[cb][2 * j]), __uint_as_float(v[cb][2 * j + 1]));
+          for (uint32_t gi = 0; gi < 4; ++gi) g[gi] = max8(&v[cb][8 * gi]);
+          const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+          if (__any_sync(kFullMask, m >= tau)) {
 #pragma unroll
-          for (uint32_t w = 8; w >= 1; w >>= 1)
+            for (uint32_t gi = 0; gi < 4; ++gi) {
+              if (__any_sync(kFullMask, g[gi] >= tau)) {
 #pragma unroll
-            for (uint32_t j = 0; j < w; ++j) mx[j] = fmaxf(mx[j], mx[j + w]);
-          if (mx[0] >= tau) {
-            // rare: count first, make room once, then predicated pushes — no call inside the unrolled loop, so
-            // the hot path (above) stays a few hundred instructions
-            const uint32_t c0 = chalf * 128 + cb * 32;  // first tile column of this 32-column block
-            const uint32_t lim = n_valid > c0 ? min(32u, n_valid - c0) : 0u;
-            uint32_t cnt = 0;
-#pragma unroll
-            for (uint32_t j = 0; j < 32; ++j) cnt += (__uint_as_float(v[cb][j]) >= tau && j < lim) ? 1u : 0u;
-            if (cnt > kRing) {
-              // more keys than a ring half holds (the first slices, where everything passes): reserve directly
-              if (n_pend) flush_begin();
-              const uint32_t pos = atomicAdd(a.cand_cnt + q, cnt);
-              uint32_t o = pos;
-#pragma unroll
-              for (uint32_t j = 0; j < 32; ++j) {
-                const float key = __uint_as_float(v[cb][j]);
-                if (key >= tau && j < lim) {
-                  if (o < a.cap) {
-                    a.cand_id[(size_t)q * a.cap + o] = t * kTileN + c0 + j;
-                    a.cand_key[(size_t)q * a.cap + o] = key;
-                  } else {
-                    a.qflags[q] = 1u;
+                for (uint32_t j = 0; j < 8; ++j) {
+                  const uint32_t col = cslice + cb * 32 + gi * 8 + j;  // tile column
+                  const float key = __uint_as_float(v[cb][gi * 8 + j]);
+                  const bool hit = key >= tau && col < n_valid;
+                  const uint32_t b = __ballot_sync(kFullMask, hit);
+                  if (b) {
+                    if (hit) {
+                      const uint32_t slot = wq_n + __popc(b & lt_mask);
+                      my_key[slot] = key;
+                      my_id[slot] = t * kTileN + col;
+                      my_lane[slot] = lane;
+                    }
+                    wq_n += __popc(b);
+                    if (wq_n > 32) flush();
                   }
-                  ++o;
-                }
-              }
-            } else if (cnt) {
-              if (n_pend + cnt > kRing) flush_begin();
-#pragma unroll
-              for (uint32_t j = 0; j < 32; ++j) {
-                const float key = __uint_as_float(v[cb][j]);
-                if (key >= tau && j < lim) {
-                  ring_key[(half * kRing + n_pend) * kEpiThreads + et] = key;
-                  ring_col[(half * kRing + n_pend) * kEpiThreads + et] = t * kTileN + c0 + j;
-                  ++n_pend;
                 }
               }
             }
@@ -565,18 +689,35 @@ exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
           atomicAdd(a.dbg + 7, (unsigned long long)(clock64() - c7));
         }
       }
-      if (n_pend) flush_begin();  // the ring belongs to query q: reserve now, write during the next item
+      if (wq_n) flush();  // the queue's entries are relative to this item's query block
     }
-    flush_end();
   }
 
   if (a.dbg && threadIdx.x == 0) atomicAdd(a.dbg + 8, (unsigned long long)clock64() - k_t0);
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if (PAIR) cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the other can still touch it
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * kTileN) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * kTileN) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * kTileN) : "memory");
   }
+}
+
+template <bool BIAS, bool STREAM_A>
+__global__ void __launch_bounds__(kExactThreads, 1)
+exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
+                         const ExactArgs a) {
+  exact_gemm_filter_body<BIAS, STREAM_A, false>(&map_q, &map_x, a);
+}
+
+// the two-CTA form: clusters of 2 CTAs (one TPC), grid = 2 x the number of pairs
+template <bool BIAS, bool STREAM_A>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kExactThreads, 1)
+exact_gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
+                              const ExactArgs a) {
+  exact_gemm_filter_body<BIAS, STREAM_A, true>(&map_q, &map_x, a);
 }
 
 // ------------------------------------------------------------------------------------------------
