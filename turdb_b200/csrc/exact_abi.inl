@@ -335,7 +335,6 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
     set_smem(exact_gemm_filter_pair_kernel<false, false>, (size_t)idx->max_smem_optin);
     set_smem(exact_gemm_filter_pair_kernel<true, true>, (size_t)idx->max_smem_optin);
     set_smem(exact_gemm_filter_pair_kernel<false, true>, (size_t)idx->max_smem_optin);
-    set_smem(exact_threshold_kernel, (size_t)16384 * 8);
   }
   if (e != cudaSuccess) return bail(fail(TURDB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)));
 
@@ -365,6 +364,12 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
     n_workers = (uint32_t)std::min<int>(max_clusters, idx->num_sms / 2);
   }
 
+  // Slice growth g: with the threshold frozen at the kprime-th best of the m rows seen so far, the next (g - 1) m rows bring
+  // about (g - 1) kprime arrivals per query.  Measured at 1M x 384, kprime 40 (profiles/r02_exact_growth.json): g = 4
+  // 8.4 ms, 8: 9.0, 13: 9.6, 16: 10.2 — arrivals cost more than passes.  TURDB_EXACT_GROWTH overrides it (measurement).
+  uint32_t growth = 4, diag = 0;
+  if (const char* ev = getenv("TURDB_EXACT_GROWTH")) growth = (uint32_t)std::max(2, atoi(ev));
+  if (const char* ev = getenv("TURDB_EXACT_DIAG")) diag = (uint32_t)atoi(ev);
   const uint32_t n_tiles = (uint32_t)((n + kTileN - 1) / kTileN);
   const uint32_t q_rows = pair ? 2 * kTileM : kTileM;  // queries per work item
   const uint32_t n_qblocks = (nq + q_rows - 1) / q_rows;
@@ -394,6 +399,7 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
     a.cap = cap;
     a.qflags = d_qflags;
     a.dbg = idx->d_dbg;
+    a.diag = diag;
     const uint32_t grid = std::min<uint32_t>(a.n_items, n_workers) * (pair ? 2u : 1u);
     if (pair) {  // __cluster_dims__(2, 1, 1) on the kernel: the grid is a multiple of 2
       if (metric == kL2) {
@@ -410,12 +416,13 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
       if (stream_a) exact_gemm_filter_kernel<false, true><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
       else exact_gemm_filter_kernel<false, false><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
     }
-    exact_threshold_kernel<<<nq, 256, cap * 8, stream>>>(nq, kprime, cap, d_cnt, d_cid, d_ckey, d_th, d_slack, d_kept, d_qflags,
+    exact_threshold_kernel<<<(nq + kThreshWarps - 1) / kThreshWarps, 32 * kThreshWarps, 0, stream>>>(nq, kprime, cap, d_cnt, d_cid, d_ckey, d_th, d_slack, d_kept, d_qflags,
                                                          d_arch_cnt, d_arch_id, arch_cap);
     e = cudaGetLastError();
     if (e != cudaSuccess) return bail(fail(TURDB_ERR_CUDA, "exact pass launch failed: %s", cudaGetErrorString(e)));
     lo = hi;
-    span = hi * 3;  // the next slice is 3x everything seen so far: ~ln(4) * kprime arrivals per query plus the slack band
+    span = hi * (growth - 1);  // the next slice is (growth - 1) x everything seen so far: ~ln(growth) * kprime arrivals per
+                               // query plus the slack band
   }
   out->scr = scr;
   out->cand_cnt = d_cnt;

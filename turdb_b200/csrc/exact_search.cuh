@@ -335,6 +335,8 @@ struct ExactArgs {
   uint32_t cap;
   uint32_t* qflags;               // [nq] bit 0: this query lost a candidate (buffer full) -> redone by the streaming scan
   unsigned long long* dbg;  // optional [16] cycle counters (diagnostics)
+  uint32_t diag;            // measurement only (TURDB_EXACT_DIAG; results are WRONG when set): 1 = the epilogue never reads
+                            // TMEM, 2 = it reads the accumulator but looks at nothing
 };
 
 // ---- two-CTA (cta_group::2) helpers ----
@@ -627,9 +629,16 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
         const uint32_t n_valid = min(kTileN, a.n_vec - t * kTileN);  // columns past the corpus are zero rows
         uint32_t v[kEpiCols / 32][32];
         const uint32_t tcol = tmem_base + ((quarter * 32) << 16) + acc * kTileN + cslice;
+        if (a.diag != 1) {
 #pragma unroll
-        for (uint32_t cb = 0; cb < kEpiCols / 32; ++cb) tmem_ld_32x32b_x32_nowait(tcol + cb * 32, v[cb]);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          for (uint32_t cb = 0; cb < kEpiCols / 32; ++cb) tmem_ld_32x32b_x32_nowait(tcol + cb * 32, v[cb]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+          for (uint32_t cb = 0; cb < kEpiCols / 32; ++cb)
+#pragma unroll
+            for (uint32_t j = 0; j < 32; ++j) v[cb][j] = 0xff800000u;  // -inf: nothing passes
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {  // the tensor pipe may refill this accumulator now
@@ -641,6 +650,7 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
           acc = 0;
           acc_phase ^= 1;
         }
+        if (a.diag == 2) continue;
 #pragma unroll
         for (uint32_t cb = 0; cb < kEpiCols / 32; ++cb) {
           if (BIAS) {
@@ -723,83 +733,139 @@ exact_gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const _
 // ------------------------------------------------------------------------------------------------
 // pass (2): per query, new threshold = (kprime-th best filter key so far) - slack; keep every key above it
 // ------------------------------------------------------------------------------------------------
-// One CTA per query; bitonic sort (descending key, ascending id on ties) of the query's buffer in shared memory.
-// The buffer holds [0, kept[q]) = what the previous call kept, then this slice's arrivals.  With `arch_id` the
-// arrivals are first appended to the query's archive (ids only, never pruned): the union of all arrivals is a superset
-// of the rows a sequential scan would ever have pushed into its top-K heap (sql_topk.inl replays exactly that).
-// A query whose buffer or archive overflowed is flagged (qflags[q]) and redone by the streaming scan.
-__global__ void __launch_bounds__(256) exact_threshold_kernel(uint32_t nq, uint32_t kprime, uint32_t cap,
-                                                              uint32_t* cand_cnt, uint32_t* cand_id, float* cand_key,
-                                                              float* thresh, const float* __restrict__ slack,
-                                                              uint32_t* kept, uint32_t* qflags, uint32_t* arch_cnt,
-                                                              uint32_t* arch_id, uint32_t arch_cap) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  float* sk = reinterpret_cast<float*>(smem_raw);
-  uint32_t* si = reinterpret_cast<uint32_t*>(sk + cap);
-  __shared__ uint32_t s_keep;
-  const uint32_t q = blockIdx.x;
-  if (q >= nq) return;
+// One WARP per query, no block barriers.  The buffer holds [0, kept[q]) = what the previous call kept, then this slice's
+// arrivals.  The kprime-th best key is found by a 4-digit radix select over the order-preserving integer image of the
+// keys (one 256-bin histogram per warp in shared memory, votes aggregated with match.any so that keys sharing an
+// exponent byte cost one atomic); everything at or above tau' = that key - 2 e(q) is compacted to the front of the
+// buffer in place (stable: a ballot per 32 entries).  (The first version sorted the whole buffer with a bitonic network in
+// shared memory, 45 block barriers for 512 entries: 0.13-0.55 ms per pass for 10k queries; nothing downstream needs
+// the order — the rerank sorts by FP32 distance, the SQL operator replays the archive.)
+// With `arch_id` the arrivals are first appended to the query's archive (ids only, never pruned): the union of all
+// arrivals is a superset of the rows a sequential scan would ever have pushed into its top-K heap (sql_topk.inl replays
+// exactly that).  A query whose buffer or archive overflowed is flagged (qflags[q]) and redone by the streaming scan.
+__device__ __forceinline__ uint32_t key_to_ordered(float f) {  // larger key <=> larger integer
+  const uint32_t b = __float_as_uint(f);
+  return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_key(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
+}
+constexpr uint32_t kThreshWarps = 4;
+__global__ void __launch_bounds__(32 * kThreshWarps) exact_threshold_kernel(uint32_t nq, uint32_t kprime, uint32_t cap,
+                                                                            uint32_t* cand_cnt, uint32_t* cand_id, float* cand_key,
+                                                                            float* thresh, const float* __restrict__ slack,
+                                                                            uint32_t* kept, uint32_t* qflags, uint32_t* arch_cnt,
+                                                                            uint32_t* arch_id, uint32_t arch_cap) {
+  __shared__ uint32_t hist[kThreshWarps][256];
+  const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t q = blockIdx.x * kThreshWarps + w;
+  if (q >= nq) return;  // whole warps leave; nothing below synchronises across warps
+  uint32_t* h = hist[w];
+  const uint32_t lt_mask = (1u << lane) - 1u;
   const uint32_t raw_cnt = cand_cnt[q];
   const uint32_t cnt = min(raw_cnt, cap);
   const uint32_t prev = min(kept[q], cnt);
-  if (raw_cnt > cap && threadIdx.x == 0) qflags[q] = 1u;
-  const uint32_t arch_base = arch_id ? arch_cnt[q] : 0u;  // read by every thread; rewritten only after the barrier below
+  bool flag = raw_cnt > cap;
+  float* keys = cand_key + (size_t)q * cap;
+  uint32_t* ids = cand_id + (size_t)q * cap;
   if (arch_id) {
-    const uint32_t n_new = cnt - prev;
-    for (uint32_t i = threadIdx.x; i < n_new; i += blockDim.x) {
-      if (arch_base + i < arch_cap) arch_id[(size_t)q * arch_cap + arch_base + i] = cand_id[(size_t)q * cap + prev + i];
-    }
+    const uint32_t base = arch_cnt[q], n_new = cnt - prev;
+    for (uint32_t i = lane; i < n_new; i += 32)
+      if (base + i < arch_cap) arch_id[(size_t)q * arch_cap + base + i] = ids[prev + i];
+    __syncwarp();
+    if (lane == 0) arch_cnt[q] = min(base + n_new, arch_cap);
+    if (base + n_new > arch_cap) flag = true;
   }
-  uint32_t n2 = 1;
-  while (n2 < cnt) n2 <<= 1;
-  for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) {
-    sk[i] = i < cnt ? cand_key[(size_t)q * cap + i] : -INFINITY;
-    si[i] = i < cnt ? cand_id[(size_t)q * cap + i] : 0xFFFFFFFFu;
-  }
-  if (threadIdx.x == 0) s_keep = 0;
-  __syncthreads();
-  if (arch_id && threadIdx.x == 0) {
-    const uint32_t n_new = cnt - prev;
-    arch_cnt[q] = min(arch_base + n_new, arch_cap);
-    if (arch_base + n_new > arch_cap) qflags[q] = 1u;
-  }
-  for (uint32_t size = 2; size <= n2; size <<= 1) {
-    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-      for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) {
-        const uint32_t j = i ^ stride;
-        if (j > i) {
-          const bool desc = (i & size) == 0;  // first half of each block sorted "better first"
-          const float ki = sk[i], kj = sk[j];
-          const uint32_t ii = si[i], ij = si[j];
-          const bool i_better = ki > kj || (ki == kj && ii < ij);
-          if (i_better != desc) {
-            sk[i] = kj; sk[j] = ki;
-            si[i] = ij; si[j] = ii;
-          }
+  float tau = -INFINITY;
+  if (kprime > 0 && cnt >= kprime) {
+    uint32_t prefix = 0, remaining = kprime;  // the remaining-th largest among the keys whose high digits equal prefix
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      for (uint32_t i = lane; i < 256; i += 32) h[i] = 0;
+      __syncwarp();
+      const uint32_t hi_mask = shift == 24 ? 0u : (0xFFFFFFFFu << (shift + 8));
+      for (uint32_t base = 0; base < cnt; base += 32) {
+        const uint32_t i = base + lane;
+        bool ok = i < cnt;
+        uint32_t u = 0;
+        if (ok) {
+          u = key_to_ordered(keys[i]);
+          ok = (u & hi_mask) == prefix;
+        }
+        const uint32_t digit = (u >> shift) & 255u;
+        const uint32_t active = __ballot_sync(kFullMask, ok);
+        if (ok) {
+          const uint32_t peers = __match_any_sync(active, digit);
+          if ((uint32_t)(__ffs(peers) - 1) == lane) atomicAdd(&h[digit], (uint32_t)__popc(peers));
         }
       }
-      __syncthreads();
+      __syncwarp();
+      // lane l owns the 8 bins 255 - 8l ... 248 - 8l (lane 0 = the largest digits); prefix sums run from the top
+      uint32_t b[8], mine = 0;
+#pragma unroll
+      for (uint32_t j = 0; j < 8; ++j) {
+        b[j] = h[255 - (8 * lane + j)];
+        mine += b[j];
+      }
+      uint32_t incl = mine;
+#pragma unroll
+      for (uint32_t off = 1; off < 32; off <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFullMask, incl, off);
+        if (lane >= off) incl += t;
+      }
+      const uint32_t excl = incl - mine;
+      const bool here = excl < remaining && remaining <= incl;  // exactly one lane (the matching keys number >= remaining)
+      uint32_t f_digit = 0, f_rem = 0, c = excl;
+      bool done = false;
+#pragma unroll
+      for (uint32_t j = 0; j < 8; ++j) {
+        if (here && !done && c + b[j] >= remaining) {
+          f_digit = 255 - (8 * lane + j);
+          f_rem = remaining - c;
+          done = true;
+        }
+        c += b[j];
+      }
+      const uint32_t src = (uint32_t)__ffs(__ballot_sync(kFullMask, here)) - 1u;
+      f_digit = __shfl_sync(kFullMask, f_digit, src & 31u);
+      remaining = __shfl_sync(kFullMask, f_rem, src & 31u);
+      prefix |= f_digit << shift;
+      __syncwarp();
     }
+    // tau' = kprime-th best key - 2 e(q); everything at or above it stays (>= kprime entries)
+    tau = ordered_to_key(prefix) - (slack ? slack[q] : 0.f);
   }
-  // tau' = kprime-th best key - 2 e(q); everything at or above it stays (>= kprime entries)
-  const float tau = cnt >= kprime ? sk[kprime - 1] - (slack ? slack[q] : 0.f) : -INFINITY;
-  uint32_t mine = 0;
-  for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) mine += (sk[i] >= tau) ? 1u : 0u;
-  if (mine) atomicAdd(&s_keep, mine);
-  __syncthreads();
-  uint32_t keep = s_keep;  // a prefix of the sorted buffer
-  if (keep > cap / 2) {    // no room left for the next slice's arrivals: give the query to the streaming scan
+  uint32_t keep = 0;
+  for (uint32_t base = 0; base < cnt; base += 32) {
+    const uint32_t i = base + lane;
+    float kf = 0.f;
+    uint32_t id = 0;
+    bool ok = false;
+    if (i < cnt) {
+      kf = keys[i];
+      id = ids[i];
+      ok = kf >= tau;
+    }
+    const uint32_t bal = __ballot_sync(kFullMask, ok);
+    __syncwarp();  // every lane has read its entry before any lane overwrites one (targets are <= own index)
+    if (ok) {
+      const uint32_t pos = keep + __popc(bal & lt_mask);
+      if (pos < cap / 2) {
+        keys[pos] = kf;
+        ids[pos] = id;
+      }
+    }
+    keep += __popc(bal);
+    __syncwarp();
+  }
+  if (keep > cap / 2) {  // no room left for the next slice's arrivals: give the query to the streaming scan
     keep = cap / 2;
-    if (threadIdx.x == 0) qflags[q] = 1u;
+    flag = true;
   }
-  for (uint32_t i = threadIdx.x; i < keep; i += blockDim.x) {
-    cand_key[(size_t)q * cap + i] = sk[i];
-    cand_id[(size_t)q * cap + i] = si[i];
-  }
-  if (threadIdx.x == 0) {
+  if (lane == 0) {
     cand_cnt[q] = keep;
     kept[q] = keep;
     thresh[q] = tau;
+    if (flag) qflags[q] = 1u;
   }
 }
 
