@@ -470,11 +470,11 @@ def main():
     e_dd = torch.empty((nq, k), dtype=torch.float32, device=dev)
     e_nodes = torch.empty((nq, k), dtype=torch.int32, device=dev)
     e_cnt = torch.empty(nq, dtype=torch.int32, device=dev)
-    idx.bruteforce_topk_device(dq[0].data_ptr(), nq, k, DistanceFunction.Cosine, 4, e_rows.data_ptr(), e_dd.data_ptr(),
+    idx.bruteforce_topk_device(dq[0].data_ptr(), nq, k, DistanceFunction.Cosine, 0, e_rows.data_ptr(), e_dd.data_ptr(),
                                e_cnt.data_ptr(), e_nodes.data_ptr(), stream)
     torch.cuda.synchronize()
     t_ex = time.perf_counter()
-    idx.bruteforce_topk_device(dq[0].data_ptr(), nq, k, DistanceFunction.Cosine, 4, e_rows.data_ptr(), e_dd.data_ptr(),
+    idx.bruteforce_topk_device(dq[0].data_ptr(), nq, k, DistanceFunction.Cosine, 0, e_rows.data_ptr(), e_dd.data_ptr(),
                                e_cnt.data_ptr(), e_nodes.data_ptr(), stream)
     torch.cuda.synchronize()
     exact_ms = (time.perf_counter() - t_ex) * 1e3

@@ -218,8 +218,8 @@ int32_t turdb_cuda_index_gather_probe(turdb_cuda_index* idx, uint32_t ctas_per_s
  * twice a bound on the BF16 score error (from the operands' actual rounding-error norms), so no row of the exact
  * FP32 top-k can be lost; a query whose candidate buffer overflows is redone by a plain FP32 scan kernel.
  * Result = top-k by (FP32 distance, node id).  Distances follow the HNSW metric contract above (squared L2 /
- * 1-cos / -dot), NOT the SQL sqrt form.  k <= TURDB_EXACT_MAX_K; rerank_factor 0 = 4; k*rerank_factor is clamped
- * to 2048.  Absent vectors (+inf rows) evaluate to +inf.
+ * 1-cos / -dot), NOT the SQL sqrt form.  k <= TURDB_EXACT_MAX_K; rerank_factor 0 = 1 (the band already certifies k' = k; a larger factor only
+ * widens the working set — 6.5 ms against 7.4 ms per 10k queries x 1M x 384 at factor 4); k*rerank_factor is clamped to 2048.  Absent vectors (+inf rows) evaluate to +inf.
  */
 int32_t turdb_cuda_bruteforce_topk(turdb_cuda_index* idx, const float* queries, uint32_t query_dim,
                                    uint32_t nq, uint32_t k, uint8_t metric, uint32_t rerank_factor,

@@ -18,7 +18,7 @@ ap.add_argument("--nq", type=int, default=10_000)
 ap.add_argument("--k", type=int, default=10)
 ap.add_argument("--metric", type=int, default=0)
 ap.add_argument("--gen", default="sift_like")
-ap.add_argument("--rerank", type=int, default=4)
+ap.add_argument("--rerank", type=int, default=0)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--debug", action="store_true")
 ap.add_argument("--out", default="gpurun_out/exact_probe.json")

@@ -195,11 +195,11 @@ static bool make_bf16_map(CUtensorMap* map, const void* base, uint64_t rows, uin
 }
 
 __global__ void exact_init_kernel(float* thresh, uint32_t* cand_cnt, uint32_t* kept, uint32_t* qflags, uint32_t* arch_cnt,
-                                  uint32_t nq) {
+                                  uint32_t nq, uint32_t first_cnt) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nq) {
     thresh[i] = -INFINITY;
-    cand_cnt[i] = 0;
+    cand_cnt[i] = first_cnt;  // the first slice is written densely (ExactArgs::dense): its column count
     kept[i] = 0;
     qflags[i] = 0;
     if (arch_cnt) arch_cnt[i] = 0;
@@ -296,7 +296,9 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
     const uint64_t total = (uint64_t)nq * kp;
     to_half_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_queries, dim, dim, kp, nq, nullptr, fp16, d_qb);
     if (metric == kL2) col_bias_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(idx->d_norm2, n, d_bias);
-    exact_init_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(d_th, d_cnt, d_kept, d_qflags, d_arch_cnt, nq);
+    const uint32_t first_tiles = std::max(1u, std::min(first_rows, cap / 2) / kTileN);
+    const uint32_t first_cnt = (uint32_t)std::min<uint64_t>(n, (uint64_t)first_tiles * kTileN);
+    exact_init_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(d_th, d_cnt, d_kept, d_qflags, d_arch_cnt, nq, first_cnt);
     // diagnostic only (measuring what the certificate costs): TURDB_EXACT_SLACK_SCALE=0 turns the slack band off, which
     // makes the filter the uncertified heuristic of round 1
     float slack_scale = 1.0f;
@@ -367,7 +369,8 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
   // Slice growth g: with the threshold frozen at the kprime-th best of the m rows seen so far, the next (g - 1) m rows bring
   // about (g - 1) kprime arrivals per query.  Measured at 1M x 384, kprime 40 (profiles/r02_exact_growth.json): g = 4
   // 8.4 ms, 8: 9.0, 13: 9.6, 16: 10.2 — arrivals cost more than passes.  TURDB_EXACT_GROWTH overrides it (measurement).
-  uint32_t growth = 4, diag = 0;
+  // With the radix-select threshold kernel a pass is cheap: g = 2: 6.60 ms, g = 3: 6.52 ms (kprime = k = 10).
+  uint32_t growth = 3, diag = 0;
   if (const char* ev = getenv("TURDB_EXACT_GROWTH")) growth = (uint32_t)std::max(2, atoi(ev));
   if (const char* ev = getenv("TURDB_EXACT_DIAG")) diag = (uint32_t)atoi(ev);
   const uint32_t n_tiles = (uint32_t)((n + kTileN - 1) / kTileN);
@@ -387,7 +390,10 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
     a.tile_lo = lo;
     a.tile_hi = hi;
     const uint32_t tiles = hi - lo;
-    uint32_t tpi = (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(1, ((uint64_t)tiles * n_qblocks) / (4ull * n_workers)));
+    // tiles per work item: the resident query block is reloaded once per item (a ~1.5 us bubble), so short-K tiles get
+    // longer items; never fewer than ~4 items per worker and pass
+    const uint32_t tpi_cap = 16u * std::max(1u, 6u / k_chunks);
+    uint32_t tpi = (uint32_t)std::min<uint64_t>(tpi_cap, std::max<uint64_t>(1, ((uint64_t)tiles * n_qblocks) / (4ull * n_workers)));
     a.tiles_per_item = tpi;
     a.n_qblocks = n_qblocks;
     a.n_items = n_qblocks * ((tiles + tpi - 1) / tpi);
@@ -400,6 +406,7 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
     a.qflags = d_qflags;
     a.dbg = idx->d_dbg;
     a.diag = diag;
+    a.dense = lo == 0 ? 1u : 0u;
     const uint32_t grid = std::min<uint32_t>(a.n_items, n_workers) * (pair ? 2u : 1u);
     if (pair) {  // __cluster_dims__(2, 1, 1) on the kernel: the grid is a multiple of 2
       if (metric == kL2) {
@@ -468,7 +475,7 @@ extern "C" int32_t turdb_cuda_bruteforce_topk_device(turdb_cuda_index* idx, cons
     return TURDB_OK;
   }
   if (k > TURDB_EXACT_MAX_K) return fail(TURDB_ERR_UNSUPPORTED, "bruteforce_topk: k = %u > %u", k, TURDB_EXACT_MAX_K);
-  if (!rerank_factor) rerank_factor = 4;
+  if (!rerank_factor) rerank_factor = 1;  // the certified band makes k' = k sufficient; more only widens the working set
   // kprime >= k rows stay in the working set: the slack band around the kprime-th key is what makes the filter exact;
   // a larger kprime only makes the band's lower edge less sensitive to outliers
   const uint32_t kprime = (uint32_t)std::min<uint64_t>(std::min<uint64_t>((uint64_t)k * rerank_factor, 2048), n);

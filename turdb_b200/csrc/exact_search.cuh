@@ -335,6 +335,8 @@ struct ExactArgs {
   uint32_t cap;
   uint32_t* qflags;               // [nq] bit 0: this query lost a candidate (buffer full) -> redone by the streaming scan
   unsigned long long* dbg;  // optional [16] cycle counters (diagnostics)
+  uint32_t dense;           // first slice (every threshold is -inf): each key goes straight to its column's slot of the
+                            // query's buffer (position = column - first column of the slice); the host presets cand_cnt
   uint32_t diag;            // measurement only (TURDB_EXACT_DIAG; results are WRONG when set): 1 = the epilogue never reads
                             // TMEM, 2 = it reads the accumulator but looks at nothing
 };
@@ -614,13 +616,22 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
       q_base = qb * kQRows + rank * kTileM + quarter * 32;
       const uint32_t q = q_base + lane;
       const float tau = q < a.nq ? a.thresh[q] : INFINITY;  // rows past the batch never keep anything
+      // per-column bias (L2: -|x|^2/2), double-buffered with the accumulators: the tile's values are staged by the first
+      // kTileN epilogue threads one tile AHEAD (the global load is issued before the tile's accumulator is awaited and
+      // lands in shared memory after the tile has been looked at, so its latency is never waited for)
+      float bias_next = 0.f;
+      if (BIAS && et < kTileN && t0 < t1) {
+        const uint64_t col = (uint64_t)t0 * kTileN + et;
+        s_bias[acc * kTileN + et] = col < a.n_vec ? a.col_bias[col] : 0.f;
+      }
       for (uint32_t t = t0; t < t1; ++t) {
-        if (BIAS) {  // stage this tile's per-column bias (L2: -|x|^2/2)
-          if (et < kTileN) {
-            const uint64_t col = (uint64_t)t * kTileN + et;
-            s_bias[acc * kTileN + et] = col < a.n_vec ? a.col_bias[col] : 0.f;
-          }
+        if (BIAS) {
+          // this tile's bias is visible, and every warp is done with the previous tile (whose buffer is refilled below)
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+          if (et < kTileN && t + 1 < t1) {
+            const uint64_t col = (uint64_t)(t + 1) * kTileN + et;
+            bias_next = col < a.n_vec ? a.col_bias[col] : 0.f;
+          }
         }
         long long c6 = (a.dbg && et == 0) ? clock64() : 0;
         mbar_wait(bar_t_full + 8 * acc, acc_phase);
@@ -664,6 +675,31 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
               v[cb][j + 3] = __float_as_uint(__uint_as_float(v[cb][j + 3]) + b.w);
             }
           }
+          if (a.dense) {  // first slice: no test, no queue — 128-bit stores of the thread's 32 consecutive columns
+            if (q < a.nq) {
+              const uint32_t c0 = cslice + cb * 32;  // tile column of v[cb][0]
+              const size_t slot = (size_t)q * a.cap + (size_t)(t - a.tile_lo) * kTileN + c0;
+              float4* kd = reinterpret_cast<float4*>(a.cand_key + slot);
+              uint4* idd = reinterpret_cast<uint4*>(a.cand_id + slot);
+#pragma unroll
+              for (uint32_t j = 0; j < 32; j += 4) {
+                float4 kv;
+                kv.x = __uint_as_float(v[cb][j]);
+                kv.y = __uint_as_float(v[cb][j + 1]);
+                kv.z = __uint_as_float(v[cb][j + 2]);
+                kv.w = __uint_as_float(v[cb][j + 3]);
+                // a NaN score (0 x inf against an absent vector's +inf marker) must not win the selection
+                kv.x = kv.x == kv.x ? kv.x : -INFINITY;
+                kv.y = kv.y == kv.y ? kv.y : -INFINITY;
+                kv.z = kv.z == kv.z ? kv.z : -INFINITY;
+                kv.w = kv.w == kv.w ? kv.w : -INFINITY;
+                kd[j >> 2] = kv;
+                const uint32_t id0 = t * kTileN + c0 + j;
+                idd[j >> 2] = make_uint4(id0, id0 + 1, id0 + 2, id0 + 3);
+              }
+            }
+            continue;
+          }
           // a key that reaches the running threshold is rare once the first slices have been seen
           float g[4];
 #pragma unroll
@@ -694,6 +730,7 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
             }
           }
         }
+        if (BIAS && et < kTileN && t + 1 < t1) s_bias[acc * kTileN + et] = bias_next;  // acc already names the next tile's buffer
         if (a.dbg && et == 0) {
           atomicAdd(a.dbg + 6, (unsigned long long)(c7 - c6));
           atomicAdd(a.dbg + 7, (unsigned long long)(clock64() - c7));

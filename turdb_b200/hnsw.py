@@ -287,7 +287,7 @@ class CudaHnswIndex:
                                                               d_rows, d_nodes or None, d_dist, d_counts, d_stats or None,
                                                               stream or None))
 
-    def bruteforce_topk(self, queries, k: int, metric: DistanceFunction | None = None, rerank_factor: int = 4):
+    def bruteforce_topk(self, queries, k: int, metric: DistanceFunction | None = None, rerank_factor: int = 0):
         """Exact path: ORDER BY <distance> LIMIT k over the whole arena (src/sql/executor.rs:2239-2392)."""
         q = np.ascontiguousarray(queries, dtype=np.float32)
         if q.ndim == 1:
