@@ -315,7 +315,7 @@ __host__ __device__ constexpr uint32_t exact_stage_bytes(bool stream_a, bool pai
 }
 // everything in dynamic shared memory except the pipeline stages (kernel and host compute the layout from this)
 __host__ __device__ constexpr uint32_t exact_fixed_smem(uint32_t k_chunks, bool stream_a) {
-  return (stream_a ? 0u : k_chunks * kChunkBytes) + 2 * kTileN * 4 + kEpiWarps * kWq * 12 + 32 * 8 + 16;
+  return (stream_a ? 0u : k_chunks * kChunkBytes) + kEpiWarps * 2 * kEpiCols * 4 + kEpiWarps * kWq * 12 + 32 * 8 + 16;
 }
 
 struct ExactArgs {
@@ -392,6 +392,15 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
   }
 }
 
+__device__ __forceinline__ bool elect_one() {  // true in exactly one lane of the (converged) warp
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ float max8(const uint32_t* v) {
   const float a = fmaxf(fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])), __uint_as_float(v[2]));
   const float b = fmaxf(fmaxf(__uint_as_float(v[3]), __uint_as_float(v[4])), __uint_as_float(v[5]));
@@ -418,7 +427,7 @@ __device__ __noinline__ void exact_wq_flush(uint32_t* cand_cnt, uint32_t* cand_i
   __syncwarp();
 }
 
-// smem: [A: k_chunks x 16 KB (resident form)][stages: n_stages x ([A chunk] B chunk)][col bias: 2 x kTileN float]
+// smem: [A: k_chunks x 16 KB (resident form)][stages: n_stages x ([A chunk] B chunk)][col bias: per warp 2 x kEpiCols float]
 //       [warp queues: key | id | lane][barriers][tmem ptr]
 template <bool BIAS, bool STREAM_A, bool PAIR>
 __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q, const CUtensorMap* map_x, const ExactArgs& a) {
@@ -433,8 +442,8 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
   uint8_t* sA = smem;
   uint8_t* sB = sA + (STREAM_A ? 0 : (size_t)a.k_chunks * kChunkBytes);
   const uint32_t kStages = a.n_stages;
-  float* s_bias = reinterpret_cast<float*>(sB + (size_t)kStages * stage_bytes);  // [2][kTileN]
-  float* wq_key = s_bias + 2 * kTileN;                                            // [kEpiWarps][kWq]
+  float* s_bias = reinterpret_cast<float*>(sB + (size_t)kStages * stage_bytes);  // [kEpiWarps][2][kEpiCols]
+  float* wq_key = s_bias + kEpiWarps * 2 * kEpiCols;                              // [kEpiWarps][kWq]
   uint32_t* wq_id = reinterpret_cast<uint32_t*>(wq_key + kEpiWarps * kWq);
   uint32_t* wq_lane = wq_id + kEpiWarps * kWq;
   uint64_t* bars = reinterpret_cast<uint64_t*>(wq_lane + kEpiWarps * kWq);
@@ -474,9 +483,14 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
   const uint32_t tmem_base = *tmem_slot;
   const unsigned long long k_t0 = a.dbg ? (unsigned long long)clock64() : 0ull;
 
+  // The two single-issuer roles run with the WHOLE warp converged (every lane evaluates the loop control and the waits,
+  // one elected lane issues): all addresses and descriptors are then warp-uniform, so the compiler keeps them in uniform
+  // registers — inside an `if (lane == 0)` region it had to broadcast every operand of every tcgen05.mma through an
+  // ELECT / R2UR / BRA.U.ANY loop (~16 instructions per MMA), which at K = 128 (8 MMAs per tile) made the issuer thread
+  // itself the pace of the tensor pipe.
   if (warp == 0) {
     // ===== TMA producer (in BOTH CTAs of a pair: own queries, own half of the vector tile) =====
-    if (lane == 0) {
+    {
       // completions are counted on the leader's barriers; only the leader arms them (with both CTAs' bytes)
       const uint32_t full_a = PAIR ? mapa_u32(bar_a_full, 0) : bar_a_full;
       const uint32_t full_b = PAIR ? mapa_u32(bar_b_full, 0) : bar_b_full;
@@ -490,12 +504,15 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
         if (!STREAM_A) {
           long long c0 = a.dbg ? clock64() : 0;
           mbar_wait(bar_a_empty, a_phase ^ 1);  // previous item's MMAs have drained A
-          if (a.dbg) atomicAdd(a.dbg + 0, (unsigned long long)(clock64() - c0));
-          if (rank == 0) mbar_expect_tx(bar_a_full, n_arm * a.k_chunks * kChunkBytes);
-          for (uint32_t kc = 0; kc < a.k_chunks; ++kc) {
-            if (PAIR) tma_load_2d_pair(smem_u32(sA + (size_t)kc * kChunkBytes), map_q, (int32_t)(kc * kChunkK), q_row0, full_a);
-            else tma_load_2d(smem_u32(sA + (size_t)kc * kChunkBytes), map_q, (int32_t)(kc * kChunkK), q_row0, full_a);
+          if (a.dbg && lane == 0) atomicAdd(a.dbg + 0, (unsigned long long)(clock64() - c0));
+          if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(bar_a_full, n_arm * a.k_chunks * kChunkBytes);
+            for (uint32_t kc = 0; kc < a.k_chunks; ++kc) {
+              if (PAIR) tma_load_2d_pair(smem_u32(sA + (size_t)kc * kChunkBytes), map_q, (int32_t)(kc * kChunkK), q_row0, full_a);
+              else tma_load_2d(smem_u32(sA + (size_t)kc * kChunkBytes), map_q, (int32_t)(kc * kChunkK), q_row0, full_a);
+            }
           }
+          __syncwarp();
           a_phase ^= 1;
         }
         for (uint32_t t = t0; t < t1; ++t) {
@@ -503,17 +520,20 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
           for (uint32_t kc = 0; kc < a.k_chunks; ++kc) {
             long long c1 = a.dbg ? clock64() : 0;
             mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
-            if (a.dbg) atomicAdd(a.dbg + 1, (unsigned long long)(clock64() - c1));
-            if (rank == 0) mbar_expect_tx(bar_b_full + 8 * stage, n_arm * stage_bytes);
-            const uint32_t dst = smem_u32(sB + (size_t)stage * stage_bytes);
-            if (PAIR) {
-              if (STREAM_A) tma_load_2d_pair(dst, map_q, (int32_t)(kc * kChunkK), q_row0, full_b + 8 * stage);
-              tma_load_2d_pair(dst + b_in_stage, map_x, (int32_t)(kc * kChunkK), x_row0, full_b + 8 * stage);
-            } else {
-              if (STREAM_A)  // the query block's chunk comes from L2 (it is 128 x K, re-read once per vector tile)
-                tma_load_2d(dst, map_q, (int32_t)(kc * kChunkK), q_row0, full_b + 8 * stage);
-              tma_load_2d(dst + b_in_stage, map_x, (int32_t)(kc * kChunkK), x_row0, full_b + 8 * stage);
+            if (a.dbg && lane == 0) atomicAdd(a.dbg + 1, (unsigned long long)(clock64() - c1));
+            if (elect_one()) {
+              if (rank == 0) mbar_expect_tx(bar_b_full + 8 * stage, n_arm * stage_bytes);
+              const uint32_t dst = smem_u32(sB + (size_t)stage * stage_bytes);
+              if (PAIR) {
+                if (STREAM_A) tma_load_2d_pair(dst, map_q, (int32_t)(kc * kChunkK), q_row0, full_b + 8 * stage);
+                tma_load_2d_pair(dst + b_in_stage, map_x, (int32_t)(kc * kChunkK), x_row0, full_b + 8 * stage);
+              } else {
+                if (STREAM_A)  // the query block's chunk comes from L2 (it is 128 x K, re-read once per vector tile)
+                  tma_load_2d(dst, map_q, (int32_t)(kc * kChunkK), q_row0, full_b + 8 * stage);
+                tma_load_2d(dst + b_in_stage, map_x, (int32_t)(kc * kChunkK), x_row0, full_b + 8 * stage);
+              }
             }
+            __syncwarp();
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
@@ -534,7 +554,7 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one elected lane; in a pair only the leader CTA's) =====
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       // instruction descriptor: D=F32, A=B=F16/BF16, both K-major, N, M (cute::UMMA::InstrDescriptor); M = 256 across a pair
       const uint32_t fmt = a.fp16 ? 0u : 1u;  // a_format (bits 7-9) / b_format (bits 10-12): 0 = F16, 1 = BF16
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((kTileN >> 3) << 17) | (((PAIR ? 2 * kTileM : kTileM) >> 4) << 24);
@@ -545,7 +565,7 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
         if (!STREAM_A) {
           long long c2 = a.dbg ? clock64() : 0;
           mbar_wait(bar_a_full, a_phase);
-          if (a.dbg) atomicAdd(a.dbg + 2, (unsigned long long)(clock64() - c2));
+          if (a.dbg && lane == 0) atomicAdd(a.dbg + 2, (unsigned long long)(clock64() - c2));
           a_phase ^= 1;
         }
         tc_fence_after();
@@ -553,40 +573,49 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
           long long c3 = a.dbg ? clock64() : 0;
           if (PAIR) mbar_wait_cluster(bar_t_empty + 8 * acc, acc_phase ^ 1);  // both CTAs' epilogues have drained it
           else mbar_wait(bar_t_empty + 8 * acc, acc_phase ^ 1);              // epilogue has drained this accumulator
-          if (a.dbg) atomicAdd(a.dbg + 3, (unsigned long long)(clock64() - c3));
+          if (a.dbg && lane == 0) atomicAdd(a.dbg + 3, (unsigned long long)(clock64() - c3));
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * kTileN;
           for (uint32_t kc = 0; kc < a.k_chunks; ++kc) {
             long long c4 = a.dbg ? clock64() : 0;
             mbar_wait(bar_b_full + 8 * stage, phase);
-            if (a.dbg) atomicAdd(a.dbg + 4, (unsigned long long)(clock64() - c4));
+            if (a.dbg && lane == 0) atomicAdd(a.dbg + 4, (unsigned long long)(clock64() - c4));
             tc_fence_after();
             const uint64_t da = umma_desc_sw128(STREAM_A ? smem_u32(sB + (size_t)stage * stage_bytes)
                                                            : smem_u32(sA + (size_t)kc * kChunkBytes));
             const uint64_t db = umma_desc_sw128(smem_u32(sB + (size_t)stage * stage_bytes + b_in_stage));
+            if (elect_one()) {
 #pragma unroll
-            for (uint32_t k4 = 0; k4 < kChunkK / 16; ++k4) {  // UMMA_K = 16 elements = 32 B inside the swizzle row
-              if (PAIR) tc_mma_pair(d_tmem, da + 2 * k4, db + 2 * k4, idesc, (kc | k4) != 0 ? 1u : 0u);
-              else tc_mma_bf16(d_tmem, da + 2 * k4, db + 2 * k4, idesc, (kc | k4) != 0 ? 1u : 0u);
+              for (uint32_t k4 = 0; k4 < kChunkK / 16; ++k4) {  // UMMA_K = 16 elements = 32 B inside the swizzle row
+                if (PAIR) tc_mma_pair(d_tmem, da + 2 * k4, db + 2 * k4, idesc, (kc | k4) != 0 ? 1u : 0u);
+                else tc_mma_bf16(d_tmem, da + 2 * k4, db + 2 * k4, idesc, (kc | k4) != 0 ? 1u : 0u);
+              }
+              if (PAIR) tc_commit_pair(bar_b_empty + 8 * stage);  // frees the stage (in both CTAs) when these MMAs retire
+              else tc_commit(bar_b_empty + 8 * stage);
             }
-            if (PAIR) tc_commit_pair(bar_b_empty + 8 * stage);  // frees the stage (in both CTAs) when these MMAs retire
-            else tc_commit(bar_b_empty + 8 * stage);
+            __syncwarp();
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
             }
           }
-          if (PAIR) tc_commit_pair(bar_t_full + 8 * acc);
-          else tc_commit(bar_t_full + 8 * acc);
-          if (a.dbg) atomicAdd(a.dbg + 5, 1ull);  // tiles
+          if (elect_one()) {
+            if (PAIR) tc_commit_pair(bar_t_full + 8 * acc);
+            else tc_commit(bar_t_full + 8 * acc);
+            if (a.dbg) atomicAdd(a.dbg + 5, 1ull);  // tiles
+          }
+          __syncwarp();
           if (++acc == 2) {
             acc = 0;
             acc_phase ^= 1;
           }
         }
         if (!STREAM_A) {
-          if (PAIR) tc_commit_pair(bar_a_empty);
-          else tc_commit(bar_a_empty);
+          if (elect_one()) {
+            if (PAIR) tc_commit_pair(bar_a_empty);
+            else tc_commit(bar_a_empty);
+          }
+          __syncwarp();
         }
       }
     }
@@ -616,21 +645,25 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
       q_base = qb * kQRows + rank * kTileM + quarter * 32;
       const uint32_t q = q_base + lane;
       const float tau = q < a.nq ? a.thresh[q] : INFINITY;  // rows past the batch never keep anything
-      // per-column bias (L2: -|x|^2/2), double-buffered with the accumulators: the tile's values are staged by the first
-      // kTileN epilogue threads one tile AHEAD (the global load is issued before the tile's accumulator is awaited and
-      // lands in shared memory after the tile has been looked at, so its latency is never waited for)
-      float bias_next = 0.f;
-      if (BIAS && et < kTileN && t0 < t1) {
-        const uint64_t col = (uint64_t)t0 * kTileN + et;
-        s_bias[acc * kTileN + et] = col < a.n_vec ? a.col_bias[col] : 0.f;
+      // per-column bias (L2: -|x|^2/2): every warp stages its OWN kEpiCols values (no CTA barrier couples the epilogue
+      // warps), double-buffered with the accumulators and one tile AHEAD — the global load is issued before the tile's
+      // accumulator is awaited and parked in shared memory after the tile has been looked at
+      float* my_bias = s_bias + ew * 2 * kEpiCols;
+      float bias_next[kEpiCols / 32];
+      if (BIAS && t0 < t1) {
+#pragma unroll
+        for (uint32_t i = 0; i < kEpiCols / 32; ++i) {
+          const uint64_t col = (uint64_t)t0 * kTileN + cslice + i * 32 + lane;
+          my_bias[acc * kEpiCols + i * 32 + lane] = col < a.n_vec ? a.col_bias[col] : 0.f;
+        }
+        __syncwarp();
       }
       for (uint32_t t = t0; t < t1; ++t) {
-        if (BIAS) {
-          // this tile's bias is visible, and every warp is done with the previous tile (whose buffer is refilled below)
-          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-          if (et < kTileN && t + 1 < t1) {
-            const uint64_t col = (uint64_t)(t + 1) * kTileN + et;
-            bias_next = col < a.n_vec ? a.col_bias[col] : 0.f;
+        if (BIAS && t + 1 < t1) {
+#pragma unroll
+          for (uint32_t i = 0; i < kEpiCols / 32; ++i) {
+            const uint64_t col = (uint64_t)(t + 1) * kTileN + cslice + i * 32 + lane;
+            bias_next[i] = col < a.n_vec ? a.col_bias[col] : 0.f;
           }
         }
         long long c6 = (a.dbg && et == 0) ? clock64() : 0;
@@ -656,7 +689,7 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
           if (PAIR) mbar_arrive_cluster(t_empty_dst + 8 * acc);
           else mbar_arrive(t_empty_dst + 8 * acc);
         }
-        const uint32_t bias_buf = acc * kTileN + cslice;
+        const uint32_t bias_buf = acc * kEpiCols;
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -665,7 +698,7 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
 #pragma unroll
         for (uint32_t cb = 0; cb < kEpiCols / 32; ++cb) {
           if (BIAS) {
-            const float4* b4 = reinterpret_cast<const float4*>(s_bias + bias_buf + cb * 32);
+            const float4* b4 = reinterpret_cast<const float4*>(my_bias + bias_buf + cb * 32);
 #pragma unroll
             for (uint32_t j = 0; j < 32; j += 4) {
               const float4 b = b4[j >> 2];
@@ -730,7 +763,11 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
             }
           }
         }
-        if (BIAS && et < kTileN && t + 1 < t1) s_bias[acc * kTileN + et] = bias_next;  // acc already names the next tile's buffer
+        if (BIAS && t + 1 < t1) {  // acc already names the next tile's buffer (last read two tiles ago, by this warp only)
+#pragma unroll
+          for (uint32_t i = 0; i < kEpiCols / 32; ++i) my_bias[acc * kEpiCols + i * 32 + lane] = bias_next[i];
+          __syncwarp();
+        }
         if (a.dbg && et == 0) {
           atomicAdd(a.dbg + 6, (unsigned long long)(c7 - c6));
           atomicAdd(a.dbg + 7, (unsigned long long)(clock64() - c7));
