@@ -158,10 +158,6 @@ extern "C" int32_t turdb_cuda_shards_search_batch(turdb_cuda_index* const* shard
   return rc;
 }
 
-#ifndef TURDB_EXACT_PAIR_DEFAULT
-#define TURDB_EXACT_PAIR_DEFAULT 0
-#endif
-
 // ---- TMA descriptors: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -309,19 +305,13 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
   }
   // Two-CTA form (tcgen05 cta_group::2, clusters of 2): each CTA of a pair stages half of every vector tile, so the L2 -> SM
   // traffic and the shared-memory fill per flop halve (exact_search.cuh).  TURDB_EXACT_PAIR=0/1 overrides the default.
-  int pair = TURDB_EXACT_PAIR_DEFAULT;
+  // Measured, 10k queries x 1M vectors (profiles/r02_exact_probe_final.json): the pair form wins where the tile is long
+  // enough for its cross-CTA synchronisation to disappear — 384-d 5.7 against 6.0 ms, 512-d 7.1 against 10.2 ms (a resident
+  // 128 KB query block leaves the one-CTA form two stages), 768-d 10.4 against 11.1 ms — and loses below: 256-d 4.6
+  // against 4.4 ms, 128-d 3.9 against 3.0 ms.
+  int pair = k_chunks >= 5 ? 1 : 0;
   if (const char* ev = getenv("TURDB_EXACT_PAIR")) pair = atoi(ev) != 0;
   if (idx->num_sms < 2) pair = 0;
-  CUtensorMap map_q, map_x;
-  if (!make_bf16_map(&map_q, d_qb, nq, kp, kTileM, fp16) || !make_bf16_map(&map_x, d_xb, n, kp, pair ? kTileN / 2 : kTileN, fp16))
-    return bail(fail(TURDB_ERR_CUDA, "cuTensorMapEncodeTiled failed"));
-
-  const size_t stage_bytes = exact_stage_bytes(stream_a != 0, pair != 0);
-  const size_t fixed_smem = exact_fixed_smem(k_chunks, stream_a != 0);
-  if ((size_t)idx->max_smem_optin < fixed_smem + 2 * stage_bytes)
-    return bail(fail(TURDB_ERR_UNSUPPORTED, "not enough shared memory for the exact path at dim %u", dim));
-  const uint32_t n_stages = (uint32_t)std::min<size_t>(kMaxStages, ((size_t)idx->max_smem_optin - fixed_smem) / stage_bytes);
-  const size_t gemm_smem = fixed_smem + (size_t)n_stages * stage_bytes;
   cudaError_t e = cudaSuccess;
   {
     static std::mutex attr_mu;  // cudaFuncSetAttribute is process-wide state
@@ -340,31 +330,54 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
   }
   if (e != cudaSuccess) return bail(fail(TURDB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)));
 
+  // shared-memory plan of one form: stage size, pipeline depth, total dynamic shared memory (0 stages = does not fit)
+  const size_t fixed_smem = exact_fixed_smem(k_chunks, stream_a != 0);
+  size_t stage_bytes = 0, gemm_smem = 0;
+  uint32_t n_stages = 0;
+  auto plan = [&](int as_pair) {
+    stage_bytes = exact_stage_bytes(stream_a != 0, as_pair != 0);
+    n_stages = (size_t)idx->max_smem_optin < fixed_smem + 2 * stage_bytes
+                   ? 0u
+                   : (uint32_t)std::min<size_t>(kMaxStages, ((size_t)idx->max_smem_optin - fixed_smem) / stage_bytes);
+    gemm_smem = fixed_smem + (size_t)n_stages * stage_bytes;
+  };
   // workers: CTAs, or CTA pairs (as many clusters of 2 as the device keeps resident at this shared-memory size)
   uint32_t n_workers = (uint32_t)idx->num_sms;
   if (pair) {
+    plan(1);
     int max_clusters = 0;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(idx->num_sms & ~1), 1, 1);
-    cfg.blockDim = dim3(kExactThreads, 1, 1);
-    cfg.dynamicSmemBytes = gemm_smem;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    cudaError_t oe = metric == kL2 ? (stream_a ? cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<true, true>, &cfg)
-                                               : cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<true, false>, &cfg))
-                                   : (stream_a ? cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<false, true>, &cfg)
-                                               : cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<false, false>, &cfg));
-    if (oe != cudaSuccess || max_clusters <= 0) {
-      cudaGetLastError();
-      max_clusters = idx->num_sms / 2;
+    if (n_stages) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)(idx->num_sms & ~1), 1, 1);
+      cfg.blockDim = dim3(kExactThreads, 1, 1);
+      cfg.dynamicSmemBytes = gemm_smem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      cudaError_t oe = metric == kL2 ? (stream_a ? cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<true, true>, &cfg)
+                                                 : cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<true, false>, &cfg))
+                                     : (stream_a ? cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<false, true>, &cfg)
+                                                 : cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<false, false>, &cfg));
+      if (oe != cudaSuccess) {
+        cudaGetLastError();
+        max_clusters = 0;
+      }
     }
-    n_workers = (uint32_t)std::min<int>(max_clusters, idx->num_sms / 2);
+    if (max_clusters > 0) n_workers = (uint32_t)std::min<int>(max_clusters, idx->num_sms / 2);
+    else pair = 0;  // no cluster of 2 fits here: one CTA per tile
   }
+  if (!pair) plan(0);
+  if (n_stages < 2) return bail(fail(TURDB_ERR_UNSUPPORTED, "not enough shared memory for the exact path at dim %u", dim));
+  if (getenv("TURDB_EXACT_VERBOSE"))
+    fprintf(stderr, "[turdb exact] form=%s workers=%u stages=%u smem=%zu k_chunks=%u stream_a=%u fp16=%d\n", pair ? "two-CTA" : "one-CTA",
+            n_workers, n_stages, gemm_smem, k_chunks, stream_a, fp16);
+  CUtensorMap map_q, map_x;
+  if (!make_bf16_map(&map_q, d_qb, nq, kp, kTileM, fp16) || !make_bf16_map(&map_x, d_xb, n, kp, pair ? kTileN / 2 : kTileN, fp16))
+    return bail(fail(TURDB_ERR_CUDA, "cuTensorMapEncodeTiled failed"));
 
   // Slice growth g: with the threshold frozen at the kprime-th best of the m rows seen so far, the next (g - 1) m rows bring
   // about (g - 1) kprime arrivals per query.  Measured at 1M x 384, kprime 40 (profiles/r02_exact_growth.json): g = 4
