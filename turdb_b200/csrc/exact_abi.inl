@@ -219,49 +219,70 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
                                 uint32_t* d_arch_id, uint32_t* d_qflags, ExactFilterResult* out, cudaStream_t stream) {
   const uint64_t n = idx->ix.n;
   const uint32_t dim = idx->ix.dim, ds = idx->ix.ds;
-  const uint32_t kp = (dim + kChunkK - 1) / kChunkK * kChunkK;
+  // 16-bit copies of the arena, built once per index: 0 raw rows (IP), 1 rows scaled by 1/|x| (cosine), 2 raw rows plus
+  // three columns carrying -|x|^2/2 (L2: the contraction itself yields the ranking key, no bias add in the epilogue —
+  // 16 broadcast LDS.128 + 64 FADD per warp and tile made the L2 instantiation 1.5x slower than IP at 128-d).
+  // TURDB_EXACT_L2_AUG=0 selects the epilogue-bias form over copy 0 (kept for comparison).
+  const bool l2_aug = metric == kL2 && !(getenv("TURDB_EXACT_L2_AUG") && atoi(getenv("TURDB_EXACT_L2_AUG")) == 0);
+  const int copy = metric == kCosine ? 1 : (l2_aug ? 2 : 0);
+  const uint32_t kp = (dim + (copy == 2 ? 3 : 0) + kChunkK - 1) / kChunkK * kChunkK;
   const uint32_t k_chunks = kp / kChunkK;
   if (k_chunks > 32) return fail(TURDB_ERR_UNSUPPORTED, "the exact path supports dim <= 2048 (dim %u)", dim);
   // up to 512 dims the query block (128 x K BF16) stays resident in shared memory; above, its K chunks are streamed
   // with the vector tile's (twice the TMA traffic per tile, but any K fits)
   const uint32_t stream_a = k_chunks > 8 ? 1u : 0u;
 
-  // BF16 copies of the arena, built once per index: raw rows (L2, IP) and rows scaled by 1/|x| (cosine), each with the
-  // maxima of its rounding-error and row norms (the inputs of the filter's error bound)
-  const int copy = metric == kCosine ? 1 : 0;
+  // each copy comes with the maxima of its rounding-error and row norms (the inputs of the filter's error bound)
   {
     std::lock_guard<std::mutex> lk(idx->mu);
-    uint16_t*& dst = copy ? idx->d_arena_bf16n : idx->d_arena_bf16;
+    uint16_t*& dst = copy == 1 ? idx->d_arena_bf16n : (copy == 2 ? idx->d_arena_bf16l2 : idx->d_arena_bf16);
     if (!dst) {
       if (!idx->d_bf16_max2) {
-        CUDA_TRY(cudaMalloc(&idx->d_bf16_max2, 5 * 4));  // [2 copies][2 maxima] + max |value| of the arena
-        CUDA_TRY(cudaMemsetAsync(idx->d_bf16_max2, 0, 5 * 4, stream));
+        CUDA_TRY(cudaMalloc(&idx->d_bf16_max2, 8 * 4));  // [3 copies][2 maxima] + max |value| + max |x|^2 of the arena
+        CUDA_TRY(cudaMemsetAsync(idx->d_bf16_max2, 0, 8 * 4, stream));
       }
-      if (!copy) {  // raw rows: FP16 only if every value fits comfortably (the cosine copy is unit-length rows: always FP16)
-        max_abs_kernel<<<(unsigned)((n * dim + 255) / 256), 256, 0, stream>>>(idx->d_arena, dim, ds, n, idx->d_bf16_max2 + 4);
-        uint32_t mbits = 0;
-        CUDA_TRY(cudaMemcpyAsync(&mbits, idx->d_bf16_max2 + 4, 4, cudaMemcpyDeviceToHost, stream));
+      const bool force_bf16 = getenv("TURDB_EXACT_FORCE_BF16") != nullptr;
+      if (copy != 1) {  // raw rows: FP16 only if every value fits comfortably (the cosine copy is unit-length rows: always FP16)
+        max_abs_kernel<<<(unsigned)((n * dim + 255) / 256), 256, 0, stream>>>(idx->d_arena, dim, ds, n, idx->d_bf16_max2 + 6);
+        max_nonneg_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(idx->d_norm2, n, idx->d_bf16_max2 + 7);
+        uint32_t mbits[2] = {0, 0};
+        CUDA_TRY(cudaMemcpyAsync(mbits, idx->d_bf16_max2 + 6, 8, cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
-        float mabs;
-        memcpy(&mabs, &mbits, 4);
-        idx->half_fp16[0] = (mabs <= 16384.0f && getenv("TURDB_EXACT_FORCE_BF16") == nullptr) ? 1 : 0;
-      } else if (getenv("TURDB_EXACT_FORCE_BF16")) {
+        float mabs, n2max;
+        memcpy(&mabs, &mbits[0], 4);
+        memcpy(&n2max, &mbits[1], 4);
+        int f16 = (mabs <= 16384.0f && !force_bf16) ? 1 : 0;
+        if (copy == 2) {
+          // FP16 bias columns hold t = -|x|^2 / (2 S) with |t| <= 16384 and the query side carries S <= 32768 (both exact
+          // powers of two); beyond that range the copy is BF16 (FP32 range, S = 1)
+          float S = 1.f;
+          while (f16 && 0.5f * n2max / S > 16384.0f && S < 65536.f) S *= 2.f;
+          if (S > 32768.f) {
+            f16 = 0;
+            S = 1.f;
+          }
+          idx->l2_scale = f16 ? S : 1.f;
+        }
+        idx->half_fp16[copy] = f16;
+      } else if (force_bf16) {
         idx->half_fp16[1] = 0;
       }
       CUDA_TRY(cudaMalloc(&dst, (size_t)n * kp * 2));
       const uint64_t total = n * kp;
       to_half_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(idx->d_arena, dim, ds, kp, n,
-                                                                            copy ? idx->d_norm2 : nullptr, idx->half_fp16[copy], dst);
+                                                                            copy != 0 ? idx->d_norm2 : nullptr, idx->half_fp16[copy], dst,
+                                                                            copy == 2 ? 1 : 0, idx->l2_scale);
       bf16_rowerr_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(idx->d_arena, dim, ds, kp, n,
-                                                                                 copy ? idx->d_norm2 : nullptr, dst,
+                                                                                 copy == 1 ? idx->d_norm2 : nullptr, dst,
                                                                                  idx->half_fp16[copy], idx->d_bf16_max2 + 2 * copy);
       CUDA_TRY(cudaGetLastError());
       CUDA_TRY(cudaStreamSynchronize(stream));
       idx->device_bytes += (size_t)n * kp * 2;
     }
   }
-  const uint16_t* d_xb = copy ? idx->d_arena_bf16n : idx->d_arena_bf16;
+  const uint16_t* d_xb = copy == 1 ? idx->d_arena_bf16n : (copy == 2 ? idx->d_arena_bf16l2 : idx->d_arena_bf16);
   const int fp16 = idx->half_fp16[copy];
+  const bool epi_bias = metric == kL2 && !l2_aug;  // the bias add in the epilogue (BIAS instantiations)
 
   // scratch: Qb | col bias | thresh | cand_cnt | kept | slack | cand_id | cand_key
   size_t off = 0;
@@ -290,8 +311,9 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
 
   {
     const uint64_t total = (uint64_t)nq * kp;
-    to_half_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_queries, dim, dim, kp, nq, nullptr, fp16, d_qb);
-    if (metric == kL2) col_bias_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(idx->d_norm2, n, d_bias);
+    to_half_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_queries, dim, dim, kp, nq, nullptr, fp16, d_qb,
+                                                                          copy == 2 ? 2 : 0, idx->l2_scale);
+    if (epi_bias) col_bias_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(idx->d_norm2, n, d_bias);
     const uint32_t first_tiles = std::max(1u, std::min(first_rows, cap / 2) / kTileN);
     const uint32_t first_cnt = (uint32_t)std::min<uint64_t>(n, (uint64_t)first_tiles * kTileN);
     exact_init_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(d_th, d_cnt, d_kept, d_qflags, d_arch_cnt, nq, first_cnt);
@@ -301,7 +323,8 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
     if (const char* ev = getenv("TURDB_EXACT_SLACK_SCALE")) slack_scale = (float)atof(ev);
     query_slack_kernel<<<(unsigned)(((uint64_t)nq * 32 + 255) / 256), 256, 0, stream>>>(d_queries, dim, kp, nq, d_qb, fp16,
                                                                                          idx->d_bf16_max2 + 2 * copy, metric,
-                                                                                         slack_scale, d_slack);
+                                                                                         slack_scale, d_slack,
+                                                                                         copy == 2 ? idx->l2_scale : 0.f);
   }
   // Two-CTA form (tcgen05 cta_group::2, clusters of 2): each CTA of a pair stages half of every vector tile, so the L2 -> SM
   // traffic and the shared-memory fill per flop halve (exact_search.cuh).  TURDB_EXACT_PAIR=0/1 overrides the default.
@@ -358,7 +381,7 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
       at[0].val.clusterDim.z = 1;
       cfg.attrs = at;
       cfg.numAttrs = 1;
-      cudaError_t oe = metric == kL2 ? (stream_a ? cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<true, true>, &cfg)
+      cudaError_t oe = epi_bias ? (stream_a ? cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<true, true>, &cfg)
                                                  : cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<true, false>, &cfg))
                                      : (stream_a ? cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<false, true>, &cfg)
                                                  : cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<false, false>, &cfg));
@@ -422,14 +445,14 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
     a.dense = lo == 0 ? 1u : 0u;
     const uint32_t grid = std::min<uint32_t>(a.n_items, n_workers) * (pair ? 2u : 1u);
     if (pair) {  // __cluster_dims__(2, 1, 1) on the kernel: the grid is a multiple of 2
-      if (metric == kL2) {
+      if (epi_bias) {
         if (stream_a) exact_gemm_filter_pair_kernel<true, true><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
         else exact_gemm_filter_pair_kernel<true, false><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
       } else {
         if (stream_a) exact_gemm_filter_pair_kernel<false, true><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
         else exact_gemm_filter_pair_kernel<false, false><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
       }
-    } else if (metric == kL2) {
+    } else if (epi_bias) {
       if (stream_a) exact_gemm_filter_kernel<true, true><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
       else exact_gemm_filter_kernel<true, false><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
     } else {

@@ -99,18 +99,41 @@ __device__ __forceinline__ float from_half_bits(uint16_t b, int fp16) {
 
 // FP32 rows [rows][ds] -> 16-bit rows [rows][kp] (kp = dim rounded up to 64, zero padded).  With `norm2` the row is
 // scaled by 1/|x| first, so that the cosine pass's score q.x/|x| is already its ranking key.
+// `aug` fills columns dim, dim+1, dim+2 (the L2 form: the contraction itself produces key = q.x - |x|^2/2):
+//   1 (vector side): the 16-bit hi / mid / lo split of t = -norm2[r] / (2 * aug_scale) — h1 = rn16(t), h2 = rn16(t - h1),
+//     h3 = rn16(t - h1 - h2); the differences are exact in FP32, so aug_scale * (h1 + h2 + h3) misses -|x|^2/2 by less than
+//     2^-23 of it (three 8-bit BF16 mantissas) plus, in FP16, aug_scale * 2^-24 (subnormal spacing);
+//   2 (query side): aug_scale in each of the three columns (a power of two: exact in either format).
+// With aug == 1 `norm2` is NOT a scaling (rows stay raw).
 __global__ void to_half_kernel(const float* __restrict__ src, uint32_t dim, uint32_t ds, uint32_t kp,
-                               uint64_t rows, const float* __restrict__ norm2, int fp16, uint16_t* __restrict__ dst) {
+                               uint64_t rows, const float* __restrict__ norm2, int fp16, uint16_t* __restrict__ dst, int aug = 0,
+                               float aug_scale = 1.f) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * kp) return;
   const uint64_t r = i / kp;
   const uint32_t c = (uint32_t)(i % kp);
   float v = c < dim ? src[r * ds + c] : 0.f;
-  if (norm2) {
+  if (aug == 0 && norm2) {
     const float n2 = norm2[r];
     v = n2 > 0.f ? v * rsqrtf(n2) : 0.f;
   }
+  if (aug == 2 && c >= dim && c < dim + 3) v = aug_scale;
+  if (aug == 1 && c >= dim && c < dim + 3) {
+    const float t = -0.5f * norm2[r] / aug_scale;  // aug_scale is a power of two: exact
+    const float h1 = from_half_bits(to_half_bits(t, fp16), fp16);
+    const float h2 = from_half_bits(to_half_bits(t - h1, fp16), fp16);
+    v = c == dim ? h1 : (c == dim + 1 ? h2 : (t - h1) - h2);
+  }
   dst[i] = to_half_bits(v, fp16);
+}
+
+// largest value of a non-negative float array (bit patterns order like the values)
+__global__ void max_nonneg_kernel(const float* __restrict__ src, uint64_t n, uint32_t* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float m = i < n ? src[i] : 0.f;
+  if (!(m >= 0.f)) m = 0.f;
+  for (uint32_t off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(kFullMask, m, off));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
 }
 
 // largest |value| of the arena (picks the copy's format)
@@ -161,9 +184,12 @@ __global__ void bf16_rowerr_kernel(const float* __restrict__ src, uint32_t dim, 
 //     f32 differences): 2^-22 (dim/8 + 8) (|q| + Xn + Dx)^2 for L2, 2^-20 |q| for the pre-scaled cosine rows.
 // The filter admits a key >= tau - 2 e(q) where tau is the kprime-th best FILTER key seen so far; a rejected row then
 // has an exact key below the exact keys of kprime admitted rows.
+// `aug_scale` > 0: the L2 bias travels inside the contraction (three extra columns, see to_half_kernel): its split
+// residual (2^-23 bmax + aug_scale 2^-24) and the FP32 accumulation over the three extra products (kp 2^-22 bmax, with
+// bmax = (Xn + Dx)^2 / 2 >= max |x|^2 / 2) join the bound.
 __global__ void query_slack_kernel(const float* __restrict__ queries, uint32_t dim, uint32_t kp, uint32_t nq,
                                    const uint16_t* __restrict__ qconv, int fp16, const uint32_t* __restrict__ arena_max2,
-                                   int metric, float scale, float* __restrict__ slack) {
+                                   int metric, float scale, float* __restrict__ slack, float aug_scale = 0.f) {
   const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (q >= nq) return;
   float e2 = 0.f, n2 = 0.f;
@@ -183,6 +209,10 @@ __global__ void query_slack_kernel(const float* __restrict__ queries, uint32_t d
     if (metric == kL2) {
       const float s = qn + Xn + Dx;
       e += 2.3841858e-7f * (float)(dim / 8 + 8) * s * s;
+      if (aug_scale > 0.f) {
+        const float bmax = 0.5f * (Xn + Dx) * (Xn + Dx);
+        e += 1.1920929e-7f * bmax + aug_scale * 5.9604645e-8f * 3.f + (float)kp * 2.3841858e-7f * bmax;
+      }
     } else if (metric == kCosine) {
       e += 9.5367432e-7f * qn;
     } else {

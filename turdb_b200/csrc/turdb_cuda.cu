@@ -72,8 +72,12 @@ struct turdb_cuda_index {
   uint32_t sq8_row_bytes = 0;
   uint16_t* d_arena_bf16 = nullptr;        // exact path operand (raw rows: L2, IP), 16-bit (FP16 or BF16), built lazily
   uint16_t* d_arena_bf16n = nullptr;       // exact path operand (rows scaled by 1/|x|: cosine), FP16, built lazily
-  int half_fp16[2] = {0, 1};               // format of the two copies: 1 FP16, 0 BF16
-  uint32_t* d_bf16_max2 = nullptr;         // [2 copies][2]: max |v - bf16(v)|_2, max |bf16(v)|_2 over rows (float bits)
+  uint16_t* d_arena_bf16l2 = nullptr;      // exact path operand for L2: raw rows + three columns holding -|x|^2/2 (hi/mid/lo
+                                           // 16-bit split, divided by l2_scale), so that the contraction itself yields the key
+  int half_fp16[3] = {0, 1, 0};            // format of the copies (raw, cosine, L2): 1 FP16, 0 BF16
+  float l2_scale = 1.f;                    // power of two the L2 copy's bias columns are divided by (the query side carries it)
+  uint32_t* d_bf16_max2 = nullptr;         // [3 copies][2]: max |v - bf16(v)|_2, max |bf16(v)|_2 over rows (float bits); [6]: max
+                                           // |value|; [7]: max |x|^2
   cudaMemPool_t pool = nullptr;            // per-index stream-ordered scratch pool (never trimmed)
   uint64_t device_bytes = 0;
   uint64_t n_up_slots = 0;
@@ -213,6 +217,7 @@ int32_t turdb_cuda_index_destroy(turdb_cuda_index* idx) {
     cudaFree(idx->d_norm2_sq8);
     cudaFree(idx->d_arena_bf16);
     cudaFree(idx->d_arena_bf16n);
+    cudaFree(idx->d_arena_bf16l2);
     cudaFree(idx->d_bf16_max2);
     for (cudaEvent_t ev : idx->prof_events) cudaEventDestroy(ev);
     cudaFree(idx->d_dbg);
