@@ -485,6 +485,7 @@ def main():
     gt_mm = exact_ground_truth(x_dev, qb[0][:200], k, torch)
     del x_dev
     exact_info = {"ms_per_batch": exact_ms, "tflops": 2.0 * nq * args.n * args.dim / exact_ms / 1e9,
+                  "frac_of_measured_bf16_peak": (2.0 * nq * args.n * args.dim / exact_ms / 1e9) / float(peaks.get("bf16_tflops", 1655.7)),
                   "agreement_with_fp32_matmul_top10": recall_at_k(gt_all[:200], gt_mm)}
 
     cpu_baseline = None

@@ -218,8 +218,16 @@ int32_t turdb_cuda_index_gather_probe(turdb_cuda_index* idx, uint32_t ctas_per_s
  * twice a bound on the BF16 score error (from the operands' actual rounding-error norms), so no row of the exact
  * FP32 top-k can be lost; a query whose candidate buffer overflows is redone by a plain FP32 scan kernel.
  * Result = top-k by (FP32 distance, node id).  Distances follow the HNSW metric contract above (squared L2 /
- * 1-cos / -dot), NOT the SQL sqrt form.  k <= TURDB_EXACT_MAX_K; rerank_factor 0 = 1 (the band already certifies k' = k; a larger factor only
- * widens the working set — 6.5 ms against 7.4 ms per 10k queries x 1M x 384 at factor 4); k*rerank_factor is clamped to 2048.  Absent vectors (+inf rows) evaluate to +inf.
+ * 1-cos / -dot), NOT the SQL sqrt form.  k <= TURDB_EXACT_MAX_K; rerank_factor 0 = 1 (the band already certifies
+ * k' = k; a larger factor only widens the working set — 6.5 ms against 7.4 ms per 10k queries x 1M x 384 at factor 4);
+ * k*rerank_factor is clamped to 2048.  Absent vectors (+inf rows) evaluate to +inf.
+ * The filter kernel has a one-CTA (tcgen05 cta_group::1) and a two-CTA (cta_group::2, clusters of 2) form; the library
+ * picks by dimension (two-CTA from 320 dims up, one-CTA when no cluster fits).  Results do not depend on the form.
+ * Measurement switches (environment, read per call; never needed in production): TURDB_EXACT_PAIR=0/1 forces a form,
+ * TURDB_EXACT_L2_AUG=0 adds the L2 bias in the epilogue instead of inside the contraction, TURDB_EXACT_GROWTH=g sets the
+ * slice growth factor, TURDB_EXACT_FORCE_BF16=1 (read when an index's 16-bit copy is built) forbids FP16 operands,
+ * TURDB_EXACT_VERBOSE=1 prints the chosen form to stderr; TURDB_EXACT_SLACK_SCALE and TURDB_EXACT_DIAG make the filter
+ * UNCERTIFIED / wrong on purpose and exist only to time its parts.
  */
 int32_t turdb_cuda_bruteforce_topk(turdb_cuda_index* idx, const float* queries, uint32_t query_dim,
                                    uint32_t nq, uint32_t k, uint8_t metric, uint32_t rerank_factor,
