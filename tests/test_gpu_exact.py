@@ -52,6 +52,33 @@ def test_exact_topk_matches_reference(gpu_required, n, dim, nq, k):
     idx.close()
 
 
+@pytest.mark.parametrize("env", [{"TURDB_EXACT_PAIR": "0"}, {"TURDB_EXACT_PAIR": "1"}, {"TURDB_EXACT_L2_AUG": "0"},
+                                 {"TURDB_EXACT_PAIR": "0", "TURDB_EXACT_L2_AUG": "0"}, {"TURDB_EXACT_GROWTH": "2"}])
+def test_every_form_of_the_filter_gives_the_same_answer(gpu_required, monkeypatch, env):
+    """One-CTA (cta_group::1) and two-CTA (cta_group::2) kernels, the L2 bias inside the contraction or added in the epilogue,
+    another slice growth: switches the library reads per call.  The answer must not depend on any of them — ids and distance
+    bits equal to the default configuration's and to the reference's exact top-k."""
+    n, nq, k = 6000, 300, 10  # 300 queries: a second (partly empty) query block in both forms
+    for dim in (96, 384):
+        x = ds.gaussian_latent(n, dim, seed=dim, normalise=False)
+        q = ds.gaussian_latent(nq, dim, seed=dim + 1, normalise=False)
+        idx = CudaHnswIndex.from_graph(flat_graph(x))
+        for metric in (ob.L2, ob.COSINE, ob.IP):
+            base = idx.bruteforce_topk(q, k, DistanceFunction(metric))
+            with monkeypatch.context() as m:
+                for key, val in env.items():
+                    m.setenv(key, val)
+                got = idx.bruteforce_topk(q, k, DistanceFunction(metric))
+            assert np.array_equal(got[1], base[1]) and np.array_equal(got[2].view(np.uint32), base[2].view(np.uint32)), (dim, metric, env)
+            ref_ids, ref_d = exact_reference(x, q[:8], k, metric)
+            for i in range(8):
+                same = got[1][i] == ref_ids[i]
+                assert np.array_equal(got[2][i][same].view(np.uint32), ref_d[i][same].view(np.uint32))
+                if not same.all():
+                    assert np.allclose(got[2][i], ref_d[i], rtol=REL_TOL, atol=1e-6), (dim, metric, i)
+        idx.close()
+
+
 def test_exact_sql_known_answers(gpu_required):
     """The reference's SQL k-NN answers (tests/hnsw_integration.rs:220-276) through the exact path."""
     x = np.array([[.1] * 4, [.5] * 4, [.9] * 4], np.float32)

@@ -328,11 +328,11 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
   }
   // Two-CTA form (tcgen05 cta_group::2, clusters of 2): each CTA of a pair stages half of every vector tile, so the L2 -> SM
   // traffic and the shared-memory fill per flop halve (exact_search.cuh).  TURDB_EXACT_PAIR=0/1 overrides the default.
-  // Measured, 10k queries x 1M vectors (profiles/r02_exact_probe_final.json): the pair form wins where the tile is long
-  // enough for its cross-CTA synchronisation to disappear — 384-d 5.7 against 6.0 ms, 512-d 7.1 against 10.2 ms (a resident
-  // 128 KB query block leaves the one-CTA form two stages), 768-d 10.4 against 11.1 ms — and loses below: 256-d 4.6
-  // against 4.4 ms, 128-d 3.9 against 3.0 ms.
-  int pair = k_chunks >= 5 ? 1 : 0;
+  // Measured, 10k queries x 1M vectors (profiles/r02_exact_probe_final.json): with the CTA-scope remote arrive the pair form
+  // wins at every K that was tried — 128-d 2.96 against 3.05 ms, 256-d 4.06 against 4.43, 384-d 5.47 against 6.02, 512-d
+  // 7.1 against 10.2 (a resident 128 KB query block leaves the one-CTA form two stages), 768-d 10.2 against 11.1.
+  // One-chunk problems (dim <= 64) keep the one-CTA form (not measured).
+  int pair = k_chunks >= 2 ? 1 : 0;
   if (const char* ev = getenv("TURDB_EXACT_PAIR")) pair = atoi(ev) != 0;
   if (idx->num_sms < 2) pair = 0;
   cudaError_t e = cudaSuccess;

@@ -406,22 +406,13 @@ __device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint64_t desc_a, ui
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Remote arrive on the leader's "accumulator drained" barrier.  No generic-memory data travels through it — what it
+// orders is this warp's TMEM reads (complete after tcgen05.wait::ld, fenced by tcgen05.fence::before_thread_sync) against
+// the tensor pipe's next writes — so the default CTA-scope form is enough; the .release.cluster form (a cluster-wide
+// fence per arrive) was the most-sampled line of the two-CTA kernel (38 % of all samples, ncu).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // acquires arrivals made by the peer CTA
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  }
-}
-
 __device__ __forceinline__ bool elect_one() {  // true in exactly one lane of the (converged) warp
   uint32_t pred;
   asm volatile(
@@ -601,8 +592,7 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
         tc_fence_after();
         for (uint32_t t = t0; t < t1; ++t) {
           long long c3 = a.dbg ? clock64() : 0;
-          if (PAIR) mbar_wait_cluster(bar_t_empty + 8 * acc, acc_phase ^ 1);  // both CTAs' epilogues have drained it
-          else mbar_wait(bar_t_empty + 8 * acc, acc_phase ^ 1);              // epilogue has drained this accumulator
+          mbar_wait(bar_t_empty + 8 * acc, acc_phase ^ 1);  // the epilogue (of both CTAs of a pair) has drained this accumulator
           if (a.dbg && lane == 0) atomicAdd(a.dbg + 3, (unsigned long long)(clock64() - c3));
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * kTileN;
