@@ -52,11 +52,10 @@ def test_exact_topk_matches_reference(gpu_required, n, dim, nq, k):
     idx.close()
 
 
-@pytest.mark.parametrize("env", [{"TURDB_EXACT_PAIR": "0"}, {"TURDB_EXACT_PAIR": "1"}, {"TURDB_EXACT_L2_AUG": "0"},
-                                 {"TURDB_EXACT_PAIR": "0", "TURDB_EXACT_L2_AUG": "0"}, {"TURDB_EXACT_GROWTH": "2"}])
+@pytest.mark.parametrize("env", [{"TURDB_EXACT_PAIR": "0"}, {"TURDB_EXACT_PAIR": "1"}, {"TURDB_EXACT_GROWTH": "2"},
+                                 {"TURDB_EXACT_PAIR": "0", "TURDB_EXACT_GROWTH": "7"}])
 def test_every_form_of_the_filter_gives_the_same_answer(gpu_required, monkeypatch, env):
-    """One-CTA (cta_group::1) and two-CTA (cta_group::2) kernels, the L2 bias inside the contraction or added in the epilogue,
-    another slice growth: switches the library reads per call.  The answer must not depend on any of them — ids and distance
+    """One-CTA (cta_group::1) and two-CTA (cta_group::2) kernels, other slice growths: switches the library reads per call.  The answer must not depend on any of them — ids and distance
     bits equal to the default configuration's and to the reference's exact top-k."""
     n, nq, k = 6000, 300, 10  # 300 queries: a second (partly empty) query block in both forms
     for dim in (96, 384):

@@ -220,11 +220,9 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
   const uint64_t n = idx->ix.n;
   const uint32_t dim = idx->ix.dim, ds = idx->ix.ds;
   // 16-bit copies of the arena, built once per index: 0 raw rows (IP), 1 rows scaled by 1/|x| (cosine), 2 raw rows plus
-  // three columns carrying -|x|^2/2 (L2: the contraction itself yields the ranking key, no bias add in the epilogue —
-  // 16 broadcast LDS.128 + 64 FADD per warp and tile made the L2 instantiation 1.5x slower than IP at 128-d).
-  // TURDB_EXACT_L2_AUG=0 selects the epilogue-bias form over copy 0 (kept for comparison).
-  const bool l2_aug = metric == kL2 && !(getenv("TURDB_EXACT_L2_AUG") && atoi(getenv("TURDB_EXACT_L2_AUG")) == 0);
-  const int copy = metric == kCosine ? 1 : (l2_aug ? 2 : 0);
+  // three columns carrying -|x|^2/2 (L2: the contraction itself yields the ranking key; an earlier version added the bias
+  // in the epilogue — 16 broadcast LDS.128 + 64 FADD per warp and tile, 1.5x slower than IP at 128-d).
+  const int copy = metric == kCosine ? 1 : (metric == kL2 ? 2 : 0);
   const uint32_t kp = (dim + (copy == 2 ? 3 : 0) + kChunkK - 1) / kChunkK * kChunkK;
   const uint32_t k_chunks = kp / kChunkK;
   if (k_chunks > 32) return fail(TURDB_ERR_UNSUPPORTED, "the exact path supports dim <= 2048 (dim %u)", dim);
@@ -282,22 +280,20 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
   }
   const uint16_t* d_xb = copy == 1 ? idx->d_arena_bf16n : (copy == 2 ? idx->d_arena_bf16l2 : idx->d_arena_bf16);
   const int fp16 = idx->half_fp16[copy];
-  const bool epi_bias = metric == kL2 && !l2_aug;  // the bias add in the epilogue (BIAS instantiations)
 
-  // scratch: Qb | col bias | thresh | cand_cnt | kept | slack | cand_id | cand_key
+  // scratch: Qb | thresh | cand_cnt | kept | slack | cand_id | cand_key
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
     off = (off + bytes + 255) & ~(size_t)255;
     return o;
   };
-  const size_t o_qb = take((size_t)nq * kp * 2), o_ab = take((size_t)n * 4), o_th = take((size_t)nq * 4),
+  const size_t o_qb = take((size_t)nq * kp * 2), o_th = take((size_t)nq * 4),
                o_cnt = take((size_t)nq * 4), o_kept = take((size_t)nq * 4), o_slack = take((size_t)nq * 4),
                o_id = take((size_t)nq * cap * 4), o_key = take((size_t)nq * cap * 4);
   uint8_t* scr = nullptr;
   CUDA_TRY(cudaMallocFromPoolAsync(&scr, off, idx->pool, stream));
   uint16_t* d_qb = (uint16_t*)(scr + o_qb);
-  float* d_bias = (float*)(scr + o_ab);
   float* d_th = (float*)(scr + o_th);
   uint32_t* d_cnt = (uint32_t*)(scr + o_cnt);
   uint32_t* d_kept = (uint32_t*)(scr + o_kept);
@@ -313,7 +309,6 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
     const uint64_t total = (uint64_t)nq * kp;
     to_half_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_queries, dim, dim, kp, nq, nullptr, fp16, d_qb,
                                                                           copy == 2 ? 2 : 0, idx->l2_scale);
-    if (epi_bias) col_bias_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(idx->d_norm2, n, d_bias);
     const uint32_t first_tiles = std::max(1u, std::min(first_rows, cap / 2) / kTileN);
     const uint32_t first_cnt = (uint32_t)std::min<uint64_t>(n, (uint64_t)first_tiles * kTileN);
     exact_init_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(d_th, d_cnt, d_kept, d_qflags, d_arch_cnt, nq, first_cnt);
@@ -342,14 +337,10 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
     auto set_smem = [&](auto kern, size_t bytes) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     };
-    set_smem(exact_gemm_filter_kernel<true, false>, (size_t)idx->max_smem_optin);
-    set_smem(exact_gemm_filter_kernel<false, false>, (size_t)idx->max_smem_optin);
-    set_smem(exact_gemm_filter_kernel<true, true>, (size_t)idx->max_smem_optin);
-    set_smem(exact_gemm_filter_kernel<false, true>, (size_t)idx->max_smem_optin);
-    set_smem(exact_gemm_filter_pair_kernel<true, false>, (size_t)idx->max_smem_optin);
-    set_smem(exact_gemm_filter_pair_kernel<false, false>, (size_t)idx->max_smem_optin);
-    set_smem(exact_gemm_filter_pair_kernel<true, true>, (size_t)idx->max_smem_optin);
-    set_smem(exact_gemm_filter_pair_kernel<false, true>, (size_t)idx->max_smem_optin);
+    set_smem(exact_gemm_filter_kernel<false>, (size_t)idx->max_smem_optin);
+    set_smem(exact_gemm_filter_kernel<true>, (size_t)idx->max_smem_optin);
+    set_smem(exact_gemm_filter_pair_kernel<false>, (size_t)idx->max_smem_optin);
+    set_smem(exact_gemm_filter_pair_kernel<true>, (size_t)idx->max_smem_optin);
   }
   if (e != cudaSuccess) return bail(fail(TURDB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)));
 
@@ -381,10 +372,8 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
       at[0].val.clusterDim.z = 1;
       cfg.attrs = at;
       cfg.numAttrs = 1;
-      cudaError_t oe = epi_bias ? (stream_a ? cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<true, true>, &cfg)
-                                                 : cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<true, false>, &cfg))
-                                     : (stream_a ? cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<false, true>, &cfg)
-                                                 : cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<false, false>, &cfg));
+      cudaError_t oe = stream_a ? cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<true>, &cfg)
+                                : cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<false>, &cfg);
       if (oe != cudaSuccess) {
         cudaGetLastError();
         max_clusters = 0;
@@ -433,7 +422,6 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
     a.tiles_per_item = tpi;
     a.n_qblocks = n_qblocks;
     a.n_items = n_qblocks * ((tiles + tpi - 1) / tpi);
-    a.col_bias = d_bias;
     a.thresh = d_th;
     a.cand_cnt = d_cnt;
     a.cand_id = d_cid;
@@ -445,19 +433,11 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
     a.dense = lo == 0 ? 1u : 0u;
     const uint32_t grid = std::min<uint32_t>(a.n_items, n_workers) * (pair ? 2u : 1u);
     if (pair) {  // __cluster_dims__(2, 1, 1) on the kernel: the grid is a multiple of 2
-      if (epi_bias) {
-        if (stream_a) exact_gemm_filter_pair_kernel<true, true><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
-        else exact_gemm_filter_pair_kernel<true, false><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
-      } else {
-        if (stream_a) exact_gemm_filter_pair_kernel<false, true><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
-        else exact_gemm_filter_pair_kernel<false, false><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
-      }
-    } else if (epi_bias) {
-      if (stream_a) exact_gemm_filter_kernel<true, true><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
-      else exact_gemm_filter_kernel<true, false><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
+      if (stream_a) exact_gemm_filter_pair_kernel<true><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
+      else exact_gemm_filter_pair_kernel<false><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
     } else {
-      if (stream_a) exact_gemm_filter_kernel<false, true><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
-      else exact_gemm_filter_kernel<false, false><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
+      if (stream_a) exact_gemm_filter_kernel<true><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
+      else exact_gemm_filter_kernel<false><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
     }
     exact_threshold_kernel<<<(nq + kThreshWarps - 1) / kThreshWarps, 32 * kThreshWarps, 0, stream>>>(nq, kprime, cap, d_cnt, d_cid, d_ckey, d_th, d_slack, d_kept, d_qflags,
                                                          d_arch_cnt, d_arch_id, arch_cap);

@@ -222,12 +222,9 @@ __global__ void query_slack_kernel(const float* __restrict__ queries, uint32_t d
   }
 }
 
-// Ranking key of a score s for column (vector) j, larger = closer (the query's own norm does not change ranks):
-//   L2: s - |x|^2 / 2  (bias array below)      cosine: s on rows pre-scaled by 1/|x|      IP: s
-__global__ void col_bias_kernel(const float* __restrict__ norm2, uint64_t n, float* __restrict__ bias) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) bias[i] = -0.5f * norm2[i];
-}
+// Ranking key of a score for column (vector) j, larger = closer (the query's own norm does not change ranks) — in every
+// case what the contraction itself produces:  L2: q.x - |x|^2/2 (three augmented columns of the L2 copy, to_half_kernel)
+// cosine: q.x on rows pre-scaled by 1/|x|      IP: q.x
 
 // ------------------------------------------------------------------------------------------------
 // tcgen05 helpers
@@ -345,7 +342,7 @@ __host__ __device__ constexpr uint32_t exact_stage_bytes(bool stream_a, bool pai
 }
 // everything in dynamic shared memory except the pipeline stages (kernel and host compute the layout from this)
 __host__ __device__ constexpr uint32_t exact_fixed_smem(uint32_t k_chunks, bool stream_a) {
-  return (stream_a ? 0u : k_chunks * kChunkBytes) + kEpiWarps * 2 * kEpiCols * 4 + kEpiWarps * kWq * 12 + 32 * 8 + 16;
+  return (stream_a ? 0u : k_chunks * kChunkBytes) + kEpiWarps * kWq * 12 + 32 * 8 + 16;
 }
 
 struct ExactArgs {
@@ -357,7 +354,6 @@ struct ExactArgs {
   uint32_t tile_lo, tile_hi;      // vector tiles of this pass
   uint32_t tiles_per_item;        // consecutive tiles one CTA (pair) handles for one query block
   uint32_t n_qblocks, n_items;    // query blocks: 128 queries each, 256 (two CTAs x 128) in the two-CTA form
-  const float* col_bias;          // [n_vec] (L2 only)
   const float* thresh;            // [nq] keep keys >= thresh
   uint32_t* cand_cnt;             // [nq]
   uint32_t* cand_id;              // [nq][cap]
@@ -448,9 +444,9 @@ __device__ __noinline__ void exact_wq_flush(uint32_t* cand_cnt, uint32_t* cand_i
   __syncwarp();
 }
 
-// smem: [A: k_chunks x 16 KB (resident form)][stages: n_stages x ([A chunk] B chunk)][col bias: per warp 2 x kEpiCols float]
+// smem: [A: k_chunks x 16 KB (resident form)][stages: n_stages x ([A chunk] B chunk)]
 //       [warp queues: key | id | lane][barriers][tmem ptr]
-template <bool BIAS, bool STREAM_A, bool PAIR>
+template <bool STREAM_A, bool PAIR>
 __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q, const CUtensorMap* map_x, const ExactArgs& a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -463,8 +459,7 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
   uint8_t* sA = smem;
   uint8_t* sB = sA + (STREAM_A ? 0 : (size_t)a.k_chunks * kChunkBytes);
   const uint32_t kStages = a.n_stages;
-  float* s_bias = reinterpret_cast<float*>(sB + (size_t)kStages * stage_bytes);  // [kEpiWarps][2][kEpiCols]
-  float* wq_key = s_bias + kEpiWarps * 2 * kEpiCols;                              // [kEpiWarps][kWq]
+  float* wq_key = reinterpret_cast<float*>(sB + (size_t)kStages * stage_bytes);  // [kEpiWarps][kWq]
   uint32_t* wq_id = reinterpret_cast<uint32_t*>(wq_key + kEpiWarps * kWq);
   uint32_t* wq_lane = wq_id + kEpiWarps * kWq;
   uint64_t* bars = reinterpret_cast<uint64_t*>(wq_lane + kEpiWarps * kWq);
@@ -641,9 +636,13 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
     }
   } else {
     // ===== epilogue: kEpiWarps warps; warp = one TMEM lane quarter (32 query rows) x kEpiCols of the tile's columns =====
+    // (Measured and dropped: two alternating SETS of eight warps, set s serving accumulator s with two rounds of kEpiCols
+    // per tile — the same work in another order: 128-d 3.32 against 3.19 ms, 768-d 10.36 against 10.20 ms.  At short K the
+    // tensor pipe idles on the accumulator hand-offs — commit -> wake -> TMEM load -> arrive -> wake, ~0.9k cycles per
+    // 1.05k-cycle tile at 128-d (ncu: pipe 53 % active, the issuer 29 % of its time on bar_t_empty) — which two
+    // 256-column buffers cannot hide; four 128-column buffers could.)
     const uint32_t ew = warp - 2;                    // index among the epilogue warps
     const uint32_t quarter = warp & 3;               // TMEM lane quarter this warp may read (= warp id % 4)
-    const uint32_t row = quarter * 32 + lane;
     const uint32_t cslice = (ew >> 2) * kEpiCols;    // first tile column of this warp's slice
     const uint32_t et = threadIdx.x - 64;            // index among the epilogue threads
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -665,27 +664,7 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
       q_base = qb * kQRows + rank * kTileM + quarter * 32;
       const uint32_t q = q_base + lane;
       const float tau = q < a.nq ? a.thresh[q] : INFINITY;  // rows past the batch never keep anything
-      // per-column bias (L2: -|x|^2/2): every warp stages its OWN kEpiCols values (no CTA barrier couples the epilogue
-      // warps), double-buffered with the accumulators and one tile AHEAD — the global load is issued before the tile's
-      // accumulator is awaited and parked in shared memory after the tile has been looked at
-      float* my_bias = s_bias + ew * 2 * kEpiCols;
-      float bias_next[kEpiCols / 32];
-      if (BIAS && t0 < t1) {
-#pragma unroll
-        for (uint32_t i = 0; i < kEpiCols / 32; ++i) {
-          const uint64_t col = (uint64_t)t0 * kTileN + cslice + i * 32 + lane;
-          my_bias[acc * kEpiCols + i * 32 + lane] = col < a.n_vec ? a.col_bias[col] : 0.f;
-        }
-        __syncwarp();
-      }
       for (uint32_t t = t0; t < t1; ++t) {
-        if (BIAS && t + 1 < t1) {
-#pragma unroll
-          for (uint32_t i = 0; i < kEpiCols / 32; ++i) {
-            const uint64_t col = (uint64_t)(t + 1) * kTileN + cslice + i * 32 + lane;
-            bias_next[i] = col < a.n_vec ? a.col_bias[col] : 0.f;
-          }
-        }
         long long c6 = (a.dbg && et == 0) ? clock64() : 0;
         mbar_wait(bar_t_full + 8 * acc, acc_phase);
         long long c7 = (a.dbg && et == 0) ? clock64() : 0;
@@ -709,7 +688,6 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
           if (PAIR) mbar_arrive_cluster(t_empty_dst + 8 * acc);
           else mbar_arrive(t_empty_dst + 8 * acc);
         }
-        const uint32_t bias_buf = acc * kEpiCols;
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -717,17 +695,6 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
         if (a.diag == 2) continue;
 #pragma unroll
         for (uint32_t cb = 0; cb < kEpiCols / 32; ++cb) {
-          if (BIAS) {
-            const float4* b4 = reinterpret_cast<const float4*>(my_bias + bias_buf + cb * 32);
-#pragma unroll
-            for (uint32_t j = 0; j < 32; j += 4) {
-              const float4 b = b4[j >> 2];
-              v[cb][j] = __float_as_uint(__uint_as_float(v[cb][j]) + b.x);
-              v[cb][j + 1] = __float_as_uint(__uint_as_float(v[cb][j + 1]) + b.y);
-              v[cb][j + 2] = __float_as_uint(__uint_as_float(v[cb][j + 2]) + b.z);
-              v[cb][j + 3] = __float_as_uint(__uint_as_float(v[cb][j + 3]) + b.w);
-            }
-          }
           if (a.dense) {  // first slice: no test, no queue — 128-bit stores of the thread's 32 consecutive columns
             if (q < a.nq) {
               const uint32_t c0 = cslice + cb * 32;  // tile column of v[cb][0]
@@ -783,11 +750,6 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
             }
           }
         }
-        if (BIAS && t + 1 < t1) {  // acc already names the next tile's buffer (last read two tiles ago, by this warp only)
-#pragma unroll
-          for (uint32_t i = 0; i < kEpiCols / 32; ++i) my_bias[acc * kEpiCols + i * 32 + lane] = bias_next[i];
-          __syncwarp();
-        }
         if (a.dbg && et == 0) {
           atomicAdd(a.dbg + 6, (unsigned long long)(c7 - c6));
           atomicAdd(a.dbg + 7, (unsigned long long)(clock64() - c7));
@@ -809,19 +771,19 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
   }
 }
 
-template <bool BIAS, bool STREAM_A>
+template <bool STREAM_A>
 __global__ void __launch_bounds__(kExactThreads, 1)
 exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                          const ExactArgs a) {
-  exact_gemm_filter_body<BIAS, STREAM_A, false>(&map_q, &map_x, a);
+  exact_gemm_filter_body<STREAM_A, false>(&map_q, &map_x, a);
 }
 
 // the two-CTA form: clusters of 2 CTAs (one TPC), grid = 2 x the number of pairs
-template <bool BIAS, bool STREAM_A>
+template <bool STREAM_A>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kExactThreads, 1)
 exact_gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                               const ExactArgs a) {
-  exact_gemm_filter_body<BIAS, STREAM_A, true>(&map_q, &map_x, a);
+  exact_gemm_filter_body<STREAM_A, true>(&map_q, &map_x, a);
 }
 
 // ------------------------------------------------------------------------------------------------
