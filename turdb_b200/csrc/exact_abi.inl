@@ -158,6 +158,11 @@ extern "C" int32_t turdb_cuda_shards_search_batch(turdb_cuda_index* const* shard
   return rc;
 }
 
+// 1: problems of up to three K-chunks (dim <= 192; L2: dim <= 189) run 128-vector tiles over four accumulators
+#ifndef TURDB_EXACT_SHORT_K_TILE128
+#define TURDB_EXACT_SHORT_K_TILE128 0
+#endif
+
 // ---- TMA descriptors: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -229,6 +234,10 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
   // up to 512 dims the query block (128 x K BF16) stays resident in shared memory; above, its K chunks are streamed
   // with the vector tile's (twice the TMA traffic per tile, but any K fits)
   const uint32_t stream_a = k_chunks > 8 ? 1u : 0u;
+  // vectors per MMA tile: 256 (two accumulators) — or, at short K, 128 with four accumulators and two alternating sets of
+  // epilogue warps (exact_search.cuh); TURDB_EXACT_TILE_N=128/256 overrides the choice (measurement)
+  uint32_t tile_n = TURDB_EXACT_SHORT_K_TILE128 && k_chunks <= 3 ? 128u : 256u;
+  if (const char* ev = getenv("TURDB_EXACT_TILE_N")) tile_n = (atoi(ev) == 128 && !stream_a) ? 128u : 256u;
 
   // each copy comes with the maxima of its rounding-error and row norms (the inputs of the filter's error bound)
   {
@@ -309,8 +318,8 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
     const uint64_t total = (uint64_t)nq * kp;
     to_half_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_queries, dim, dim, kp, nq, nullptr, fp16, d_qb,
                                                                           copy == 2 ? 2 : 0, idx->l2_scale);
-    const uint32_t first_tiles = std::max(1u, std::min(first_rows, cap / 2) / kTileN);
-    const uint32_t first_cnt = (uint32_t)std::min<uint64_t>(n, (uint64_t)first_tiles * kTileN);
+    const uint32_t first_tiles = std::max(1u, std::min(first_rows, cap / 2) / tile_n);
+    const uint32_t first_cnt = (uint32_t)std::min<uint64_t>(n, (uint64_t)first_tiles * tile_n);
     exact_init_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(d_th, d_cnt, d_kept, d_qflags, d_arch_cnt, nq, first_cnt);
     // diagnostic only (measuring what the certificate costs): TURDB_EXACT_SLACK_SCALE=0 turns the slack band off, which
     // makes the filter the uncertified heuristic of round 1
@@ -337,10 +346,12 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
     auto set_smem = [&](auto kern, size_t bytes) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     };
-    set_smem(exact_gemm_filter_kernel<false>, (size_t)idx->max_smem_optin);
-    set_smem(exact_gemm_filter_kernel<true>, (size_t)idx->max_smem_optin);
-    set_smem(exact_gemm_filter_pair_kernel<false>, (size_t)idx->max_smem_optin);
-    set_smem(exact_gemm_filter_pair_kernel<true>, (size_t)idx->max_smem_optin);
+    set_smem(exact_gemm_filter_kernel<false, 256>, (size_t)idx->max_smem_optin);
+    set_smem(exact_gemm_filter_kernel<true, 256>, (size_t)idx->max_smem_optin);
+    set_smem(exact_gemm_filter_kernel<false, 128>, (size_t)idx->max_smem_optin);
+    set_smem(exact_gemm_filter_pair_kernel<false, 256>, (size_t)idx->max_smem_optin);
+    set_smem(exact_gemm_filter_pair_kernel<true, 256>, (size_t)idx->max_smem_optin);
+    set_smem(exact_gemm_filter_pair_kernel<false, 128>, (size_t)idx->max_smem_optin);
   }
   if (e != cudaSuccess) return bail(fail(TURDB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)));
 
@@ -349,7 +360,7 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
   size_t stage_bytes = 0, gemm_smem = 0;
   uint32_t n_stages = 0;
   auto plan = [&](int as_pair) {
-    stage_bytes = exact_stage_bytes(stream_a != 0, as_pair != 0);
+    stage_bytes = exact_stage_bytes(stream_a != 0, as_pair != 0, tile_n);
     n_stages = (size_t)idx->max_smem_optin < fixed_smem + 2 * stage_bytes
                    ? 0u
                    : (uint32_t)std::min<size_t>(kMaxStages, ((size_t)idx->max_smem_optin - fixed_smem) / stage_bytes);
@@ -372,8 +383,9 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
       at[0].val.clusterDim.z = 1;
       cfg.attrs = at;
       cfg.numAttrs = 1;
-      cudaError_t oe = stream_a ? cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<true>, &cfg)
-                                : cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<false>, &cfg);
+      cudaError_t oe = stream_a       ? cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<true, 256>, &cfg)
+                       : tile_n == 128 ? cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<false, 128>, &cfg)
+                                       : cudaOccupancyMaxActiveClusters(&max_clusters, exact_gemm_filter_pair_kernel<false, 256>, &cfg);
       if (oe != cudaSuccess) {
         cudaGetLastError();
         max_clusters = 0;
@@ -385,10 +397,10 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
   if (!pair) plan(0);
   if (n_stages < 2) return bail(fail(TURDB_ERR_UNSUPPORTED, "not enough shared memory for the exact path at dim %u", dim));
   if (getenv("TURDB_EXACT_VERBOSE"))
-    fprintf(stderr, "[turdb exact] form=%s workers=%u stages=%u smem=%zu k_chunks=%u stream_a=%u fp16=%d\n", pair ? "two-CTA" : "one-CTA",
-            n_workers, n_stages, gemm_smem, k_chunks, stream_a, fp16);
+    fprintf(stderr, "[turdb exact] form=%s tile_n=%u workers=%u stages=%u smem=%zu k_chunks=%u stream_a=%u fp16=%d\n", pair ? "two-CTA" : "one-CTA",
+            tile_n, n_workers, n_stages, gemm_smem, k_chunks, stream_a, fp16);
   CUtensorMap map_q, map_x;
-  if (!make_bf16_map(&map_q, d_qb, nq, kp, kTileM, fp16) || !make_bf16_map(&map_x, d_xb, n, kp, pair ? kTileN / 2 : kTileN, fp16))
+  if (!make_bf16_map(&map_q, d_qb, nq, kp, kTileM, fp16) || !make_bf16_map(&map_x, d_xb, n, kp, pair ? tile_n / 2 : tile_n, fp16))
     return bail(fail(TURDB_ERR_CUDA, "cuTensorMapEncodeTiled failed"));
 
   // Slice growth g: with the threshold frozen at the kprime-th best of the m rows seen so far, the next (g - 1) m rows bring
@@ -398,11 +410,11 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
   uint32_t growth = 3, diag = 0;
   if (const char* ev = getenv("TURDB_EXACT_GROWTH")) growth = (uint32_t)std::max(2, atoi(ev));
   if (const char* ev = getenv("TURDB_EXACT_DIAG")) diag = (uint32_t)atoi(ev);
-  const uint32_t n_tiles = (uint32_t)((n + kTileN - 1) / kTileN);
+  const uint32_t n_tiles = (uint32_t)((n + tile_n - 1) / tile_n);
   const uint32_t q_rows = pair ? 2 * kTileM : kTileM;  // queries per work item
   const uint32_t n_qblocks = (nq + q_rows - 1) / q_rows;
   // first slice: every column becomes a candidate (threshold -inf), so it must fit the buffer
-  uint32_t lo = 0, span = std::max(1u, std::min(first_rows, cap / 2) / kTileN);
+  uint32_t lo = 0, span = std::max(1u, std::min(first_rows, cap / 2) / tile_n);
   while (lo < n_tiles) {
     const uint32_t hi = std::min(n_tiles, lo + span);
     ExactArgs a{};
@@ -417,7 +429,7 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
     const uint32_t tiles = hi - lo;
     // tiles per work item: the resident query block is reloaded once per item (a ~1.5 us bubble), so short-K tiles get
     // longer items; never fewer than ~4 items per worker and pass
-    const uint32_t tpi_cap = 16u * std::max(1u, 6u / k_chunks);
+    const uint32_t tpi_cap = 16u * std::max(1u, 6u / k_chunks) * (256u / tile_n);
     uint32_t tpi = (uint32_t)std::min<uint64_t>(tpi_cap, std::max<uint64_t>(1, ((uint64_t)tiles * n_qblocks) / (4ull * n_workers)));
     a.tiles_per_item = tpi;
     a.n_qblocks = n_qblocks;
@@ -433,11 +445,13 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
     a.dense = lo == 0 ? 1u : 0u;
     const uint32_t grid = std::min<uint32_t>(a.n_items, n_workers) * (pair ? 2u : 1u);
     if (pair) {  // __cluster_dims__(2, 1, 1) on the kernel: the grid is a multiple of 2
-      if (stream_a) exact_gemm_filter_pair_kernel<true><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
-      else exact_gemm_filter_pair_kernel<false><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
+      if (stream_a) exact_gemm_filter_pair_kernel<true, 256><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
+      else if (tile_n == 128) exact_gemm_filter_pair_kernel<false, 128><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
+      else exact_gemm_filter_pair_kernel<false, 256><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
     } else {
-      if (stream_a) exact_gemm_filter_kernel<true><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
-      else exact_gemm_filter_kernel<false><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
+      if (stream_a) exact_gemm_filter_kernel<true, 256><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
+      else if (tile_n == 128) exact_gemm_filter_kernel<false, 128><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
+      else exact_gemm_filter_kernel<false, 256><<<grid, kExactThreads, gemm_smem, stream>>>(map_q, map_x, a);
     }
     exact_threshold_kernel<<<(nq + kThreshWarps - 1) / kThreshWarps, 32 * kThreshWarps, 0, stream>>>(nq, kprime, cap, d_cnt, d_cid, d_ckey, d_th, d_slack, d_kept, d_qflags,
                                                          d_arch_cnt, d_arch_id, arch_cap);

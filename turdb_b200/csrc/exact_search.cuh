@@ -336,9 +336,9 @@ static_assert(kEpiCols == 32 || kEpiCols == 64 || kEpiCols == 128, "epilogue sli
 static_assert(kExactThreads <= 1024, "CTA size");
 
 // bytes of one B (vector) chunk a CTA stages: the whole tile's rows, or half of them in the two-CTA form
-__host__ __device__ constexpr uint32_t exact_b_chunk_bytes(bool pair) { return (pair ? kTileN / 2 : kTileN) * kChunkK * 2; }
-__host__ __device__ constexpr uint32_t exact_stage_bytes(bool stream_a, bool pair) {
-  return (stream_a ? kChunkBytes : 0u) + exact_b_chunk_bytes(pair);
+__host__ __device__ constexpr uint32_t exact_b_chunk_bytes(bool pair, uint32_t tile_n) { return (pair ? tile_n / 2 : tile_n) * kChunkK * 2; }
+__host__ __device__ constexpr uint32_t exact_stage_bytes(bool stream_a, bool pair, uint32_t tile_n) {
+  return (stream_a ? kChunkBytes : 0u) + exact_b_chunk_bytes(pair, tile_n);
 }
 // everything in dynamic shared memory except the pipeline stages (kernel and host compute the layout from this)
 __host__ __device__ constexpr uint32_t exact_fixed_smem(uint32_t k_chunks, bool stream_a) {
@@ -446,14 +446,24 @@ __device__ __noinline__ void exact_wq_flush(uint32_t* cand_cnt, uint32_t* cand_i
 
 // smem: [A: k_chunks x 16 KB (resident form)][stages: n_stages x ([A chunk] B chunk)]
 //       [warp queues: key | id | lane][barriers][tmem ptr]
-template <bool STREAM_A, bool PAIR>
+template <bool STREAM_A, bool PAIR, uint32_t TILE_N>
 __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q, const CUtensorMap* map_x, const ExactArgs& a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;   // CTA within the pair; rank 0 (the leader) issues the MMAs
   const uint32_t n_workers = PAIR ? gridDim.x >> 1 : gridDim.x, worker = PAIR ? blockIdx.x >> 1 : blockIdx.x;
-  constexpr uint32_t kBRows = PAIR ? kTileN / 2 : kTileN;          // vector rows this CTA stages per tile
-  constexpr uint32_t stage_bytes = exact_stage_bytes(STREAM_A, PAIR);  // [A chunk |] B chunk
+  // TILE_N = 256 (shipped): two 256-column accumulators, every epilogue warp on every tile.  TILE_N = 128 (measured
+  // alternative, TURDB_EXACT_TILE_N=128): FOUR 128-column accumulators and two alternating sets of eight epilogue warps (set
+  // s takes the tiles with sequence number = s mod 2), so that every accumulator hand-off (commit -> wake -> TMEM load ->
+  // arrive -> wake, ~0.9k cycles against ~1k cycles of MMAs per 256-column tile at K = 128) has three tiles of cover.
+  // Parity-green and slower at every short K tried (128-d L2 4.63 against 3.26 ms): twice the MMA instructions, commits and
+  // barrier round trips per score.
+  constexpr uint32_t kBufs = 512 / TILE_N;                          // accumulator buffers in TMEM
+  constexpr uint32_t kSets = TILE_N == 128 ? 2 : 1;                 // alternating sets of epilogue warps
+  static_assert(TILE_N == 128 || TILE_N == 256, "UMMA N");
+  static_assert((kEpiWarps / kSets) * kEpiCols == 4 * TILE_N, "a set's warps cover the tile: 4 lane quarters x TILE_N columns");
+  constexpr uint32_t kBRows = PAIR ? TILE_N / 2 : TILE_N;          // vector rows this CTA stages per tile
+  constexpr uint32_t stage_bytes = exact_stage_bytes(STREAM_A, PAIR, TILE_N);  // [A chunk |] B chunk
   constexpr uint32_t b_in_stage = STREAM_A ? kChunkBytes : 0;
   constexpr uint32_t kQRows = PAIR ? 2 * kTileM : kTileM;          // queries per work item
   uint8_t* sA = smem;
@@ -466,7 +476,7 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
   const uint32_t bar_a_full = smem_u32(bars + 0), bar_a_empty = smem_u32(bars + 1);
   const uint32_t bar_b_full = smem_u32(bars + 2), bar_b_empty = smem_u32(bars + 2 + kMaxStages);
-  const uint32_t bar_t_full = smem_u32(bars + 2 + 2 * kMaxStages), bar_t_empty = smem_u32(bars + 4 + 2 * kMaxStages);
+  const uint32_t bar_t_full = smem_u32(bars + 2 + 2 * kMaxStages), bar_t_empty = smem_u32(bars + 6 + 2 * kMaxStages);  // 4 + 4 slots
 
   if (threadIdx.x == 0) {
     mbar_init(bar_a_full, 1);
@@ -475,19 +485,19 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
       mbar_init(bar_b_full + 8 * s, 1);
       mbar_init(bar_b_empty + 8 * s, 1);
     }
-    for (uint32_t s = 0; s < 2; ++s) {
+    for (uint32_t s = 0; s < kBufs; ++s) {
       mbar_init(bar_t_full + 8 * s, 1);
-      mbar_init(bar_t_empty + 8 * s, (PAIR ? 2 : 1) * kEpiWarps);  // one arrive per epilogue warp (of both CTAs)
+      mbar_init(bar_t_empty + 8 * s, (PAIR ? 2 : 1) * (kEpiWarps / kSets));  // one arrive per warp of the tile's set (of both CTAs)
     }
     mbar_fence_init();
   }
-  if (warp == 1) {  // 2 accumulator buffers x kTileN FP32 columns (in each CTA of a pair)
+  if (warp == 1) {  // kBufs accumulator buffers x TILE_N FP32 columns = all 512 (in each CTA of a pair)
     if (PAIR) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2u * kTileN)
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
                    : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2u * kTileN)
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
                    : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -532,7 +542,7 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
           a_phase ^= 1;
         }
         for (uint32_t t = t0; t < t1; ++t) {
-          const int32_t x_row0 = (int32_t)(t * kTileN + rank * kBRows);
+          const int32_t x_row0 = (int32_t)(t * TILE_N + rank * kBRows);
           for (uint32_t kc = 0; kc < a.k_chunks; ++kc) {
             long long c1 = a.dbg ? clock64() : 0;
             mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
@@ -573,7 +583,7 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
     if (rank == 0) {
       // instruction descriptor: D=F32, A=B=F16/BF16, both K-major, N, M (cute::UMMA::InstrDescriptor); M = 256 across a pair
       const uint32_t fmt = a.fp16 ? 0u : 1u;  // a_format (bits 7-9) / b_format (bits 10-12): 0 = F16, 1 = BF16
-      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((kTileN >> 3) << 17) | (((PAIR ? 2 * kTileM : kTileM) >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((TILE_N >> 3) << 17) | (((PAIR ? 2 * kTileM : kTileM) >> 4) << 24);
       uint32_t stage = 0, phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
       for (uint32_t item = worker; item < a.n_items; item += n_workers) {
         const uint32_t t0 = a.tile_lo + (item / a.n_qblocks) * a.tiles_per_item;
@@ -590,7 +600,7 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
           mbar_wait(bar_t_empty + 8 * acc, acc_phase ^ 1);  // the epilogue (of both CTAs of a pair) has drained this accumulator
           if (a.dbg && lane == 0) atomicAdd(a.dbg + 3, (unsigned long long)(clock64() - c3));
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * kTileN;
+          const uint32_t d_tmem = tmem_base + acc * TILE_N;
           for (uint32_t kc = 0; kc < a.k_chunks; ++kc) {
             long long c4 = a.dbg ? clock64() : 0;
             mbar_wait(bar_b_full + 8 * stage, phase);
@@ -620,7 +630,7 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
             if (a.dbg) atomicAdd(a.dbg + 5, 1ull);  // tiles
           }
           __syncwarp();
-          if (++acc == 2) {
+          if (++acc == kBufs) {
             acc = 0;
             acc_phase ^= 1;
           }
@@ -640,17 +650,19 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
     // per tile — the same work in another order: 128-d 3.32 against 3.19 ms, 768-d 10.36 against 10.20 ms.  At short K the
     // tensor pipe idles on the accumulator hand-offs — commit -> wake -> TMEM load -> arrive -> wake, ~0.9k cycles per
     // 1.05k-cycle tile at 128-d (ncu: pipe 53 % active, the issuer 29 % of its time on bar_t_empty) — which two
-    // 256-column buffers cannot hide; four 128-column buffers could.)
+    // 256-column buffers cannot hide.  Four 128-column buffers (TILE_N = 128 below) hide them and still lose: 4.63 against
+    // 3.26 ms at 128-d L2.)
     const uint32_t ew = warp - 2;                    // index among the epilogue warps
     const uint32_t quarter = warp & 3;               // TMEM lane quarter this warp may read (= warp id % 4)
-    const uint32_t cslice = (ew >> 2) * kEpiCols;    // first tile column of this warp's slice
+    const uint32_t set = kSets == 2 ? ew / (kEpiWarps / 2) : 0u;              // which tiles this warp takes (sequence % kSets)
+    const uint32_t cslice = ((ew % (kEpiWarps / kSets)) >> 2) * kEpiCols;     // first tile column of this warp's slice
     const uint32_t et = threadIdx.x - 64;            // index among the epilogue threads
     const uint32_t lt_mask = (1u << lane) - 1u;
     float* my_key = wq_key + ew * kWq;
     uint32_t* my_id = wq_id + ew * kWq;
     uint32_t* my_lane = wq_lane + ew * kWq;
     const uint32_t t_empty_dst = PAIR ? mapa_u32(bar_t_empty, 0) : bar_t_empty;  // the leader's barrier
-    uint32_t acc = 0, acc_phase = 0;
+    uint32_t seq = 0;                                // tiles this CTA has started, all items: tile seq uses buffer seq % kBufs
     uint32_t wq_n = 0;                               // entries in the warp's queue (warp-uniform)
     uint32_t q_base = 0;                             // query of queue entry i = q_base + my_lane[i]
     auto flush = [&]() {                             // whole warp: entry i is written out by lane i (and i + 32)
@@ -664,14 +676,16 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
       q_base = qb * kQRows + rank * kTileM + quarter * 32;
       const uint32_t q = q_base + lane;
       const float tau = q < a.nq ? a.thresh[q] : INFINITY;  // rows past the batch never keep anything
-      for (uint32_t t = t0; t < t1; ++t) {
+      for (uint32_t t = t0; t < t1; ++t, ++seq) {
+        if (kSets == 2 && (seq & 1u) != set) continue;  // the other set's tile
+        const uint32_t acc = seq % kBufs, acc_phase = (seq / kBufs) & 1u;
         long long c6 = (a.dbg && et == 0) ? clock64() : 0;
         mbar_wait(bar_t_full + 8 * acc, acc_phase);
         long long c7 = (a.dbg && et == 0) ? clock64() : 0;
         tc_fence_after();
-        const uint32_t n_valid = min(kTileN, a.n_vec - t * kTileN);  // columns past the corpus are zero rows
+        const uint32_t n_valid = min(TILE_N, a.n_vec - t * TILE_N);  // columns past the corpus are zero rows
         uint32_t v[kEpiCols / 32][32];
-        const uint32_t tcol = tmem_base + ((quarter * 32) << 16) + acc * kTileN + cslice;
+        const uint32_t tcol = tmem_base + ((quarter * 32) << 16) + acc * TILE_N + cslice;
         if (a.diag != 1) {
 #pragma unroll
           for (uint32_t cb = 0; cb < kEpiCols / 32; ++cb) tmem_ld_32x32b_x32_nowait(tcol + cb * 32, v[cb]);
@@ -688,17 +702,13 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
           if (PAIR) mbar_arrive_cluster(t_empty_dst + 8 * acc);
           else mbar_arrive(t_empty_dst + 8 * acc);
         }
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
-        }
         if (a.diag == 2) continue;
 #pragma unroll
         for (uint32_t cb = 0; cb < kEpiCols / 32; ++cb) {
           if (a.dense) {  // first slice: no test, no queue — 128-bit stores of the thread's 32 consecutive columns
             if (q < a.nq) {
               const uint32_t c0 = cslice + cb * 32;  // tile column of v[cb][0]
-              const size_t slot = (size_t)q * a.cap + (size_t)(t - a.tile_lo) * kTileN + c0;
+              const size_t slot = (size_t)q * a.cap + (size_t)(t - a.tile_lo) * TILE_N + c0;
               float4* kd = reinterpret_cast<float4*>(a.cand_key + slot);
               uint4* idd = reinterpret_cast<uint4*>(a.cand_id + slot);
 #pragma unroll
@@ -714,7 +724,7 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
                 kv.z = kv.z == kv.z ? kv.z : -INFINITY;
                 kv.w = kv.w == kv.w ? kv.w : -INFINITY;
                 kd[j >> 2] = kv;
-                const uint32_t id0 = t * kTileN + c0 + j;
+                const uint32_t id0 = t * TILE_N + c0 + j;
                 idd[j >> 2] = make_uint4(id0, id0 + 1, id0 + 2, id0 + 3);
               }
             }
@@ -739,7 +749,7 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
                     if (hit) {
                       const uint32_t slot = wq_n + __popc(b & lt_mask);
                       my_key[slot] = key;
-                      my_id[slot] = t * kTileN + col;
+                      my_id[slot] = t * TILE_N + col;
                       my_lane[slot] = lane;
                     }
                     wq_n += __popc(b);
@@ -766,24 +776,24 @@ __device__ __forceinline__ void exact_gemm_filter_body(const CUtensorMap* map_q,
   else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * kTileN) : "memory");
-    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * kTileN) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
-template <bool STREAM_A>
+template <bool STREAM_A, uint32_t TILE_N>
 __global__ void __launch_bounds__(kExactThreads, 1)
 exact_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                          const ExactArgs a) {
-  exact_gemm_filter_body<STREAM_A, false>(&map_q, &map_x, a);
+  exact_gemm_filter_body<STREAM_A, false, TILE_N>(&map_q, &map_x, a);
 }
 
 // the two-CTA form: clusters of 2 CTAs (one TPC), grid = 2 x the number of pairs
-template <bool STREAM_A>
+template <bool STREAM_A, uint32_t TILE_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kExactThreads, 1)
 exact_gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                               const ExactArgs a) {
-  exact_gemm_filter_body<STREAM_A, true>(&map_q, &map_x, a);
+  exact_gemm_filter_body<STREAM_A, true, TILE_N>(&map_q, &map_x, a);
 }
 
 // ------------------------------------------------------------------------------------------------
