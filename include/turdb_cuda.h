@@ -220,7 +220,8 @@ int32_t turdb_cuda_index_gather_probe(turdb_cuda_index* idx, uint32_t ctas_per_s
  * Result = top-k by (FP32 distance, node id).  Distances follow the HNSW metric contract above (squared L2 /
  * 1-cos / -dot), NOT the SQL sqrt form.  k <= TURDB_EXACT_MAX_K; rerank_factor 0 = 1 (the band already certifies
  * k' = k; a larger factor only widens the working set — 6.5 ms against 7.4 ms per 10k queries x 1M x 384 at factor 4);
- * k*rerank_factor is clamped to 2048.  Absent vectors (+inf rows) evaluate to +inf.
+ * k*rerank_factor is clamped to 2048.  dim <= 2048 (L2: <= 2045, its 16-bit copy carries three extra columns).  Absent
+ * vectors (+inf rows) evaluate to +inf.
  * The filter kernel has a one-CTA (tcgen05 cta_group::1) and a two-CTA (cta_group::2, clusters of 2) form; the library
  * picks by dimension (two-CTA above 64 dims, one-CTA when no cluster fits).  Results do not depend on the form.
  * Measurement switches (environment, read per call; never needed in production): TURDB_EXACT_PAIR=0/1 forces a form,

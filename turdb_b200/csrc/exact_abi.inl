@@ -230,7 +230,8 @@ static int32_t exact_filter_run(turdb_cuda_index* idx, const float* d_queries, u
   const int copy = metric == kCosine ? 1 : (metric == kL2 ? 2 : 0);
   const uint32_t kp = (dim + (copy == 2 ? 3 : 0) + kChunkK - 1) / kChunkK * kChunkK;
   const uint32_t k_chunks = kp / kChunkK;
-  if (k_chunks > 32) return fail(TURDB_ERR_UNSUPPORTED, "the exact path supports dim <= 2048 (dim %u)", dim);
+  if (k_chunks > 32)
+    return fail(TURDB_ERR_UNSUPPORTED, "the exact path supports dim <= %u for this metric (dim %u)", copy == 2 ? 2045u : 2048u, dim);
   // up to 512 dims the query block (128 x K BF16) stays resident in shared memory; above, its K chunks are streamed
   // with the vector tile's (twice the TMA traffic per tile, but any K fits)
   const uint32_t stream_a = k_chunks > 8 ? 1u : 0u;
